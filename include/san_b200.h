@@ -1,0 +1,148 @@
+/* san_b200.h — C ABI of libsan_b200.so, the B200 (sm_100a) kernels behind the
+ * VarNet + spatial-alignment hot path of woxuankai/SpatialAlignmentNetwork.
+ *
+ * The reference has no FFI: its arithmetic is PyTorch library calls made from
+ * flat Python modules.  Each entry point below names the reference call site
+ * (file:line under the reference repo) whose arithmetic it replaces; the
+ * Python modules in spatialalignmentnetwork_b200/ bind them with ctypes and
+ * re-expose the reference's module API (INTEGRATION.md shows the stub).
+ *
+ * Conventions
+ *  - every pointer is a DEVICE pointer into caller-owned, contiguous memory
+ *    (complex64 = interleaved float pairs; "planar" = [.., 2, H, W] float with
+ *    the real plane first); the library allocates nothing per call except
+ *    cached twiddle tables / repacked weights, never synchronises, and launches
+ *    on `stream` (a cudaStream_t passed as void*);
+ *  - return 0 on success, <0 on error (SAN_ERR_*); san_last_error() returns the
+ *    message of the last failure on the calling thread;
+ *  - `scratch` arguments are small caller-owned device buffers (size stated).
+ */
+#ifndef SAN_B200_H_
+#define SAN_B200_H_
+#include <stddef.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+const char* san_last_error(void);
+int san_version(void);
+/* number of kernels launched by this library since load (bench.py's gpu_launches) */
+long long san_launch_count(void);
+
+/* ---- FFT / data consistency  (signal_utils.py:4-12, varnet.py:395-402,486,508-530) ---- */
+size_t san_fft_workspace_bytes(int B, int H, int W);
+/* out = (i)fft2(in) with norm='ortho' over the last two dims of [B,H,W].
+ * in/out may be complex64 or planar ([B,2,H,W]); colmask_in multiplies column w of a
+ * complex64 input by colmask_in[w] before the transform (ACS mask, varnet.py:395-402),
+ * colmask_out multiplies the complex64 output (its adjoint).  tmp: B*H*W complex64
+ * (may alias `out` when out is complex64). */
+int san_fft2(const void* in, int in_planar, const float* colmask_in, void* out, int out_planar,
+             const float* colmask_out, void* tmp, int B, int H, int W, int inverse, void* stream);
+/* sens_reduce, varnet.py:511-512: x[n] = sign * sum_c ifft2(k[n,c]) * conj(S[n,c]); x planar
+ * [N,2,H,W]; u_out (optional, complex64 [N,C,H,W]) receives sign*ifft2(k) for the backward. */
+int san_fft_reduce(const void* k, const void* sens, float* x_planar, void* u_out, void* tmp, int N, int C,
+                   int H, int W, int inverse, float sign, void* stream);
+/* sens_expand + soft data consistency, varnet.py:508-509,525-530:
+ *   out = k - where(mask[w], k - k0, 0) * dc_weight - fft2(x * S)
+ * x planar [N,2,H,W]; mask = W bytes (bool); dc_weight = 1 float on device.
+ * With k == NULL: out = fft2(x * S) (the adjoint of sens_reduce). */
+int san_fft_expand_dc(const float* x_planar, const void* sens, const void* k, const void* k0,
+                      const unsigned char* mask, const float* dc_weight, void* out, void* tmp, int N, int C,
+                      int H, int W, int inverse, void* stream);
+/* rss(ifft2(k)), varnet.py:486: out [N,H,W] float; u_out optional complex64 copy of ifft2(k). */
+int san_fft_rss(const void* k, float* out, void* u_out, void* tmp, int N, int C, int H, int W, int inverse,
+                void* stream);
+/* out[b,p] = sign * u[b,p] * conj(planar[n = b / C, p])  (sensitivity-map gradients) */
+int san_cmul_conj_planar(const void* u, const float* planar, void* out, int N, int C, long long P, float sign,
+                         void* stream);
+/* backward of the soft-DC term: dk = G - where(mask, G, 0)*w (dk may be NULL);
+ * d_dc_weight = -sum Re(conj(where(mask, k-k0, 0)) * G).  scratch: 1 double. */
+int san_dc_bwd(const void* G, const void* k, const void* k0, const unsigned char* mask, const float* dc_weight,
+               void* dk, float* d_dc_weight, double* scratch, long long rows, int W, void* stream);
+/* signal_utils.rss (signal_utils.py:24-26) over dim 1 of [N,C,P] (complex64 or float) */
+int san_rss_fwd(const float* x, float* out, int N, int C, long long P, int is_complex, void* stream);
+int san_rss_bwd(const float* g, const float* x, const float* r, float* dx, int N, int C, long long P,
+                int is_complex, void* stream);
+/* S = s / (rss_c(s) + eps), varnet.py:419; s planar [N*C,2,P] -> S complex64 [N,C,P] */
+int san_sens_normalize_fwd(const float* s_planar, void* S, int N, int C, long long P, float eps, void* stream);
+int san_sens_normalize_bwd(const void* G, const float* s_planar, float* ds_planar, int N, int C, long long P,
+                           float eps, void* stream);
+/* out = a*x + b*y (y may be NULL): residual adds (unet.py:15-24) and gradient accumulation */
+int san_axpby(const float* x, const float* y, float* out, float a, float b, long long n, void* stream);
+
+/* ---- convolutions (varnet.py:75-80,139-146,176-179; unet.py:119-140; cross.py:15) ---- */
+/* repack OIHW weights for the kernels: dgrad=0 -> [Cin][K*K][Cout]; dgrad=1 -> flipped,
+ * [Cout][K*K][Cin] (so the data-gradient is the same forward kernel run on dY). */
+int san_conv_pack_weights(const float* w, float* packed, int Cout, int Cin, int K, int dgrad, void* stream);
+/* y = conv2d(x, w) + bias, stride 1, padding K/2, K in {1,3}; NCHW fp32.
+ * x_bs / y_bs: batch strides in floats (0 = dense), so outputs can land inside a
+ * wider concat buffer. */
+int san_conv2d_fwd(const float* x, const float* w_packed, const float* bias, float* y, int N, int Cin, int H, int W,
+                   int Cout, int K, long long x_bs, long long y_bs, void* stream);
+/* dw[Cout,Cin,K,K] (OIHW) and optional dbias[Cout] */
+int san_conv2d_wgrad(const float* x, const float* dy, float* dw, float* dbias, int N, int Cin, int H, int W, int Cout,
+                     int K, long long x_bs, long long dy_bs, void* stream);
+/* x [N,Co*4,H,W] (channel = co*4 + a*2 + b) <-> y [N,Co,2H,2W]: ConvTranspose2d(k=2,s=2) =
+ * 1x1 conv to 4*Co channels + depth_to_space */
+int san_depth_to_space2(const float* x, float* y, int N, int Co, int H, int W, void* stream);
+int san_space_to_depth2(const float* y, float* x, int N, int Co, int H, int W, void* stream);
+
+/* ---- normalisation / activation / resampling (varnet.py:98,139-146,235,257-273; unet.py:119-140) ---- */
+int san_plane_stats(const float* x, float* mean, float* m2, int planes, int P, void* stream);
+int san_in_finalize_fwd(const float* mean, const float* m2, float* a, float* b, int planes, int P, float eps,
+                        void* stream);
+int san_bn_finalize_fwd(const float* mean, const float* m2, const float* gamma, const float* beta,
+                        float* running_mean, float* running_var, float* a, float* b, float* sa, float* sb, int N,
+                        int C, int P, float eps, float momentum, int training, void* stream);
+/* out = leaky_relu(a[plane]*y + b[plane], slope) */
+int san_affine_act_fwd(const float* y, const float* a, const float* b, float slope, float* out, int planes, int P,
+                       void* stream);
+/* s1 = sum g', s2 = sum g'*(sa*y+sb) per plane, g' = g * lrelu'(a*y+b); sa/sb NULL = (1, 0) */
+int san_act_bwd_reduce(const float* g, const float* y, const float* a, const float* b, const float* sa,
+                       const float* sb, float slope, float* s1, float* s2, int planes, int P, void* stream);
+int san_in_finalize_bwd(const float* s1, const float* s2, const float* a, const float* b, float* p, float* q,
+                        float* r, int planes, int P, void* stream);
+int san_bn_finalize_bwd(const float* s1, const float* s2, const float* gamma, const float* sa, const float* sb,
+                        float* p, float* q, float* r, float* dgamma, float* dbeta, int N, int C, int P, int training,
+                        void* stream);
+/* dy = p*g' + q*y + r (q, r may be NULL) */
+int san_act_bwd_apply(const float* g, const float* y, const float* a, const float* b, float slope, const float* p,
+                      const float* q, const float* r, float* dy, int planes, int P, void* stream);
+/* y = scale * (2x2 block sum of x): avg_pool2d (scale .25) and the adjoint of nearest up-sampling (scale 1) */
+int san_pool2(const float* x, float* y, long long planes, int H, int W, float scale, void* stream);
+/* y[2h+a,2w+b] = scale * x[h,w]: nearest x2 (scale 1) and the adjoint of avg_pool2d (scale .25) */
+int san_up2(const float* x, float* y, long long planes, int H, int W, float scale, void* stream);
+
+/* ---- spatial alignment (cross.py:23-38, model.py:21-28) ---- */
+int san_grid_from_offset(const float* x_nchw, float* grid, int N, int H, int W, void* stream);
+int san_grid_to_nchw(const float* g_nhwc, float* dx_nchw, int N, int H, int W, void* stream);
+int san_warp_fwd(const float* img, const float* grid, float* out, int N, int C, int H, int W, int Ho, int Wo,
+                 void* stream);
+int san_warp_bwd(const float* gout, const float* img, const float* grid, float* dimg, float* dgrid, int N, int C,
+                 int H, int W, int Ho, int Wo, void* stream);
+/* s[n,h,w,c] at n*sn + h*sh + w*sw + c*sc (floats), c in {0,1}.  scratch: 2 doubles. */
+int san_grad_loss_fwd(const float* s, long long sn, long long sh, long long sw, long long sc, int N, int H, int W,
+                      float* out, double* scratch, void* stream);
+int san_grad_loss_bwd(const float* s, long long sn, long long sh, long long sw, long long sc, int N, int H, int W,
+                      const float* gout, float* ds, void* stream);
+
+/* ---- losses (ssimloss.py:11-40, lnccloss.py:7-56, miloss.py:6-57) ---- */
+/* images [N,1,H,W] float; out = 1 scalar on device; scratch: 1 double */
+int san_ssim_loss_fwd(const float* X, const float* Y, int N, int H, int W, float* out, double* scratch, void* stream);
+int san_ssim_loss_bwd(const float* X, const float* Y, const float* gout, int N, int H, int W, float* dX, float* dY,
+                      void* stream);
+int san_lncc_loss_fwd(const float* I, const float* J, int N, int H, int W, float* out, double* scratch, void* stream);
+int san_lncc_loss_bwd(const float* I, const float* J, const float* gout, int N, int H, int W, float* dI, float* dJ,
+                      void* stream);
+/* Parzen soft histograms: joint[N,64,64] = p_I p_J^T, mI/mJ[N,64] = row sums (miloss.py:26-42) */
+int san_mi_hist_fwd(const float* I, const float* J, float* joint, float* mI, float* mJ, int N, int P, int bins,
+                    float sigma, float minv, float maxv, void* stream);
+int san_mi_hist_bwd(const float* I, const float* J, const float* gjoint, const float* gmI, const float* gmJ, float* dI,
+                    float* dJ, int N, int P, int bins, float sigma, float minv, float maxv, void* stream);
+/* single-channel KxK correlation, zero padding K/2 (gaussian_smooth, miloss.py:13-24) */
+int san_filter2d(const float* x, const float* w, float* y, long long planes, int H, int W, int K, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SAN_B200_H_ */

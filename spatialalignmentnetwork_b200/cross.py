@@ -1,0 +1,61 @@
+"""Drop-in for the reference ``cross.py`` ``SpatialTransformer`` (cross.py:9-38): the
+alignment U-Net estimates a dense displacement field, added to the identity sampling grid;
+``warp`` is bilinear ``grid_sample`` (zeros padding, align_corners=False).  All arithmetic
+runs on the san_b200 kernels."""
+import torch
+
+from . import ops
+from .unet import UNet, Conv2dB200
+
+
+class _LeakyReLU(torch.nn.LeakyReLU):
+    """Stand-alone LeakyReLU (cross.py:14) through the library's per-plane affine+activation kernel."""
+
+    def forward(self, x):
+        return _LReLUFn.apply(x, self.negative_slope)
+
+
+class _LReLUFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, slope):
+        x = x.contiguous()
+        N, C, H, W = x.shape
+        ab = torch.zeros(2, N * C, dtype=torch.float32, device=x.device)
+        ab[0].fill_(1.0)
+        out = torch.empty_like(x)
+        ops.call("affine_act_fwd", x, ab[0], ab[1], slope, out, N * C, H * W)
+        ctx.save_for_backward(x, ab)
+        ctx.slope = slope
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        x, ab = ctx.saved_tensors
+        N, C, H, W = x.shape
+        dx = torch.empty_like(x)
+        ops.call("act_bwd_apply", g.contiguous(), x, ab[0], ab[1], ctx.slope, ab[0], None, None, dx, N * C, H * W)
+        return dx, None
+
+
+class SpatialTransformer(torch.nn.Module):
+    def __init__(self, channels=1):
+        super().__init__()
+        self.net = torch.nn.Sequential(
+            UNet(2 * channels, 32, (32, 64, 64, 64, 64)),
+            _LeakyReLU(inplace=True),
+            Conv2dB200(32, 2, kernel_size=3, padding=1))
+        # (the reference's "param / 100" loop, cross.py:16-18, rebinds a local: a no-op)
+        torch.nn.init.zeros_(self.net[-1].weight)
+        torch.nn.init.zeros_(self.net[-1].bias)
+
+    def forward(self, moving, fixed, features=None):
+        out = self.net(torch.cat([moving, fixed], 1))          # [N,2,H,W]
+        offset = out.permute(0, 2, 3, 1)                        # view, (x, y) last
+        grid = ops.GridFromOffset.apply(out)                    # identity + offset, [N,H,W,2]
+        return offset, grid
+
+    def warp(self, img, grid, interp=False):
+        warped = ops.Warp.apply(img.float(), grid.float())
+        if interp and (warped.shape != img.shape):
+            warped = torch.nn.functional.interpolate(warped, size=img.shape[2:])
+        return warped

@@ -1,0 +1,374 @@
+// Per-plane normalisation / activation / resampling kernels for the U-Nets:
+// InstanceNorm2d + LeakyReLU (reference varnet.py:139-146,176-182,235), BatchNorm2d +
+// LeakyReLU (reference unet.py:119-140), the per-sample group norm of NormUnet
+// (varnet.py:257-273), avg_pool2d(2) (varnet.py:98, unet.py:137), nearest x2
+// up-sampling (unet.py:130) and the pixel shuffles used by the 2x2 stride-2
+// transposed convolution (varnet.py:176-179).
+//
+// A "plane" is one (n, c) image of P = H*W contiguous floats.  Normalisation is
+// expressed as  out = lrelu(a[plane] * y + b[plane])  with the coefficients
+// produced by tiny finalize kernels from two-pass (centred) plane statistics, so a
+// conv output is read twice (stats; L2-resident second pass) and written once.
+#include "san_common.cuh"
+#include "../../include/san_b200.h"
+
+namespace {
+
+// ---- statistics -------------------------------------------------------------
+__global__ void __launch_bounds__(256) plane_stats_kernel(const float* __restrict__ x, float* __restrict__ mean,
+                                                          float* __restrict__ m2, int P) {
+  __shared__ double red[32];
+  const float* p = x + (long long)blockIdx.x * P;
+  float s = 0.f;
+  if ((P & 3) == 0) {
+    const float4* p4 = (const float4*)p;
+    for (int i = threadIdx.x; i < P / 4; i += blockDim.x) {
+      float4 v = p4[i];
+      s += (v.x + v.y) + (v.z + v.w);
+    }
+  } else {
+    for (int i = threadIdx.x; i < P; i += blockDim.x) s += p[i];
+  }
+  const double tot = block_sum_d((double)s, red);
+  const float mu = (float)(tot / P);
+  float q = 0.f;
+  if ((P & 3) == 0) {
+    const float4* p4 = (const float4*)p;
+    for (int i = threadIdx.x; i < P / 4; i += blockDim.x) {
+      float4 v = p4[i];
+      const float a = v.x - mu, b = v.y - mu, c = v.z - mu, d = v.w - mu;
+      q += (a * a + b * b) + (c * c + d * d);
+    }
+  } else {
+    for (int i = threadIdx.x; i < P; i += blockDim.x) {
+      const float a = p[i] - mu;
+      q += a * a;
+    }
+  }
+  const double tq = block_sum_d((double)q, red);
+  if (threadIdx.x == 0) {
+    mean[blockIdx.x] = mu;
+    m2[blockIdx.x] = (float)tq;
+  }
+}
+
+__global__ void in_finalize_fwd_kernel(const float* __restrict__ mean, const float* __restrict__ m2,
+                                       float* __restrict__ a, float* __restrict__ b, int planes, int P, float eps) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= planes) return;
+  const float var = m2[i] / (float)P;
+  const float rstd = 1.f / sqrtf(var + eps);
+  a[i] = rstd;
+  b[i] = -mean[i] * rstd;
+}
+
+// one thread per channel
+__global__ void bn_finalize_fwd_kernel(const float* __restrict__ mean, const float* __restrict__ m2,
+                                       const float* __restrict__ gamma, const float* __restrict__ beta,
+                                       float* running_mean, float* running_var, float* __restrict__ a,
+                                       float* __restrict__ b, float* __restrict__ sa, float* __restrict__ sb, int N,
+                                       int C, int P, float eps, float momentum, int training) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  double mu, rstd;
+  if (training) {
+    double sm = 0.0;
+    for (int n = 0; n < N; ++n) sm += (double)mean[n * C + c];
+    mu = sm / N;
+    double M2 = 0.0;
+    for (int n = 0; n < N; ++n) {
+      const double d = (double)mean[n * C + c] - mu;
+      M2 += (double)m2[n * C + c] + d * d * P;
+    }
+    const double cnt = (double)N * P;
+    const double var = M2 / cnt;
+    rstd = 1.0 / sqrt(var + (double)eps);
+    if (running_mean) {
+      running_mean[c] = (float)((1.0 - momentum) * running_mean[c] + momentum * mu);
+      const double unb = cnt > 1 ? M2 / (cnt - 1.0) : var;
+      running_var[c] = (float)((1.0 - momentum) * running_var[c] + momentum * unb);
+    }
+  } else {
+    mu = running_mean[c];
+    rstd = 1.0 / sqrt((double)running_var[c] + (double)eps);
+  }
+  const float fa = (float)(gamma[c] * rstd);
+  const float fb = (float)(beta[c] - mu * gamma[c] * rstd);
+  const float fsa = (float)rstd, fsb = (float)(-mu * rstd);
+  for (int n = 0; n < N; ++n) {
+    a[n * C + c] = fa; b[n * C + c] = fb; sa[n * C + c] = fsa; sb[n * C + c] = fsb;
+  }
+}
+
+// ---- forward apply ------------------------------------------------------------
+__device__ __forceinline__ float lrelu(float v, float slope) { return v > 0.f ? v : v * slope; }
+
+// grid (planes, chunks)
+__global__ void __launch_bounds__(256) affine_act_fwd_kernel(const float* __restrict__ y, const float* __restrict__ a,
+                                                             const float* __restrict__ b, float slope,
+                                                             float* __restrict__ out, int P) {
+  const long long base = (long long)blockIdx.x * P;
+  const float ca = a[blockIdx.x], cb = b[blockIdx.x];
+  if ((P & 3) == 0) {
+    const float4* y4 = (const float4*)(y + base);
+    float4* o4 = (float4*)(out + base);
+    for (int i = blockIdx.y * blockDim.x + threadIdx.x; i < P / 4; i += gridDim.y * blockDim.x) {
+      float4 v = y4[i];
+      v.x = lrelu(fmaf(ca, v.x, cb), slope); v.y = lrelu(fmaf(ca, v.y, cb), slope);
+      v.z = lrelu(fmaf(ca, v.z, cb), slope); v.w = lrelu(fmaf(ca, v.w, cb), slope);
+      o4[i] = v;
+    }
+  } else {
+    for (int i = blockIdx.y * blockDim.x + threadIdx.x; i < P; i += gridDim.y * blockDim.x)
+      out[base + i] = lrelu(fmaf(ca, y[base + i], cb), slope);
+  }
+}
+
+// ---- backward -------------------------------------------------------------------
+// s1 = sum g', s2 = sum g' * (sa*y + sb), g' = g * lrelu'(a*y + b); one block per plane
+__global__ void __launch_bounds__(256) act_bwd_reduce_kernel(const float* __restrict__ g, const float* __restrict__ y,
+                                                             const float* __restrict__ a, const float* __restrict__ b,
+                                                             const float* __restrict__ sa, const float* __restrict__ sb,
+                                                             float slope, float* __restrict__ s1, float* __restrict__ s2,
+                                                             int P) {
+  __shared__ double red[32];
+  const long long base = (long long)blockIdx.x * P;
+  const float ca = a[blockIdx.x], cb = b[blockIdx.x];
+  const float csa = sa ? sa[blockIdx.x] : 1.f, csb = sb ? sb[blockIdx.x] : 0.f;
+  float t1 = 0.f, t2 = 0.f;
+  for (int i = threadIdx.x; i < P; i += blockDim.x) {
+    const float yy = y[base + i];
+    float gg = g[base + i];
+    if (fmaf(ca, yy, cb) <= 0.f) gg *= slope;
+    t1 += gg;
+    t2 += gg * fmaf(csa, yy, csb);
+  }
+  const double r1 = block_sum_d((double)t1, red);
+  const double r2 = block_sum_d((double)t2, red);
+  if (threadIdx.x == 0) { s1[blockIdx.x] = (float)r1; s2[blockIdx.x] = (float)r2; }
+}
+
+__global__ void in_finalize_bwd_kernel(const float* __restrict__ s1, const float* __restrict__ s2,
+                                       const float* __restrict__ a, const float* __restrict__ b, float* __restrict__ p,
+                                       float* __restrict__ q, float* __restrict__ r, int planes, int P) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= planes) return;
+  const double A = a[i], B = b[i], M = P;
+  const double qx = -A * (double)s2[i] / M;  // multiplies xhat = A*y + B
+  p[i] = (float)A;
+  q[i] = (float)(qx * A);
+  r[i] = (float)(-A * (double)s1[i] / M + qx * B);
+}
+
+__global__ void bn_finalize_bwd_kernel(const float* __restrict__ s1, const float* __restrict__ s2,
+                                       const float* __restrict__ gamma, const float* __restrict__ sa,
+                                       const float* __restrict__ sb, float* __restrict__ p, float* __restrict__ q,
+                                       float* __restrict__ r, float* __restrict__ dgamma, float* __restrict__ dbeta,
+                                       int N, int C, int P, int training) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  double S1 = 0.0, S2 = 0.0;
+  for (int n = 0; n < N; ++n) { S1 += (double)s1[n * C + c]; S2 += (double)s2[n * C + c]; }
+  dgamma[c] = (float)S2;
+  dbeta[c] = (float)S1;
+  const double rstd = sa[c], nmr = sb[c];  // sa/sb identical over n; row 0
+  const double G = gamma[c], Mc = (double)N * P;
+  float fp, fq, fr;
+  if (training) {
+    const double qx = -G * rstd * S2 / Mc;
+    fp = (float)(G * rstd);
+    fq = (float)(qx * rstd);
+    fr = (float)(-G * rstd * S1 / Mc + qx * nmr);
+  } else {
+    fp = (float)(G * rstd); fq = 0.f; fr = 0.f;
+  }
+  for (int n = 0; n < N; ++n) { p[n * C + c] = fp; q[n * C + c] = fq; r[n * C + c] = fr; }
+}
+
+// dy = p * g' + q * y + r ; grid (planes, chunks)
+__global__ void __launch_bounds__(256) act_bwd_apply_kernel(const float* __restrict__ g, const float* __restrict__ y,
+                                                            const float* __restrict__ a, const float* __restrict__ b,
+                                                            float slope, const float* __restrict__ p,
+                                                            const float* __restrict__ q, const float* __restrict__ r,
+                                                            float* __restrict__ dy, int P) {
+  const long long base = (long long)blockIdx.x * P;
+  const float ca = a[blockIdx.x], cb = b[blockIdx.x];
+  const float cp = p[blockIdx.x], cq = q ? q[blockIdx.x] : 0.f, cr = r ? r[blockIdx.x] : 0.f;
+  for (int i = blockIdx.y * blockDim.x + threadIdx.x; i < P; i += gridDim.y * blockDim.x) {
+    const float yy = y[base + i];
+    float gg = g[base + i];
+    if (fmaf(ca, yy, cb) <= 0.f) gg *= slope;
+    dy[base + i] = fmaf(cp, gg, fmaf(cq, yy, cr));
+  }
+}
+
+// ---- resampling -----------------------------------------------------------------
+// y[h,w] = scale * sum of the 2x2 block of x; x planes are H x W, y planes Ho x Wo
+__global__ void pool2_kernel(const float* __restrict__ x, float* __restrict__ y, int H, int W, int Ho, int Wo,
+                             float scale, long long total) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int wo = (int)(i % Wo);
+    const long long t = i / Wo;
+    const int ho = (int)(t % Ho);
+    const long long pl = t / Ho;
+    const float* p = x + (pl * H + 2 * ho) * W + 2 * wo;
+    y[i] = scale * ((p[0] + p[1]) + (p[W] + p[W + 1]));
+  }
+}
+
+// y[2h+a, 2w+b] = scale * x[h,w]; total = planes * 2H * 2W
+__global__ void up2_kernel(const float* __restrict__ x, float* __restrict__ y, int H, int W, float scale,
+                           long long total) {
+  const int Wo = 2 * W, Ho = 2 * H;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int wo = (int)(i % Wo);
+    const long long t = i / Wo;
+    const int ho = (int)(t % Ho);
+    const long long pl = t / Ho;
+    y[i] = scale * x[(pl * H + (ho >> 1)) * W + (wo >> 1)];
+  }
+}
+
+// x [N, Co*4, H, W] (channel = co*4 + a*2 + b)  <->  y [N, Co, 2H, 2W]
+template <bool TO_SPACE>
+__global__ void shuffle2_kernel(const float* __restrict__ src, float* __restrict__ dst, int Co, int H, int W,
+                                long long total) {
+  const int Wo = 2 * W, Ho = 2 * H;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    // i enumerates the spatial-layout tensor [N, Co, 2H, 2W]
+    const int wo = (int)(i % Wo);
+    long long t = i / Wo;
+    const int ho = (int)(t % Ho);
+    t /= Ho;
+    const int co = (int)(t % Co);
+    const long long n = t / Co;
+    const long long j = ((n * Co * 4 + co * 4 + (ho & 1) * 2 + (wo & 1)) * H + (ho >> 1)) * W + (wo >> 1);
+    if (TO_SPACE) dst[i] = src[j]; else dst[j] = src[i];
+  }
+}
+
+inline int ew_grid(long long total) {
+  long long g = (total + 255) / 256;
+  const long long cap = (long long)san_num_sms() * 16;
+  return (int)(g < cap ? (g < 1 ? 1 : g) : cap);
+}
+inline int chunks_for(int planes, int P) {
+  // enough blocks to fill the machine, at most one block per 1024 elements
+  int per = (P + 1023) / 1024;
+  long long want = ((long long)san_num_sms() * 8 + planes - 1) / planes;
+  int c = (int)(want < per ? want : per);
+  return c < 1 ? 1 : c;
+}
+
+}  // namespace
+
+extern "C" {
+
+int san_plane_stats(const float* x, float* mean, float* m2, int planes, int P, void* stream) {
+  SAN_CHECK_ARG(x && mean && m2 && planes > 0 && P > 0, "san_plane_stats: bad args");
+  plane_stats_kernel<<<planes, 256, 0, (cudaStream_t)stream>>>(x, mean, m2, P);
+  SAN_LAUNCH_CHECK();
+  return SAN_OK;
+}
+
+int san_in_finalize_fwd(const float* mean, const float* m2, float* a, float* b, int planes, int P, float eps,
+                        void* stream) {
+  SAN_CHECK_ARG(mean && m2 && a && b && planes > 0, "san_in_finalize_fwd: bad args");
+  in_finalize_fwd_kernel<<<san_cdiv(planes, 256), 256, 0, (cudaStream_t)stream>>>(mean, m2, a, b, planes, P, eps);
+  SAN_LAUNCH_CHECK();
+  return SAN_OK;
+}
+
+int san_bn_finalize_fwd(const float* mean, const float* m2, const float* gamma, const float* beta,
+                        float* running_mean, float* running_var, float* a, float* b, float* sa, float* sb, int N,
+                        int C, int P, float eps, float momentum, int training, void* stream) {
+  SAN_CHECK_ARG(gamma && beta && a && b && sa && sb && N > 0 && C > 0, "san_bn_finalize_fwd: bad args");
+  SAN_CHECK_ARG(training ? (mean && m2) : (running_mean && running_var), "san_bn_finalize_fwd: missing statistics");
+  bn_finalize_fwd_kernel<<<san_cdiv(C, 64), 64, 0, (cudaStream_t)stream>>>(mean, m2, gamma, beta, running_mean,
+                                                                           running_var, a, b, sa, sb, N, C, P, eps,
+                                                                           momentum, training);
+  SAN_LAUNCH_CHECK();
+  return SAN_OK;
+}
+
+int san_affine_act_fwd(const float* y, const float* a, const float* b, float slope, float* out, int planes, int P,
+                       void* stream) {
+  SAN_CHECK_ARG(y && a && b && out && planes > 0 && P > 0, "san_affine_act_fwd: bad args");
+  dim3 grid(planes, chunks_for(planes, P));
+  affine_act_fwd_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(y, a, b, slope, out, P);
+  SAN_LAUNCH_CHECK();
+  return SAN_OK;
+}
+
+int san_act_bwd_reduce(const float* g, const float* y, const float* a, const float* b, const float* sa,
+                       const float* sb, float slope, float* s1, float* s2, int planes, int P, void* stream) {
+  SAN_CHECK_ARG(g && y && a && b && s1 && s2 && planes > 0 && P > 0, "san_act_bwd_reduce: bad args");
+  act_bwd_reduce_kernel<<<planes, 256, 0, (cudaStream_t)stream>>>(g, y, a, b, sa, sb, slope, s1, s2, P);
+  SAN_LAUNCH_CHECK();
+  return SAN_OK;
+}
+
+int san_in_finalize_bwd(const float* s1, const float* s2, const float* a, const float* b, float* p, float* q,
+                        float* r, int planes, int P, void* stream) {
+  SAN_CHECK_ARG(s1 && s2 && a && b && p && q && r && planes > 0, "san_in_finalize_bwd: bad args");
+  in_finalize_bwd_kernel<<<san_cdiv(planes, 256), 256, 0, (cudaStream_t)stream>>>(s1, s2, a, b, p, q, r, planes, P);
+  SAN_LAUNCH_CHECK();
+  return SAN_OK;
+}
+
+int san_bn_finalize_bwd(const float* s1, const float* s2, const float* gamma, const float* sa, const float* sb,
+                        float* p, float* q, float* r, float* dgamma, float* dbeta, int N, int C, int P, int training,
+                        void* stream) {
+  SAN_CHECK_ARG(s1 && s2 && gamma && sa && sb && p && q && r && dgamma && dbeta, "san_bn_finalize_bwd: bad args");
+  bn_finalize_bwd_kernel<<<san_cdiv(C, 64), 64, 0, (cudaStream_t)stream>>>(s1, s2, gamma, sa, sb, p, q, r, dgamma,
+                                                                           dbeta, N, C, P, training);
+  SAN_LAUNCH_CHECK();
+  return SAN_OK;
+}
+
+int san_act_bwd_apply(const float* g, const float* y, const float* a, const float* b, float slope, const float* p,
+                      const float* q, const float* r, float* dy, int planes, int P, void* stream) {
+  SAN_CHECK_ARG(g && y && a && b && p && dy && planes > 0 && P > 0, "san_act_bwd_apply: bad args");
+  dim3 grid(planes, chunks_for(planes, P));
+  act_bwd_apply_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(g, y, a, b, slope, p, q, r, dy, P);
+  SAN_LAUNCH_CHECK();
+  return SAN_OK;
+}
+
+int san_pool2(const float* x, float* y, long long planes, int H, int W, float scale, void* stream) {
+  SAN_CHECK_ARG(x && y && planes > 0 && H >= 2 && W >= 2, "san_pool2: bad args");
+  const int Ho = H / 2, Wo = W / 2;
+  const long long total = planes * Ho * Wo;
+  pool2_kernel<<<ew_grid(total), 256, 0, (cudaStream_t)stream>>>(x, y, H, W, Ho, Wo, scale, total);
+  SAN_LAUNCH_CHECK();
+  return SAN_OK;
+}
+
+int san_up2(const float* x, float* y, long long planes, int H, int W, float scale, void* stream) {
+  SAN_CHECK_ARG(x && y && planes > 0 && H > 0 && W > 0, "san_up2: bad args");
+  const long long total = planes * 4 * H * W;
+  up2_kernel<<<ew_grid(total), 256, 0, (cudaStream_t)stream>>>(x, y, H, W, scale, total);
+  SAN_LAUNCH_CHECK();
+  return SAN_OK;
+}
+
+int san_depth_to_space2(const float* x, float* y, int N, int Co, int H, int W, void* stream) {
+  SAN_CHECK_ARG(x && y && N > 0 && Co > 0 && H > 0 && W > 0, "san_depth_to_space2: bad args");
+  const long long total = (long long)N * Co * 4 * H * W;
+  shuffle2_kernel<true><<<ew_grid(total), 256, 0, (cudaStream_t)stream>>>(x, y, Co, H, W, total);
+  SAN_LAUNCH_CHECK();
+  return SAN_OK;
+}
+
+int san_space_to_depth2(const float* y, float* x, int N, int Co, int H, int W, void* stream) {
+  SAN_CHECK_ARG(x && y && N > 0 && Co > 0 && H > 0 && W > 0, "san_space_to_depth2: bad args");
+  const long long total = (long long)N * Co * 4 * H * W;
+  shuffle2_kernel<false><<<ew_grid(total), 256, 0, (cudaStream_t)stream>>>(y, x, Co, H, W, total);
+  SAN_LAUNCH_CHECK();
+  return SAN_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,155 @@
+"""Module-level parity of the san_b200 drop-in modules against golden vectors minted from
+the unmodified reference (tests/golden/make_golden.py) — the tests read like the reference's
+own usage: build the module with the reference's constructor arguments, load the reference's
+``state_dict``, call ``forward`` / ``backward``.  Bar: 1e-3 relative (north star, fp32);
+actual bounds are written next to each assert.  Needs a GPU."""
+import random
+
+import pytest
+import torch
+
+from conftest import grad_floor, load_golden, rel_l2, sub
+
+pytestmark = pytest.mark.gpu
+
+TOL = 5e-5      # forward values
+GTOL = 5e-4     # gradients through the deep nets
+
+
+@pytest.mark.parametrize("tag", ["varnet_s", "varnet_p"])
+def test_varnet_fwd_bwd(tag):
+    from spatialalignmentnetwork_b200.varnet import VarNet
+    g = load_golden(tag)
+    nc, ch, pools, sch, sp = [int(v) for v in g["cfg"]]
+    net = VarNet(num_cascades=nc, sens_chans=sch, sens_pools=sp, chans=ch, pools=pools, use_ref=True)
+    net.load_state_dict(sub(g, "sd."))
+    net.cuda()
+    ks = g["kspace"].cuda().requires_grad_(True)
+    ref = g["ref"].cuda().requires_grad_(True)
+    nlf = int(g["nlf"])
+    mask = (~g["pruned"]).cuda()
+    with torch.no_grad():
+        sens = net.sens_net(ks.detach(), nlf)
+    assert rel_l2(sens, g["sens"]) < TOL
+    rec = net(ks, mask, ref, nlf)
+    assert rec.shape == g["rec"].shape
+    assert rel_l2(rec, g["rec"]) < TOL
+    loss = ((rec - g["tgt"].cuda()) ** 2).mean()
+    loss.backward()
+    assert abs(loss.item() - g["loss"].item()) < 1e-4 * abs(g["loss"].item())
+    assert rel_l2(ks.grad, g["g_kspace"]) < GTOL
+    assert rel_l2(ref.grad, g["g_ref"]) < GTOL
+    grads = sub(g, "g.")
+    fl = grad_floor(grads)
+    params = dict(net.named_parameters())
+    for name, gg in grads.items():
+        assert rel_l2(params[name].grad, gg, fl) < GTOL, name
+
+
+def test_varnet_checkpointed_matches():
+    """Per-cascade recomputation (memory knob) must not change results."""
+    from spatialalignmentnetwork_b200.varnet import VarNet
+    g = load_golden("varnet_s")
+    nc, ch, pools, sch, sp = [int(v) for v in g["cfg"]]
+    outs = []
+    for ck in (False, True):
+        net = VarNet(num_cascades=nc, sens_chans=sch, sens_pools=sp, chans=ch, pools=pools, use_ref=True)
+        net.load_state_dict(sub(g, "sd."))
+        net.cuda()
+        net.checkpoint_cascades = ck
+        ks = g["kspace"].cuda().requires_grad_(True)
+        rec = net(ks, (~g["pruned"]).cuda(), g["ref"].cuda(), int(g["nlf"]))
+        ((rec - g["tgt"].cuda()) ** 2).mean().backward()
+        outs.append((rec.detach(), ks.grad.clone(), net.cascades[0].dc_weight.grad.clone()))
+    for a, b in zip(*outs):
+        assert rel_l2(a, b) < 1e-6
+
+
+def test_align_fwd_bwd():
+    from spatialalignmentnetwork_b200.cross import SpatialTransformer
+    from spatialalignmentnetwork_b200.model import gradient_loss
+    g = load_golden("align_s")
+    st = SpatialTransformer(1)
+    st.load_state_dict(sub(g, "sd."))
+    st.cuda().train()
+    img = g["img"].cuda().requires_grad_(True)
+    offset, grid = st(g["moving"].cuda(), g["fixed"].cuda())
+    assert offset.shape == g["offset"].shape and grid.shape == g["grid"].shape
+    assert rel_l2(offset, g["offset"]) < TOL
+    assert rel_l2(grid, g["grid"]) < TOL
+    warped = st.warp(img, grid)
+    assert rel_l2(warped, g["warped"]) < TOL
+    ls = gradient_loss(offset)
+    assert abs(ls.item() - g["loss_smooth"].item()) < 1e-4 * abs(g["loss_smooth"].item())
+    loss = ((warped - g["tgt"].cuda()) ** 2).mean() + 1000.0 * ls
+    loss.backward()
+    assert rel_l2(img.grad, g["g_img"]) < GTOL
+    grads = sub(g, "g.")
+    fl = grad_floor(grads)
+    params = dict(st.named_parameters())
+    for name, gg in grads.items():
+        assert rel_l2(params[name].grad, gg, fl) < GTOL, name
+    sd = st.state_dict()
+    for name, v in sub(g, "sd_after.").items():           # BatchNorm running-stat side effect
+        assert rel_l2(sd[name].double(), v.double()) < 1e-5, name
+    st.eval()
+    with torch.no_grad():
+        off_e, _ = st(g["moving"].cuda(), g["fixed"].cuda())
+    assert rel_l2(off_e, g["offset_eval"]) < TOL
+
+
+def test_rec_step_end_to_end():
+    """CSModel reg='Rec' (model.py:142-169, 206-216) against the reference CSModel's dump."""
+    from spatialalignmentnetwork_b200 import model as M
+    from spatialalignmentnetwork_b200.varnet import VarNet
+    g = load_golden("rec_step")
+    cfg = M.Config(sparsity=0.25, lr=1e-4, shape=32, coils=1, reg="Rec", mask="equispaced",
+                   weight_smooth=1000.0, weight_gan=0.1, weight_gan_sim=1.0, weight_sim=1.0, use_amp=False,
+                   num_cascades=2)
+    random.seed(11)
+    net = M.CSModel(cfg)
+    net.net_R = VarNet(num_cascades=2, sens_chans=2, sens_pools=2, chans=4, pools=2, use_ref=True)
+    assert torch.equal(net.net_mask.pruned, g["pruned"])         # mask bit-exact
+    net.net_T.load_state_dict(sub(g, "sdT."))
+    net.net_R.load_state_dict(sub(g, "sdR."))
+    net.to("cuda")
+    net.set_input(g["full"].cuda(), g["aux"].cuda())
+    assert rel_l2(net.img_k_sampled, g["k_sampled"]) < 3e-6
+    assert rel_l2(net.img_sampled, g["img_sampled"]) < 3e-6
+    net.loss_all = 0
+    net.forwardT()
+    net.forwardR()
+    for k in ("img_offset", "img_warped", "img_rec"):
+        assert rel_l2(getattr(net, k), g[k]) < TOL, k
+    for k in ("loss_all", "loss_smooth", "loss_sim"):
+        assert abs(getattr(net, k).item() - g[k].item()) < 1e-4 * max(1e-3, abs(g[k].item())), k
+    net.loss_all.backward()
+    for pre, mod in (("gT.", net.net_T), ("gR.", net.net_R)):
+        grads = sub(g, pre)
+        fl = grad_floor(grads)
+        params = dict(mod.named_parameters())
+        for name, gg in grads.items():
+            assert rel_l2(params[name].grad, gg, fl) < 1e-3, name
+
+
+def test_update_and_test_api():
+    """update() steps the optimisers; test() fills the metric_* attributes; get_vis harvests."""
+    from spatialalignmentnetwork_b200 import model as M
+    torch.manual_seed(0)
+    random.seed(0)
+    cfg = M.Config(sparsity=0.25, lr=1e-4, shape=64, coils=1, reg="Rec", mask="equispaced",
+                   weight_smooth=1000.0, weight_sim=1.0, num_cascades=1)
+    net = M.CSModel(cfg).to("cuda")
+    full = torch.complex(torch.rand(2, 1, 64, 64), torch.rand(2, 1, 64, 64)).cuda()
+    aux = torch.complex(torch.rand(2, 1, 64, 64), torch.rand(2, 1, 64, 64)).cuda()
+    before = net.net_R.cascades[0].dc_weight.detach().clone()
+    net.train()
+    net.set_input(full, aux)
+    net.update()
+    assert not torch.equal(before, net.net_R.cascades[0].dc_weight.detach())
+    vis = net.get_vis("scalars")["scalars"]
+    assert {"loss_all", "loss_smooth", "loss_sim"} <= set(vis)
+    net.eval()
+    net.set_input(full, aux)
+    r = net.test()
+    assert r == -net.metric_PSNR and 0.0 <= net.metric_SSIM <= 1.0
