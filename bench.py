@@ -1,0 +1,421 @@
+#!/usr/bin/env python
+"""Benchmark of the VarNet + spatial-alignment hot path (BASELINE.json metric: slices/sec).
+
+One "step" = what ``train.py`` does per iteration for ``--reg Rec`` (reference train.py:207-217,
+model.py:89-121, 142-169, 206-216) on one batch of synthetic 320x320 complex64 T1/T2 slice pairs:
+``set_input`` (fft2, mask, ifft2, rss) -> ``forwardT`` (alignment U-Net, displacement field, bilinear
+warp, smoothness loss) -> ``forwardR`` (12-cascade VarNet with the warped reference channel, SSIM
+loss) -> backward -> gradient all-reduce (N > 1) -> AdamW step of ``net_T`` and ``net_R``.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W]            # this repo's CUDA path
+    python bench.py --impl reference [--gpus N] ...                # CPU oracle port of the reference
+
+Prints ONE JSON line (rank 0).  ``value`` = slices/s with the inputs resident in HBM;
+``e2e`` = the same step driven from pinned HOST buffers (H2D of both modalities + D2H of the loss
+inside the timed region); ``roofline`` = the dominant kernel class, timed per launch with CUDA
+events on the launching stream in one extra instrumented step; ``cpu_baseline`` = the CPU oracle
+(port of the reference's PyTorch path) on this box's host cores on a bounded sample.
+"""
+import argparse
+import json
+import os
+import random
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+SEED = 20221017
+METRIC = "slices/sec (320x320 complex, 12-cascade VarNet+align, fwd+bwd+optimizer step)"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--batch", type=int, default=64, help="slices per GPU per step (weak scaling)")
+    ap.add_argument("--shape", type=int, default=320)
+    ap.add_argument("--cascades", type=int, default=12)
+    ap.add_argument("--checkpoint", default="auto", choices=["auto", "0", "1"],
+                    help="recompute each cascade in backward (memory knob)")
+    ap.add_argument("--cpu-sample", type=int, default=2, help="slices in the CPU baseline sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-profile", action="store_true", help="skip the instrumented per-kernel step")
+    ap.add_argument("--breakdown", default="", help="write the per-op time table (JSON) to this path")
+    return ap.parse_args()
+
+
+def load_peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            p = json.load(f)
+        return dict(hbm=float(p["hbm_gbs"]), tf_burst=float(p["bf16_tflops"]),
+                    tf_sust=float(p.get("bf16_tflops_sustained", p["bf16_tflops"])), src="measured")
+    except Exception:
+        return dict(hbm=6650.0, tf_burst=1590.0, tf_sust=1400.0, src="fallback")
+
+
+# ------------------------------------------------------------------------------------- clocks
+class ClockSampler:
+    """Samples nvidia-smi SM clocks / throttle reasons while the timed region runs."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                 "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for ln in self.proc.stdout:
+            self.lines.append(ln.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        self.t.join(timeout=2)
+        sm, mx, pw, reasons = [], [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1])); pw.append(float(f[2]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "power_w_max": max(pw),
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ------------------------------------------------------------------------------------- inputs
+def make_inputs(batch, shape, device="cpu", pin=False):
+    """"rand" set of SURVEY.md 8(d): real & imag ~ U[0,1), complex64 (mirrors reference model.py:372-375)."""
+    import torch
+    g = torch.Generator().manual_seed(SEED + 1)
+    full = torch.complex(torch.rand(batch, 1, shape, shape, generator=g), torch.rand(batch, 1, shape, shape, generator=g))
+    aux = torch.complex(torch.rand(batch, 1, shape, shape, generator=g), torch.rand(batch, 1, shape, shape, generator=g))
+    if pin:
+        full, aux = full.pin_memory(), aux.pin_memory()
+    if device != "cpu":
+        full, aux = full.to(device), aux.to(device)
+    return full, aux
+
+
+def build_model(args):
+    import torch
+    from spatialalignmentnetwork_b200 import model as M
+    torch.manual_seed(SEED)
+    random.seed(SEED)
+    cfg = M.Config(sparsity=0.25, lr=1e-4, shape=args.shape, coils=1, reg="Rec", mask="equispaced",
+                   weight_smooth=1000.0, weight_gan=0.1, weight_gan_sim=1.0, weight_sim=1.0, use_amp=False,
+                   num_cascades=args.cascades)
+    net = M.CSModel(cfg)
+    with torch.no_grad():  # non-trivial displacement field (zero-init makes offset == 0), SURVEY 8(d)
+        torch.nn.init.normal_(net.net_T.net[-1].weight, 0, 1e-2)
+    return net
+
+
+# ------------------------------------------------------------------------------------- per-op model
+def algorithmic(name, a):
+    """(flops, bytes) of one C-ABI call from its scalar arguments (DESIGN.md 'algorithmic work')."""
+    if name == "conv2d_fwd":
+        N, Cin, H, W, Cout, K = a[4:10]
+        return 2.0 * N * Cout * H * W * Cin * K * K, 4.0 * N * H * W * (Cin + Cout)
+    if name == "conv2d_wgrad":
+        N, Cin, H, W, Cout, K = a[4:10]
+        return 2.0 * N * Cout * H * W * Cin * K * K, 4.0 * N * H * W * (Cin + Cout)
+    if name == "fft_expand_dc":
+        N, C, H, W = a[8:12]
+        P = N * H * W
+        return 0.0, ((32.0 * C + 8) * P if a[2] is not None else (16.0 * C + 8) * P)
+    if name == "fft_reduce":
+        N, C, H, W = a[5:9]
+        P = N * H * W
+        return 0.0, (16.0 * C + 8) * P + (8.0 * C * P if a[3] is not None else 0.0)
+    if name == "fft_rss":
+        N, C, H, W = a[4:8]
+        return 0.0, (8.0 * C + 4) * N * H * W + (8.0 * C * N * H * W if a[2] is not None else 0.0)
+    if name == "fft2":
+        B, H, W = a[7:10]
+        return 0.0, 16.0 * B * H * W
+    return 0.0, 0.0
+
+
+CLASSES = {
+    "conv": ("conv2d_fwd", "conv2d_wgrad", "conv_pack_weights"),
+    "fft_dc": ("fft_expand_dc", "fft_reduce", "fft_rss", "fft2", "dc_bwd", "cmul_conj_planar"),
+    "norm_act": ("plane_stats", "in_finalize_fwd", "bn_finalize_fwd", "affine_act_fwd", "act_bwd_reduce",
+                 "in_finalize_bwd", "bn_finalize_bwd", "act_bwd_apply"),
+    "resample": ("pool2", "up2", "depth_to_space2", "space_to_depth2", "axpby"),
+    "align_warp": ("grid_from_offset", "grid_to_nchw", "warp_fwd", "warp_bwd", "grad_loss_fwd", "grad_loss_bwd"),
+    "losses": ("ssim_loss_fwd", "ssim_loss_bwd", "lncc_loss_fwd", "lncc_loss_bwd", "mi_hist_fwd", "mi_hist_bwd",
+               "filter2d"),
+}
+
+
+def summarise_profile(records, step_ms, peaks):
+    """records: [(name, args, ms)] of one instrumented step -> (roofline dict, breakdown dict)."""
+    per = {}
+    for name, a, ms in records:
+        fl, by = algorithmic(name, a)
+        d = per.setdefault(name, dict(launches=0, ms=0.0, flops=0.0, bytes=0.0))
+        d["launches"] += 1; d["ms"] += ms; d["flops"] += fl; d["bytes"] += by
+    total = sum(d["ms"] for d in per.values())
+    classes = {}
+    for cname, members in CLASSES.items():
+        ms = sum(per[m]["ms"] for m in members if m in per)
+        classes[cname] = dict(ms=round(ms, 3), share_of_kernel_time=round(ms / total, 4) if total else 0.0)
+    breakdown = dict(step_ms_instrumented=round(step_ms, 3), kernel_ms_total=round(total, 3), classes=classes,
+                     ops={k: dict(launches=v["launches"], ms=round(v["ms"], 3),
+                                  tflops=round(v["flops"] / v["ms"] / 1e9, 2) if v["flops"] and v["ms"] else None,
+                                  gbs=round(v["bytes"] / v["ms"] / 1e6, 1) if v["bytes"] and v["ms"] else None)
+                          for k, v in sorted(per.items(), key=lambda kv: -kv[1]["ms"])})
+    # dominant kernel = the U-Net convolutions (forward + data-gradient launches of conv2d_fwd)
+    roof = None
+    c = per.get("conv2d_fwd")
+    if c and c["ms"] > 0:
+        ach = c["flops"] / c["ms"] / 1e9  # TFLOP/s, algorithmic (1x) FLOPs
+        roof = dict(kernel="conv2d_fwd (U-Net 3x3/1x1 convs, fwd + dgrad)", bound="tensor", achieved=round(ach, 2),
+                    peak=peaks["tf_sust"], unit="TFLOP/s", frac=round(ach / peaks["tf_sust"], 5),
+                    peak_source=f"bf16 dense sustained, {peaks['src']}", traffic=None,
+                    launches=c["launches"], avg_launch_ms=round(c["ms"] / c["launches"], 4),
+                    share_of_kernel_time=round(c["ms"] / total, 4),
+                    hbm_gbs_compulsory=round(c["bytes"] / c["ms"] / 1e6, 1))
+    f = per.get("fft_expand_dc")
+    roof_fft = None
+    if f and f["ms"] > 0:
+        ach = f["bytes"] / f["ms"] / 1e6
+        roof_fft = dict(kernel="fft_expand_dc (x*S -> fft2 -> soft-DC + residual; and its adjoint use)", bound="hbm",
+                        achieved=round(ach, 1), peak=peaks["hbm"], unit="GB/s", frac=round(ach / peaks["hbm"], 4),
+                        peak_source=f"copy bandwidth, {peaks['src']}", traffic=None, launches=f["launches"],
+                        avg_launch_ms=round(f["ms"] / f["launches"], 4),
+                        share_of_kernel_time=round(f["ms"] / total, 4))
+    return roof, roof_fft, breakdown
+
+
+# ------------------------------------------------------------------------------------- CPU oracle arm
+def cpu_step_factory(args, nslices):
+    """The reference's path restated on CPU (oracle/): set_input + forwardT + forwardR + backward +
+    AdamW step, on ``nslices`` slices, all host threads."""
+    import torch
+    from oracle import step as ostep
+    torch.set_num_threads(os.cpu_count() or 1)
+    net = build_model(args)
+    pruned = net.net_mask.pruned.clone()
+    sdT = {k: v.detach().clone() for k, v in net.net_T.state_dict().items()}
+    sdR = {k: v.detach().clone() for k, v in net.net_R.state_dict().items()}
+    params = []
+    for d in (sdT, sdR):
+        for k, v in d.items():
+            if v.is_floating_point() and "running" not in k:
+                v.requires_grad_(True)
+                params.append(v)
+    opt = torch.optim.AdamW(params, lr=1e-4, weight_decay=0)
+    full, aux = make_inputs(nslices, args.shape)
+
+    def step():
+        inp = ostep.set_input(full, aux, pruned)
+        out = ostep.rec_step(sdT, sdR, inp, pruned, args.shape, 0.25, args.cascades)
+        opt.zero_grad()
+        out["loss_all"].backward()
+        opt.step()
+        return out["loss_all"].item()
+
+    return step
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    ns = args.cpu_sample
+    step = cpu_step_factory(args, ns)
+    for _ in range(min(args.warmup, 1)):
+        step()
+    times = []
+    for _ in range(args.steps):
+        t0 = time.perf_counter()
+        step()
+        times.append(time.perf_counter() - t0)
+    ms = 1e3 * sum(times) / len(times)
+    val = ns / (ms / 1e3)
+    cores = os.cpu_count() or 1
+    sample = (f"{ns} slices/step of the same workload ({args.cascades}-cascade VarNet + align, {args.shape}x{args.shape}, "
+              f"fwd+bwd+AdamW), CPU oracle port (torch CPU fp32), {cores} threads; warm-up capped at 1 step")
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": round(val, 4), "unit": "slices/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": min(args.warmup, 1), "ms_per_step": round(ms, 2), "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(args, max(args.gpus, 1), checkpoint=False),
+        "cpu_baseline": {"value": round(val, 4), "unit": "slices/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": round(val, 4), "unit": "slices/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0}))
+
+
+def workload_config(args, world, checkpoint, sample=None):
+    return {"workload": f"cfg2: bs={args.batch}/GPU {args.shape}x{args.shape} synthetic T1/T2 pairs, "
+                        f"{args.cascades}-cascade VarNet + alignment U-Net, reg='Rec' (smooth*1000 + SSIM), "
+                        "4x equispaced mask, fwd+bwd+AdamW",
+            "batch_per_gpu": args.batch, "global_batch": args.batch * world,
+            "shape": args.shape, "cascades": args.cascades, "coils": 1, "parallelism": f"dp{world}",
+            "checkpoint_cascades": bool(checkpoint),
+            "l2": "inputs (105 MB/step) + activations (GBs) exceed the 126 MB L2; no flush needed"}
+
+
+# ------------------------------------------------------------------------------------- CUDA arm
+def run_b200(args):
+    import torch
+    import torch.distributed as dist
+    from spatialalignmentnetwork_b200 import _lib, parallel
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback for the san_b200 path)"
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    peaks = load_peaks()
+
+    net = build_model(args)
+    total_mem = torch.cuda.get_device_properties(dev).total_memory
+    est = args.batch * (args.cascades * 0.19 + 0.5) * 2 ** 30 * (args.shape / 320.0) ** 2
+    ckpt = {"auto": est > 0.7 * total_mem, "0": False, "1": True}[args.checkpoint]
+    net.net_R.checkpoint_cascades = ckpt
+    net.to(dev).train()
+    if world > 1:
+        parallel.attach(net)
+
+    # per-rank shard of the global batch (weak scaling: args.batch slices per GPU)
+    full_h, aux_h = make_inputs(args.batch, args.shape, pin=True)
+    if rank:
+        full_h, aux_h = full_h.roll(rank, 0).pin_memory(), aux_h.roll(rank, 0).pin_memory()
+    full_d, aux_d = full_h.to(dev), aux_h.to(dev)
+
+    def step_resident():
+        net.set_input(full_d, aux_d)
+        net.update()
+
+    def step_e2e():
+        f = full_h.to(dev, non_blocking=True)
+        a = aux_h.to(dev, non_blocking=True)
+        net.set_input(f, a)
+        net.update()
+        return net.loss_all.item()      # D2H of the step's result
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        barrier()
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = t.item()
+        return ms
+
+    for _ in range(max(args.warmup, 3)):
+        step_resident()
+    clocks = ClockSampler(local)
+    if rank == 0:
+        clocks.start()
+    n0 = _lib.launch_count()
+    ms_res = timed(step_resident, args.steps)
+    launches = _lib.launch_count() - n0
+    ms_e2e = timed(step_e2e, args.steps)
+    clk = clocks.stop() if rank == 0 else None
+    peak_mem = torch.cuda.max_memory_allocated(dev)
+
+    roof = roof_fft = breakdown = None
+    if not args.no_profile:
+        barrier()
+        _lib.profile_begin()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        step_resident()
+        e1.record()
+        torch.cuda.synchronize()
+        recs = _lib.profile_end()
+        if rank == 0:
+            roof, roof_fft, breakdown = summarise_profile(recs, e0.elapsed_time(e1), peaks)
+
+    cpu_base = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        ns = args.cpu_sample
+        cstep = cpu_step_factory(args, ns)
+        t0 = time.perf_counter()
+        cstep()
+        dt = time.perf_counter() - t0
+        cores = os.cpu_count() or 1
+        cpu_base = {"value": round(ns / dt, 4), "unit": "slices/s", "cores": cores, "kind": "port",
+                    "sample": f"1 step on {ns} slices of the same workload (CPU oracle port, torch CPU fp32, {cores} threads, "
+                              f"{dt:.1f} s)"}
+
+    if rank == 0:
+        gb = args.batch * world
+        val = gb * args.steps / (ms_res / 1e3)
+        e2e = gb * args.steps / (ms_e2e / 1e3)
+        inbytes = full_h.numel() * 8 + aux_h.numel() * 8
+        out = {"metric": METRIC, "value": round(val, 3), "unit": "slices/s", "n_gpus": world, "steps": args.steps,
+               "warmup": max(args.warmup, 3), "ms_per_step": round(ms_res / args.steps, 3), "higher_is_better": True,
+               "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+               "config": workload_config(args, world, ckpt),
+               "e2e": {"value": round(e2e, 3), "unit": "slices/s", "h2d_bytes_per_step": inbytes, "d2h_bytes_per_step": 4,
+                       "ms_per_step": round(ms_e2e / args.steps, 3)},
+               "gpu_launches": int(launches), "clocks": clk, "roofline": roof, "roofline_fft_dc": roof_fft,
+               "cpu_baseline": cpu_base, "peak_mem_gb": round(peak_mem / 2 ** 30, 2), "impl": "b200"}
+        if breakdown is not None:
+            out["kernel_time_shares"] = {k: v["share_of_kernel_time"] for k, v in breakdown["classes"].items()}
+            if args.breakdown:
+                os.makedirs(os.path.dirname(os.path.abspath(args.breakdown)), exist_ok=True)
+                with open(args.breakdown, "w") as f:
+                    json.dump(breakdown, f, indent=1)
+        print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    a = parse()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_b200(a)

@@ -55,10 +55,10 @@ int san_fft_rss(const void* k, float* out, void* u_out, void* tmp, int N, int C,
 /* out[b,p] = sign * u[b,p] * conj(planar[n = b / C, p])  (sensitivity-map gradients) */
 int san_cmul_conj_planar(const void* u, const float* planar, void* out, int N, int C, long long P, float sign,
                          void* stream);
-/* backward of the soft-DC term: dk = G - where(mask, G, 0)*w (dk may be NULL);
- * d_dc_weight = -sum Re(conj(where(mask, k-k0, 0)) * G).  scratch: 1 double. */
+/* backward of the soft-DC term: dk = G - where(mask, G, 0)*w, dk0 = where(mask, G, 0)*w (either
+ * may be NULL); d_dc_weight = -sum Re(conj(where(mask, k-k0, 0)) * G).  scratch: 1 double. */
 int san_dc_bwd(const void* G, const void* k, const void* k0, const unsigned char* mask, const float* dc_weight,
-               void* dk, float* d_dc_weight, double* scratch, long long rows, int W, void* stream);
+               void* dk, void* dk0, float* d_dc_weight, double* scratch, long long rows, int W, void* stream);
 /* signal_utils.rss (signal_utils.py:24-26) over dim 1 of [N,C,P] (complex64 or float) */
 int san_rss_fwd(const float* x, float* out, int N, int C, long long P, int is_complex, void* stream);
 int san_rss_bwd(const float* g, const float* x, const float* r, float* dx, int N, int C, long long P,

@@ -94,9 +94,35 @@ def call(name, *args):
     for a, (t, an) in zip(args, protoargs):
         conv.append(_ptr(a, full, an) if "*" in t else a)
     conv.append(torch.cuda.current_stream().cuda_stream)
-    rc = getattr(L, full)(*conv)
+    if _profile is not None:
+        # bench.py's instrumented step: bracket the launch with CUDA events on the launching stream
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        rc = getattr(L, full)(*conv)
+        e1.record()
+        _profile.append((name, tuple(None if a is None else (a if isinstance(a, (int, float)) else 0) for a in args),
+                         e0, e1))
+    else:
+        rc = getattr(L, full)(*conv)
     if rc != 0:
         raise RuntimeError(f"{full} failed ({rc}): {L.san_last_error().decode()}")
+
+
+_profile = None
+
+
+def profile_begin():
+    """Start recording (op name, scalar args, start/stop CUDA events) for every C-ABI call."""
+    global _profile
+    _profile = []
+
+
+def profile_end():
+    """Stop recording; synchronise and return [(name, args, milliseconds)]."""
+    global _profile
+    recs, _profile = _profile, None
+    torch.cuda.synchronize()
+    return [(n, a, e0.elapsed_time(e1)) for n, a, e0, e1 in recs]
 
 
 def launch_count():

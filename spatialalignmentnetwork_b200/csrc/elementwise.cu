@@ -24,11 +24,11 @@ __global__ void cmul_conj_planar_kernel(const float2* __restrict__ u, const floa
   }
 }
 
-// dk = G - where(m, G, 0) * w ;  acc += -sum Re(conj(where(m, k-k0, 0)) * G)
+// dk = G - where(m, G, 0) * w ;  dk0 = where(m, G, 0) * w ;  acc += -sum Re(conj(where(m, k-k0, 0)) * G)
 __global__ void dc_bwd_kernel(const float2* __restrict__ G, const float2* __restrict__ k,
                               const float2* __restrict__ k0, const unsigned char* __restrict__ mask,
-                              const float* __restrict__ dcw, float2* __restrict__ dk, double* acc, int W,
-                              long long total) {
+                              const float* __restrict__ dcw, float2* __restrict__ dk, float2* __restrict__ dk0,
+                              double* acc, int W, long long total) {
   __shared__ double red[32];
   const float w = __ldg(dcw);
   double local = 0.0;
@@ -41,8 +41,10 @@ __global__ void dc_bwd_kernel(const float2* __restrict__ G, const float2* __rest
       const float dx = a.x - b.x, dy = a.y - b.y;
       local -= (double)(dx * g.x + dy * g.y);
       if (dk) dk[i] = make_float2(g.x - g.x * w, g.y - g.y * w);
-    } else if (dk) {
-      dk[i] = g;
+      if (dk0) dk0[i] = make_float2(g.x * w, g.y * w);
+    } else {
+      if (dk) dk[i] = g;
+      if (dk0) dk0[i] = make_float2(0.f, 0.f);
     }
   }
   local = block_sum_d(local, red);
@@ -161,13 +163,13 @@ int san_cmul_conj_planar(const void* u, const float* planar, void* out, int N, i
 }
 
 int san_dc_bwd(const void* G, const void* k, const void* k0, const unsigned char* mask, const float* dc_weight,
-               void* dk, float* d_dc_weight, double* scratch, long long rows, int W, void* stream) {
+               void* dk, void* dk0, float* d_dc_weight, double* scratch, long long rows, int W, void* stream) {
   SAN_CHECK_ARG(G && k && k0 && mask && dc_weight && d_dc_weight && scratch && rows > 0 && W > 0, "san_dc_bwd: bad args");
   cudaStream_t st = (cudaStream_t)stream;
   SAN_CUDA(cudaMemsetAsync(scratch, 0, sizeof(double), st));
   const long long total = rows * W;
   dc_bwd_kernel<<<ew_grid(total), 256, 0, st>>>((const float2*)G, (const float2*)k, (const float2*)k0, mask, dc_weight,
-                                                (float2*)dk, scratch, W, total);
+                                                (float2*)dk, (float2*)dk0, scratch, W, total);
   SAN_LAUNCH_CHECK();
   return san_finalize_scalar(scratch, d_dc_weight, 1.0, st);
 }

@@ -137,7 +137,7 @@ class FftExpandDC(Function):
         x, sens, k, k0, mask, dc_weight = ctx.saved_tensors
         G = _c64(G, "fft_expand_dc.backward")
         N, C, H, W = k.shape
-        dx = dS = dk = dw = None
+        dx = dS = dk = dk0 = dw = None
         if ctx.needs_input_grad[0] or ctx.needs_input_grad[1]:
             dx = torch.empty_like(x)
             u = torch.empty_like(k) if ctx.needs_input_grad[1] else None
@@ -146,12 +146,13 @@ class FftExpandDC(Function):
             if u is not None:
                 dS = torch.empty_like(k)
                 call("cmul_conj_planar", u, x, dS, N, C, H * W, 1.0)
-        if ctx.needs_input_grad[2] or ctx.needs_input_grad[5]:
+        if ctx.needs_input_grad[2] or ctx.needs_input_grad[3] or ctx.needs_input_grad[5]:
             dk = torch.empty_like(k) if ctx.needs_input_grad[2] else None
+            dk0 = torch.empty_like(k) if ctx.needs_input_grad[3] else None
             dw = torch.empty_like(dc_weight)
             scratch = torch.empty(1, dtype=torch.float64, device=k.device)
-            call("dc_bwd", G, k, k0, mask, dc_weight, dk, dw, scratch, N * C * H, W)
-        return dx, dS, dk, None, None, dw
+            call("dc_bwd", G, k, k0, mask, dc_weight, dk, dk0, dw, scratch, N * C * H, W)
+        return dx, dS, dk, dk0, None, dw
 
 
 class FftRss(Function):

@@ -105,7 +105,7 @@ def test_dc_block_backward():
     w = torch.tensor([0.7])
     G = crandn(N, C, H, W)
 
-    def ref(k, S, xp, w):
+    def ref(k, S, xp, w, k0):
         x = torch.complex(xp[:, :1], xp[:, 1:])
         soft = torch.where(m, k - k0, torch.zeros(1, 1, 1, 1, dtype=k.dtype)) * w
         out = k - soft - torch.fft.fft2(x * S, norm="ortho")
@@ -113,17 +113,15 @@ def test_dc_block_backward():
         return out, red
 
     a = [t.clone().double().requires_grad_(True) if not t.is_complex() else t.clone().to(torch.complex128).requires_grad_(True)
-         for t in (k, S, xp, w)]
-    k0_ = k0
-    k0 = k0.to(torch.complex128)
+         for t in (k, S, xp, w, k0)]
     out, red = ref(*a)
     ((out * G.to(torch.complex128).conj()).real.sum() + (red.real * 0.3 + red.imag * 0.7).sum()).backward()
-    k0 = k0_
-    b = [t.clone().cuda().requires_grad_(True) for t in (k, S, xp, w)]
-    out_c = ops.FftExpandDC.apply(b[2], b[1], b[0], k0.cuda(), m.cuda(), b[3])
+    b = [t.clone().cuda().requires_grad_(True) for t in (k, S, xp, w, k0)]
+    out_c = ops.FftExpandDC.apply(b[2], b[1], b[0], b[4], m.cuda(), b[3])
     red_c = ops.FftReduce.apply(b[0], b[1])
     ((out_c * G.cuda().conj()).real.sum() + (red_c[:, 0] * 0.3 + red_c[:, 1] * 0.7).sum()).backward()
-    for name, x, y in zip(("k", "S", "x", "dc_weight"), b, a):
+    # k0 = the acquired k-space (VarNetBlock's ref_kspace): d/dk0 = +where(mask, G, 0) * dc_weight
+    for name, x, y in zip(("k", "S", "x", "dc_weight", "k0"), b, a):
         assert rel_l2(x.grad, y.grad) < 1e-5, name
 
 
