@@ -88,26 +88,30 @@ int san_depth_to_space2(const float* x, float* y, int N, int Co, int H, int W, v
 int san_space_to_depth2(const float* y, float* x, int N, int Co, int H, int W, void* stream);
 
 /* ---- normalisation / activation / resampling (varnet.py:98,139-146,235,257-273; unet.py:119-140) ---- */
+/* per-plane mean and centred sum of squares (two-pass) */
 int san_plane_stats(const float* x, float* mean, float* m2, int planes, int P, void* stream);
+/* InstanceNorm coefficients: a = rstd, b = 0 (the centre mu is the `mean` array itself) */
 int san_in_finalize_fwd(const float* mean, const float* m2, float* a, float* b, int planes, int P, float eps,
                         void* stream);
+/* BatchNorm coefficients per plane [N*C]: mu, a = gamma*rstd, b = beta, sa = rstd; updates the
+ * running buffers in training mode (momentum, unbiased variance) */
 int san_bn_finalize_fwd(const float* mean, const float* m2, const float* gamma, const float* beta,
-                        float* running_mean, float* running_var, float* a, float* b, float* sa, float* sb, int N,
+                        float* running_mean, float* running_var, float* mu, float* a, float* b, float* sa, int N,
                         int C, int P, float eps, float momentum, int training, void* stream);
-/* out = leaky_relu(a[plane]*y + b[plane], slope) */
-int san_affine_act_fwd(const float* y, const float* a, const float* b, float slope, float* out, int planes, int P,
-                       void* stream);
-/* s1 = sum g', s2 = sum g'*(sa*y+sb) per plane, g' = g * lrelu'(a*y+b); sa/sb NULL = (1, 0) */
-int san_act_bwd_reduce(const float* g, const float* y, const float* a, const float* b, const float* sa,
-                       const float* sb, float slope, float* s1, float* s2, int planes, int P, void* stream);
-int san_in_finalize_bwd(const float* s1, const float* s2, const float* a, const float* b, float* p, float* q,
+/* out = leaky_relu(a[plane] * (y - mu[plane]) + b[plane], slope); mu, b may be NULL (= 0) */
+int san_affine_act_fwd(const float* y, const float* mu, const float* a, const float* b, float slope, float* out,
+                       int planes, int P, void* stream);
+/* s1 = sum g', s2 = sum g' * sa*(y - mu) per plane, g' = g * lrelu'(a*(y - mu) + b); sa NULL = 1 */
+int san_act_bwd_reduce(const float* g, const float* y, const float* mu, const float* a, const float* b,
+                       const float* sa, float slope, float* s1, float* s2, int planes, int P, void* stream);
+int san_in_finalize_bwd(const float* s1, const float* s2, const float* a, float* p, float* q,
                         float* r, int planes, int P, void* stream);
-int san_bn_finalize_bwd(const float* s1, const float* s2, const float* gamma, const float* sa, const float* sb,
+int san_bn_finalize_bwd(const float* s1, const float* s2, const float* gamma, const float* sa,
                         float* p, float* q, float* r, float* dgamma, float* dbeta, int N, int C, int P, int training,
                         void* stream);
-/* dy = p*g' + q*y + r (q, r may be NULL) */
-int san_act_bwd_apply(const float* g, const float* y, const float* a, const float* b, float slope, const float* p,
-                      const float* q, const float* r, float* dy, int planes, int P, void* stream);
+/* dy = p*g' + q*(y - mu) + r (q, r may be NULL) */
+int san_act_bwd_apply(const float* g, const float* y, const float* mu, const float* a, const float* b, float slope,
+                      const float* p, const float* q, const float* r, float* dy, int planes, int P, void* stream);
 /* y = scale * (2x2 block sum of x): avg_pool2d (scale .25) and the adjoint of nearest up-sampling (scale 1) */
 int san_pool2(const float* x, float* y, long long planes, int H, int W, float scale, void* stream);
 /* y[2h+a,2w+b] = scale * x[h,w]: nearest x2 (scale 1) and the adjoint of avg_pool2d (scale .25) */

@@ -20,10 +20,9 @@ class _LReLUFn(torch.autograd.Function):
     def forward(ctx, x, slope):
         x = x.contiguous()
         N, C, H, W = x.shape
-        ab = torch.zeros(2, N * C, dtype=torch.float32, device=x.device)
-        ab[0].fill_(1.0)
+        ab = torch.ones(1, N * C, dtype=torch.float32, device=x.device)
         out = torch.empty_like(x)
-        ops.call("affine_act_fwd", x, ab[0], ab[1], slope, out, N * C, H * W)
+        ops.call("affine_act_fwd", x, None, ab[0], None, slope, out, N * C, H * W)
         ctx.save_for_backward(x, ab)
         ctx.slope = slope
         return out
@@ -33,7 +32,7 @@ class _LReLUFn(torch.autograd.Function):
         x, ab = ctx.saved_tensors
         N, C, H, W = x.shape
         dx = torch.empty_like(x)
-        ops.call("act_bwd_apply", g.contiguous(), x, ab[0], ab[1], ctx.slope, ab[0], None, None, dx, N * C, H * W)
+        ops.call("act_bwd_apply", g.contiguous(), x, None, ab[0], None, ctx.slope, ab[0], None, None, dx, N * C, H * W)
         return dx, None
 
 

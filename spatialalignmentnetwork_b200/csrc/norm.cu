@@ -6,8 +6,9 @@
 // transposed convolution (varnet.py:176-179).
 //
 // A "plane" is one (n, c) image of P = H*W contiguous floats.  Normalisation is
-// expressed as  out = lrelu(a[plane] * y + b[plane])  with the coefficients
-// produced by tiny finalize kernels from two-pass (centred) plane statistics, so a
+// expressed in CENTRED form  out = lrelu(a[plane] * (y - mu[plane]) + b[plane])  (so a
+// large mean/std ratio costs no precision, like PyTorch's (x - mean) * rstd) with the
+// coefficients produced by tiny finalize kernels from two-pass plane statistics, so a
 // conv output is read twice (stats; L2-resident second pass) and written once.
 #include "san_common.cuh"
 #include "../../include/san_b200.h"
@@ -59,14 +60,14 @@ __global__ void in_finalize_fwd_kernel(const float* __restrict__ mean, const flo
   const float var = m2[i] / (float)P;
   const float rstd = 1.f / sqrtf(var + eps);
   a[i] = rstd;
-  b[i] = -mean[i] * rstd;
+  b[i] = 0.f;  // out = rstd * (y - mean)
 }
 
 // one thread per channel
 __global__ void bn_finalize_fwd_kernel(const float* __restrict__ mean, const float* __restrict__ m2,
                                        const float* __restrict__ gamma, const float* __restrict__ beta,
-                                       float* running_mean, float* running_var, float* __restrict__ a,
-                                       float* __restrict__ b, float* __restrict__ sa, float* __restrict__ sb, int N,
+                                       float* running_mean, float* running_var, float* __restrict__ mu_out,
+                                       float* __restrict__ a, float* __restrict__ b, float* __restrict__ sa, int N,
                                        int C, int P, float eps, float momentum, int training) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= C) return;
@@ -92,11 +93,10 @@ __global__ void bn_finalize_fwd_kernel(const float* __restrict__ mean, const flo
     mu = running_mean[c];
     rstd = 1.0 / sqrt((double)running_var[c] + (double)eps);
   }
-  const float fa = (float)(gamma[c] * rstd);
-  const float fb = (float)(beta[c] - mu * gamma[c] * rstd);
-  const float fsa = (float)rstd, fsb = (float)(-mu * rstd);
+  // out = gamma*rstd * (y - mu) + beta ; xhat = rstd * (y - mu)
+  const float fa = (float)(gamma[c] * rstd), fb = beta[c], fsa = (float)rstd, fmu = (float)mu;
   for (int n = 0; n < N; ++n) {
-    a[n * C + c] = fa; b[n * C + c] = fb; sa[n * C + c] = fsa; sb[n * C + c] = fsb;
+    mu_out[n * C + c] = fmu; a[n * C + c] = fa; b[n * C + c] = fb; sa[n * C + c] = fsa;
   }
 }
 
@@ -104,65 +104,69 @@ __global__ void bn_finalize_fwd_kernel(const float* __restrict__ mean, const flo
 __device__ __forceinline__ float lrelu(float v, float slope) { return v > 0.f ? v : v * slope; }
 
 // grid (planes, chunks)
-__global__ void __launch_bounds__(256) affine_act_fwd_kernel(const float* __restrict__ y, const float* __restrict__ a,
+__global__ void __launch_bounds__(256) affine_act_fwd_kernel(const float* __restrict__ y, const float* __restrict__ mu,
+                                                             const float* __restrict__ a,
                                                              const float* __restrict__ b, float slope,
                                                              float* __restrict__ out, int P) {
   const long long base = (long long)blockIdx.x * P;
-  const float ca = a[blockIdx.x], cb = b[blockIdx.x];
+  const float cm = mu ? mu[blockIdx.x] : 0.f;
+  const float ca = a[blockIdx.x], cb = b ? b[blockIdx.x] : 0.f;
   if ((P & 3) == 0) {
     const float4* y4 = (const float4*)(y + base);
     float4* o4 = (float4*)(out + base);
     for (int i = blockIdx.y * blockDim.x + threadIdx.x; i < P / 4; i += gridDim.y * blockDim.x) {
       float4 v = y4[i];
-      v.x = lrelu(fmaf(ca, v.x, cb), slope); v.y = lrelu(fmaf(ca, v.y, cb), slope);
-      v.z = lrelu(fmaf(ca, v.z, cb), slope); v.w = lrelu(fmaf(ca, v.w, cb), slope);
+      v.x = lrelu(fmaf(ca, v.x - cm, cb), slope); v.y = lrelu(fmaf(ca, v.y - cm, cb), slope);
+      v.z = lrelu(fmaf(ca, v.z - cm, cb), slope); v.w = lrelu(fmaf(ca, v.w - cm, cb), slope);
       o4[i] = v;
     }
   } else {
     for (int i = blockIdx.y * blockDim.x + threadIdx.x; i < P; i += gridDim.y * blockDim.x)
-      out[base + i] = lrelu(fmaf(ca, y[base + i], cb), slope);
+      out[base + i] = lrelu(fmaf(ca, y[base + i] - cm, cb), slope);
   }
 }
 
 // ---- backward -------------------------------------------------------------------
-// s1 = sum g', s2 = sum g' * (sa*y + sb), g' = g * lrelu'(a*y + b); one block per plane
+// s1 = sum g', s2 = sum g' * sa*(y - mu), g' = g * lrelu'(a*(y - mu) + b); one block per plane
 __global__ void __launch_bounds__(256) act_bwd_reduce_kernel(const float* __restrict__ g, const float* __restrict__ y,
+                                                             const float* __restrict__ mu,
                                                              const float* __restrict__ a, const float* __restrict__ b,
-                                                             const float* __restrict__ sa, const float* __restrict__ sb,
+                                                             const float* __restrict__ sa,
                                                              float slope, float* __restrict__ s1, float* __restrict__ s2,
                                                              int P) {
   __shared__ double red[32];
   const long long base = (long long)blockIdx.x * P;
-  const float ca = a[blockIdx.x], cb = b[blockIdx.x];
-  const float csa = sa ? sa[blockIdx.x] : 1.f, csb = sb ? sb[blockIdx.x] : 0.f;
+  const float cm = mu ? mu[blockIdx.x] : 0.f;
+  const float ca = a[blockIdx.x], cb = b ? b[blockIdx.x] : 0.f;
+  const float csa = sa ? sa[blockIdx.x] : 1.f;
   float t1 = 0.f, t2 = 0.f;
   for (int i = threadIdx.x; i < P; i += blockDim.x) {
-    const float yy = y[base + i];
+    const float yc = y[base + i] - cm;
     float gg = g[base + i];
-    if (fmaf(ca, yy, cb) <= 0.f) gg *= slope;
+    if (fmaf(ca, yc, cb) <= 0.f) gg *= slope;
     t1 += gg;
-    t2 += gg * fmaf(csa, yy, csb);
+    t2 += gg * (csa * yc);
   }
   const double r1 = block_sum_d((double)t1, red);
   const double r2 = block_sum_d((double)t2, red);
   if (threadIdx.x == 0) { s1[blockIdx.x] = (float)r1; s2[blockIdx.x] = (float)r2; }
 }
 
+// dx = rstd * (g' - mean(g') - xhat * mean(g' xhat)), xhat = rstd*(y - mu)  ->  dy = p g' + q (y - mu) + r
 __global__ void in_finalize_bwd_kernel(const float* __restrict__ s1, const float* __restrict__ s2,
-                                       const float* __restrict__ a, const float* __restrict__ b, float* __restrict__ p,
+                                       const float* __restrict__ a, float* __restrict__ p,
                                        float* __restrict__ q, float* __restrict__ r, int planes, int P) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= planes) return;
-  const double A = a[i], B = b[i], M = P;
-  const double qx = -A * (double)s2[i] / M;  // multiplies xhat = A*y + B
+  const double A = a[i], M = P;
   p[i] = (float)A;
-  q[i] = (float)(qx * A);
-  r[i] = (float)(-A * (double)s1[i] / M + qx * B);
+  q[i] = (float)(-A * A * (double)s2[i] / M);
+  r[i] = (float)(-A * (double)s1[i] / M);
 }
 
 __global__ void bn_finalize_bwd_kernel(const float* __restrict__ s1, const float* __restrict__ s2,
                                        const float* __restrict__ gamma, const float* __restrict__ sa,
-                                       const float* __restrict__ sb, float* __restrict__ p, float* __restrict__ q,
+                                       float* __restrict__ p, float* __restrict__ q,
                                        float* __restrict__ r, float* __restrict__ dgamma, float* __restrict__ dbeta,
                                        int N, int C, int P, int training) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
@@ -171,34 +175,35 @@ __global__ void bn_finalize_bwd_kernel(const float* __restrict__ s1, const float
   for (int n = 0; n < N; ++n) { S1 += (double)s1[n * C + c]; S2 += (double)s2[n * C + c]; }
   dgamma[c] = (float)S2;
   dbeta[c] = (float)S1;
-  const double rstd = sa[c], nmr = sb[c];  // sa/sb identical over n; row 0
+  const double rstd = sa[c];  // identical over n; row 0
   const double G = gamma[c], Mc = (double)N * P;
   float fp, fq, fr;
   if (training) {
-    const double qx = -G * rstd * S2 / Mc;
     fp = (float)(G * rstd);
-    fq = (float)(qx * rstd);
-    fr = (float)(-G * rstd * S1 / Mc + qx * nmr);
+    fq = (float)(-G * rstd * rstd * S2 / Mc);   // multiplies (y - mu)
+    fr = (float)(-G * rstd * S1 / Mc);
   } else {
     fp = (float)(G * rstd); fq = 0.f; fr = 0.f;
   }
   for (int n = 0; n < N; ++n) { p[n * C + c] = fp; q[n * C + c] = fq; r[n * C + c] = fr; }
 }
 
-// dy = p * g' + q * y + r ; grid (planes, chunks)
+// dy = p * g' + q * (y - mu) + r ; grid (planes, chunks)
 __global__ void __launch_bounds__(256) act_bwd_apply_kernel(const float* __restrict__ g, const float* __restrict__ y,
+                                                            const float* __restrict__ mu,
                                                             const float* __restrict__ a, const float* __restrict__ b,
                                                             float slope, const float* __restrict__ p,
                                                             const float* __restrict__ q, const float* __restrict__ r,
                                                             float* __restrict__ dy, int P) {
   const long long base = (long long)blockIdx.x * P;
-  const float ca = a[blockIdx.x], cb = b[blockIdx.x];
+  const float cm = mu ? mu[blockIdx.x] : 0.f;
+  const float ca = a[blockIdx.x], cb = b ? b[blockIdx.x] : 0.f;
   const float cp = p[blockIdx.x], cq = q ? q[blockIdx.x] : 0.f, cr = r ? r[blockIdx.x] : 0.f;
   for (int i = blockIdx.y * blockDim.x + threadIdx.x; i < P; i += gridDim.y * blockDim.x) {
-    const float yy = y[base + i];
+    const float yc = y[base + i] - cm;
     float gg = g[base + i];
-    if (fmaf(ca, yy, cb) <= 0.f) gg *= slope;
-    dy[base + i] = fmaf(cp, gg, fmaf(cq, yy, cr));
+    if (fmaf(ca, yc, cb) <= 0.f) gg *= slope;
+    dy[base + i] = fmaf(cp, gg, fmaf(cq, yc, cr));
   }
 }
 
@@ -283,57 +288,57 @@ int san_in_finalize_fwd(const float* mean, const float* m2, float* a, float* b, 
 }
 
 int san_bn_finalize_fwd(const float* mean, const float* m2, const float* gamma, const float* beta,
-                        float* running_mean, float* running_var, float* a, float* b, float* sa, float* sb, int N,
+                        float* running_mean, float* running_var, float* mu, float* a, float* b, float* sa, int N,
                         int C, int P, float eps, float momentum, int training, void* stream) {
-  SAN_CHECK_ARG(gamma && beta && a && b && sa && sb && N > 0 && C > 0, "san_bn_finalize_fwd: bad args");
+  SAN_CHECK_ARG(gamma && beta && mu && a && b && sa && N > 0 && C > 0, "san_bn_finalize_fwd: bad args");
   SAN_CHECK_ARG(training ? (mean && m2) : (running_mean && running_var), "san_bn_finalize_fwd: missing statistics");
   bn_finalize_fwd_kernel<<<san_cdiv(C, 64), 64, 0, (cudaStream_t)stream>>>(mean, m2, gamma, beta, running_mean,
-                                                                           running_var, a, b, sa, sb, N, C, P, eps,
+                                                                           running_var, mu, a, b, sa, N, C, P, eps,
                                                                            momentum, training);
   SAN_LAUNCH_CHECK();
   return SAN_OK;
 }
 
-int san_affine_act_fwd(const float* y, const float* a, const float* b, float slope, float* out, int planes, int P,
-                       void* stream) {
-  SAN_CHECK_ARG(y && a && b && out && planes > 0 && P > 0, "san_affine_act_fwd: bad args");
+int san_affine_act_fwd(const float* y, const float* mu, const float* a, const float* b, float slope, float* out,
+                       int planes, int P, void* stream) {
+  SAN_CHECK_ARG(y && a && out && planes > 0 && P > 0, "san_affine_act_fwd: bad args");
   dim3 grid(planes, chunks_for(planes, P));
-  affine_act_fwd_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(y, a, b, slope, out, P);
+  affine_act_fwd_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(y, mu, a, b, slope, out, P);
   SAN_LAUNCH_CHECK();
   return SAN_OK;
 }
 
-int san_act_bwd_reduce(const float* g, const float* y, const float* a, const float* b, const float* sa,
-                       const float* sb, float slope, float* s1, float* s2, int planes, int P, void* stream) {
-  SAN_CHECK_ARG(g && y && a && b && s1 && s2 && planes > 0 && P > 0, "san_act_bwd_reduce: bad args");
-  act_bwd_reduce_kernel<<<planes, 256, 0, (cudaStream_t)stream>>>(g, y, a, b, sa, sb, slope, s1, s2, P);
+int san_act_bwd_reduce(const float* g, const float* y, const float* mu, const float* a, const float* b,
+                       const float* sa, float slope, float* s1, float* s2, int planes, int P, void* stream) {
+  SAN_CHECK_ARG(g && y && a && s1 && s2 && planes > 0 && P > 0, "san_act_bwd_reduce: bad args");
+  act_bwd_reduce_kernel<<<planes, 256, 0, (cudaStream_t)stream>>>(g, y, mu, a, b, sa, slope, s1, s2, P);
   SAN_LAUNCH_CHECK();
   return SAN_OK;
 }
 
-int san_in_finalize_bwd(const float* s1, const float* s2, const float* a, const float* b, float* p, float* q,
+int san_in_finalize_bwd(const float* s1, const float* s2, const float* a, float* p, float* q,
                         float* r, int planes, int P, void* stream) {
-  SAN_CHECK_ARG(s1 && s2 && a && b && p && q && r && planes > 0, "san_in_finalize_bwd: bad args");
-  in_finalize_bwd_kernel<<<san_cdiv(planes, 256), 256, 0, (cudaStream_t)stream>>>(s1, s2, a, b, p, q, r, planes, P);
+  SAN_CHECK_ARG(s1 && s2 && a && p && q && r && planes > 0, "san_in_finalize_bwd: bad args");
+  in_finalize_bwd_kernel<<<san_cdiv(planes, 256), 256, 0, (cudaStream_t)stream>>>(s1, s2, a, p, q, r, planes, P);
   SAN_LAUNCH_CHECK();
   return SAN_OK;
 }
 
-int san_bn_finalize_bwd(const float* s1, const float* s2, const float* gamma, const float* sa, const float* sb,
+int san_bn_finalize_bwd(const float* s1, const float* s2, const float* gamma, const float* sa,
                         float* p, float* q, float* r, float* dgamma, float* dbeta, int N, int C, int P, int training,
                         void* stream) {
-  SAN_CHECK_ARG(s1 && s2 && gamma && sa && sb && p && q && r && dgamma && dbeta, "san_bn_finalize_bwd: bad args");
-  bn_finalize_bwd_kernel<<<san_cdiv(C, 64), 64, 0, (cudaStream_t)stream>>>(s1, s2, gamma, sa, sb, p, q, r, dgamma,
+  SAN_CHECK_ARG(s1 && s2 && gamma && sa && p && q && r && dgamma && dbeta, "san_bn_finalize_bwd: bad args");
+  bn_finalize_bwd_kernel<<<san_cdiv(C, 64), 64, 0, (cudaStream_t)stream>>>(s1, s2, gamma, sa, p, q, r, dgamma,
                                                                            dbeta, N, C, P, training);
   SAN_LAUNCH_CHECK();
   return SAN_OK;
 }
 
-int san_act_bwd_apply(const float* g, const float* y, const float* a, const float* b, float slope, const float* p,
-                      const float* q, const float* r, float* dy, int planes, int P, void* stream) {
-  SAN_CHECK_ARG(g && y && a && b && p && dy && planes > 0 && P > 0, "san_act_bwd_apply: bad args");
+int san_act_bwd_apply(const float* g, const float* y, const float* mu, const float* a, const float* b, float slope,
+                      const float* p, const float* q, const float* r, float* dy, int planes, int P, void* stream) {
+  SAN_CHECK_ARG(g && y && a && p && dy && planes > 0 && P > 0, "san_act_bwd_apply: bad args");
   dim3 grid(planes, chunks_for(planes, P));
-  act_bwd_apply_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(g, y, a, b, slope, p, q, r, dy, P);
+  act_bwd_apply_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(g, y, mu, a, b, slope, p, q, r, dy, P);
   SAN_LAUNCH_CHECK();
   return SAN_OK;
 }

@@ -315,11 +315,11 @@ class InstanceNormLReLU(Function):
     def forward(ctx, y, slope, eps):
         y = _f32(y, "instance_norm")
         planes, P = _planes(y)
-        st = torch.empty(4, planes, dtype=torch.float32, device=y.device)
+        st = torch.empty(4, planes, dtype=torch.float32, device=y.device)   # mean, m2, a (= rstd), b (= 0)
         call("plane_stats", y, st[0], st[1], planes, P)
         call("in_finalize_fwd", st[0], st[1], st[2], st[3], planes, P, eps)
         out = torch.empty_like(y)
-        call("affine_act_fwd", y, st[2], st[3], slope, out, planes, P)
+        call("affine_act_fwd", y, st[0], st[2], None, slope, out, planes, P)
         ctx.save_for_backward(y, st)
         ctx.slope = slope
         return out
@@ -330,12 +330,12 @@ class InstanceNormLReLU(Function):
         y, st = ctx.saved_tensors
         g = _f32(g, "instance_norm.backward")
         planes, P = _planes(y)
-        a, b = st[2], st[3]
+        mu, a = st[0], st[2]
         w = torch.empty(5, planes, dtype=torch.float32, device=y.device)
-        call("act_bwd_reduce", g, y, a, b, a, b, ctx.slope, w[0], w[1], planes, P)
-        call("in_finalize_bwd", w[0], w[1], a, b, w[2], w[3], w[4], planes, P)
+        call("act_bwd_reduce", g, y, mu, a, None, a, ctx.slope, w[0], w[1], planes, P)
+        call("in_finalize_bwd", w[0], w[1], a, w[2], w[3], w[4], planes, P)
         dy = torch.empty_like(y)
-        call("act_bwd_apply", g, y, a, b, ctx.slope, w[2], w[3], w[4], dy, planes, P)
+        call("act_bwd_apply", g, y, mu, a, None, ctx.slope, w[2], w[3], w[4], dy, planes, P)
         return dy, None, None
 
 
@@ -347,16 +347,15 @@ class BatchNormLReLU(Function):
         y = _f32(y, "batch_norm")
         N, C, H, W = y.shape
         planes, P = N * C, H * W
-        st = torch.empty(6, planes, dtype=torch.float32, device=y.device)
+        st = torch.empty(6, planes, dtype=torch.float32, device=y.device)   # mean, m2, mu, a, b, sa
         if training:
             call("plane_stats", y, st[0], st[1], planes, P)
         call("bn_finalize_fwd", st[0], st[1], gamma, beta, running_mean, running_var, st[2], st[3], st[4], st[5],
              N, C, P, eps, momentum, int(training))
         out = torch.empty_like(y)
-        call("affine_act_fwd", y, st[2], st[3], slope, out, planes, P)
+        call("affine_act_fwd", y, st[2], st[3], st[4], slope, out, planes, P)
         ctx.save_for_backward(y, st, gamma)
         ctx.cfg = (slope, bool(training))
-        ctx.mark_non_differentiable()
         return out
 
     @staticmethod
@@ -367,14 +366,14 @@ class BatchNormLReLU(Function):
         g = _f32(g, "batch_norm.backward")
         N, C, H, W = y.shape
         planes, P = N * C, H * W
-        a, b, sa, sb = st[2], st[3], st[4], st[5]
+        mu, a, b, sa = st[2], st[3], st[4], st[5]
         w = torch.empty(5, planes, dtype=torch.float32, device=y.device)
-        call("act_bwd_reduce", g, y, a, b, sa, sb, slope, w[0], w[1], planes, P)
+        call("act_bwd_reduce", g, y, mu, a, b, sa, slope, w[0], w[1], planes, P)
         dgamma = torch.empty_like(gamma)
         dbeta = torch.empty_like(gamma)
-        call("bn_finalize_bwd", w[0], w[1], gamma, sa, sb, w[2], w[3], w[4], dgamma, dbeta, N, C, P, int(training))
+        call("bn_finalize_bwd", w[0], w[1], gamma, sa, w[2], w[3], w[4], dgamma, dbeta, N, C, P, int(training))
         dy = torch.empty_like(y)
-        call("act_bwd_apply", g, y, a, b, slope, w[2], w[3], w[4], dy, planes, P)
+        call("act_bwd_apply", g, y, mu, a, b, slope, w[2], w[3], w[4], dy, planes, P)
         return dy, dgamma, dbeta, None, None, None, None, None, None
 
 
@@ -398,39 +397,44 @@ class PlaneStats(Function):
         N, C, H, W = x.shape
         P = H * W
         a = (2.0 * gm2).reshape(-1).contiguous()
-        b = (gmean.reshape(-1) / P - a * st[0]).contiguous()
+        b = (gmean.reshape(-1) / P).contiguous()
         dx = torch.empty_like(x)
-        call("affine_act_fwd", x, a, b, 1.0, dx, N * C, P)
+        call("affine_act_fwd", x, st[0], a, b, 1.0, dx, N * C, P)
         return dx
 
 
 class PlaneAffine(Function):
-    """out[n,c] = a[n,c] * x[n,c] + b[n,c] with per-plane scalars a, b (differentiable in all
-    three); the norm / unnorm of NormUnet (reference varnet.py:257-273)."""
+    """out[n,c] = a[n,c] * (x[n,c] - mu[n,c]) + b[n,c] with per-plane scalars (mu, b optional),
+    differentiable in all four; the norm / unnorm of NormUnet (reference varnet.py:257-273) in the
+    centred form PyTorch's ``(x - mean) / std`` has."""
 
     @staticmethod
-    def forward(ctx, x, a, b):
+    def forward(ctx, x, mu, a, b):
         x = _f32(x, "plane_affine")
         N, C, H, W = x.shape
         a = _f32(a.reshape(-1), "plane_affine")
-        b = _f32(b.reshape(-1), "plane_affine")
+        mu = _f32(mu.reshape(-1), "plane_affine") if mu is not None else None
+        b = _f32(b.reshape(-1), "plane_affine") if b is not None else None
         out = torch.empty_like(x)
-        call("affine_act_fwd", x, a, b, 1.0, out, N * C, H * W)
-        ctx.save_for_backward(x, a, b)
+        call("affine_act_fwd", x, mu, a, b, 1.0, out, N * C, H * W)
+        ctx.save_for_backward(x, mu, a)
+        ctx.has = (mu is not None, b is not None)
         return out
 
     @staticmethod
     @once_differentiable
     def backward(ctx, g):
-        x, a, b = ctx.saved_tensors
+        x, mu, a = ctx.saved_tensors
         g = _f32(g, "plane_affine.backward")
         N, C, H, W = x.shape
         planes, P = N * C, H * W
-        s = torch.empty(2, planes, dtype=torch.float32, device=x.device)
-        call("act_bwd_reduce", g, x, a, b, None, None, 1.0, s[0], s[1], planes, P)
+        s = torch.empty(2, planes, dtype=torch.float32, device=x.device)   # sum g, sum g*(x - mu)
+        call("act_bwd_reduce", g, x, mu, a, None, None, 1.0, s[0], s[1], planes, P)
         dx = torch.empty_like(x)
-        call("act_bwd_apply", g, x, a, b, 1.0, a, None, None, dx, planes, P)
-        return dx, s[1].view(N, C), s[0].view(N, C)
+        call("act_bwd_apply", g, x, mu, a, None, 1.0, a, None, None, dx, planes, P)
+        dmu = (-a * s[0]).view(N, C) if ctx.has[0] else None
+        db = s[0].view(N, C) if ctx.has[1] else None
+        return dx, dmu, s[1].view(N, C), db
 
 
 class AvgPool2(Function):

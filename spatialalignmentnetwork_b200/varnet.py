@@ -150,12 +150,12 @@ class NormUnet(nn.Module):
         mean, m2 = ops.PlaneStats.apply(x)
         std = torch.sqrt(m2 / (h * w - 1))
         a = 1.0 / (std + 1e-6)
-        xn = ops.PlaneAffine.apply(x, a, -mean * a)
+        xn = ops.PlaneAffine.apply(x, mean, a, None)          # (x - mean) / (std + 1e-6)
         return xn, mean.view(b, 2, 1, 1), std.view(b, 2, 1, 1)
 
     def unnorm(self, x, mean, std):
         b = x.shape[0]
-        return ops.PlaneAffine.apply(x, std.reshape(b, 2), mean.reshape(b, 2))
+        return ops.PlaneAffine.apply(x, None, std.reshape(b, 2), mean.reshape(b, 2))   # x * std + mean
 
     def pad(self, x):
         _, _, h, w = x.shape

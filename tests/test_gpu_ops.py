@@ -244,6 +244,32 @@ def test_batch_norm_lrelu(training):
     assert rel_l2(rmc, rmr) < 1e-6 and rel_l2(rvc, rvr) < 1e-6
 
 
+@pytest.mark.parametrize("kind", ["instance", "batch"])
+def test_norm_large_mean_over_std(kind):
+    """mean/std = 500: the centred form (y - mu) * rstd must keep forward AND backward accurate
+    (an a*y + b formulation loses ~mean/std ulps, which showed up as 5e-3 gradient error in net_T)."""
+    ops = _ops()
+    torch.manual_seed(12)
+    N, C, H, W = 2, 4, 16, 24
+    y = torch.randn(N, C, H, W) * 0.1 + 50.0
+    g = torch.randn(N, C, H, W)
+    yr = y.double().requires_grad_(True)
+    yc = y.cuda().requires_grad_(True)
+    if kind == "instance":
+        outr = F.leaky_relu(F.instance_norm(yr, eps=1e-5), 0.2)
+        outc = ops.InstanceNormLReLU.apply(yc, 0.2, 1e-5)
+    else:
+        gamma, beta = torch.rand(C) + 0.5, torch.randn(C) * 0.2
+        outr = F.leaky_relu(F.batch_norm(yr, None, None, gamma.double(), beta.double(), True, 0.1, 1e-5), 0.01)
+        outc = ops.BatchNormLReLU.apply(yc, gamma.cuda(), beta.cuda(), torch.zeros(C).cuda(), torch.ones(C).cuda(),
+                                        True, 0.1, 1e-5, 0.01)
+    (outr * g.double()).sum().backward()
+    (outc * g.cuda()).sum().backward()
+    # the input itself carries 50/0.1 * 2^-24 = 3e-5 relative rounding of (y - mean); allow 4x that
+    assert rel_l2(outc, outr) < 1.2e-4
+    assert rel_l2(yc.grad, yr.grad) < 1.2e-4
+
+
 def test_plane_stats_affine_normunet_norm():
     """NormUnet.norm / unnorm (varnet.py:257-273) incl. the gradient through mean and std."""
     from spatialalignmentnetwork_b200.varnet import NormUnet
