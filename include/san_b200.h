@@ -87,6 +87,33 @@ int san_conv2d_wgrad(const float* x, const float* dy, float* dw, float* dbias, i
 int san_depth_to_space2(const float* x, float* y, int N, int Co, int H, int W, void* stream);
 int san_space_to_depth2(const float* y, float* x, int N, int Co, int H, int W, void* stream);
 
+/* ---- tcgen05 tensor-core convolutions (same call sites as above; BF16x3 split, fp32 TMEM accumulate) ----
+ * Activations are staged as Xs[n][hl][kg][(H+2)*(W+2)][8] bf16 (hl = hi/lo halves of the fp32 value,
+ * kg = groups of 8 channels, Cin padded to 16, one-pixel zero border); weights as
+ * Ws[nsplit][KS][taps][hl][2][Npad][8].  Element counts of the caller-allocated buffers: */
+long long san_tc_staged_act_elems(int N, int H, int W, int C);
+long long san_tc_staged_weight_elems(int Cout, int Cin, int K);
+int san_tc_supported(int H, int W, int Cin, int Cout, int K);
+/* Fused operand producer: up to 3 channel-concatenated sources (varnet.py:116 concat order),
+ * each out = leaky_relu(a[plane]*(y - mu[plane]) + b[plane], slope) (a NULL = identity), i.e. the
+ * InstanceNorm / BatchNorm + LeakyReLU of varnet.py:141-145 / unet.py:124-126 applied on the fly;
+ * mode 0 same resolution, 1 avg_pool2d(2) of the activated source (varnet.py:98), 2 depth-to-space
+ * of a [N,4C,H/2,W/2] source (the ConvTranspose2d pixel shuffle), 3 nearest x2 (unet.py:130). */
+int san_tc_stage_act(void* xs, int N, int H, int W, int Cpad,
+                     const float* y0, const float* mu0, const float* a0, const float* b0, float slope0, int C0, int mode0,
+                     const float* y1, const float* mu1, const float* a1, const float* b1, float slope1, int C1, int mode1,
+                     const float* y2, const float* mu2, const float* a2, const float* b2, float slope2, int C2, int mode2,
+                     void* stream);
+/* x[N,C,H,W] = hi + lo of a staged tensor (input of the fp32 weight-gradient kernel) */
+int san_tc_unstage_act(const void* xs, float* x, int N, int C, int H, int W, void* stream);
+/* OIHW fp32 -> staged hi/lo; dgrad = 1 stages the flipped, transposed filter so that the data
+ * gradient is san_tc_conv run on the staged dY (then Cout/Cin below are the ORIGINAL ones) */
+int san_tc_stage_weights(const float* w, void* ws, int Cout, int Cin, int K, int dgrad, void* stream);
+/* y[N,Cout,H,W] (+ bias) = conv2d(staged x, staged w), stride 1, padding K/2, K in {1,3};
+ * Cin/Cout are the channel counts of THIS launch (for dgrad: Cin = original Cout, Cout = original Cin) */
+int san_tc_conv(const void* xs, const void* ws, const float* bias, float* y, int N, int H, int W, int Cin, int Cout,
+                int K, long long y_bs, void* stream);
+
 /* ---- normalisation / activation / resampling (varnet.py:98,139-146,235,257-273; unet.py:119-140) ---- */
 /* per-plane mean and centred sum of squares (two-pass) */
 int san_plane_stats(const float* x, float* mean, float* m2, int planes, int P, void* stream);

@@ -1,0 +1,543 @@
+// tcgen05 (5th-gen tensor core) implicit-GEMM convolution for the U-Net conv stacks, sm_100a only.
+//
+// Replaces the cuDNN convs of the reference's VarNet / alignment U-Nets (reference
+// varnet.py:139-146 3x3 no-bias, :75-80 1x1 + bias, :176-179 ConvTranspose2d 2x2 s2 run as a 1x1
+// conv + pixel shuffle; unet.py:119-140 3x3 / 1x1 + bias).
+//
+// Precision: fp32 parity needs more than one bf16 pass (single-pass BF16 is 2.9e-2
+// off after 12 cascades, BF16x3 is 7e-5).  Operands are split x = hi + lo (two bf16) and the
+// product is accumulated in fp32 TMEM as  hi*hi + lo*hi + hi*lo  (3 tcgen05.mma per K-step).
+//
+// Formulation ("flattened padded pixels"): activations are STAGED by san_tc_stage_act as
+//     Xs[n][hl][kg][slot][8]  bf16,   slot = (h+1)*Wp + (w+1),  Wp = W+2, Hp = H+2, zero border,
+//     hl = 0 (hi) / 1 (lo), kg = channel group of 8 (Cin padded to a multiple of 16 with zeros).
+// For one (hl, kg) a span of image rows is ONE contiguous byte range, so the producer warp moves it
+// with a single TMA bulk copy (cp.async.bulk, UBLKCP), and in shared memory it is exactly the
+// canonical no-swizzle K-major UMMA operand: 8 channels = 16 B per pixel row, uniform 16 B row
+// pitch (SBO = 128 B), channel groups LBO apart.  Output pixel q = r*Wp + x of a strip of R rows
+// needs, for tap (dy, dx), the operand row  q + dy*Wp + dx: a 3x3 tap is just a different START
+// ADDRESS of the same staged tile -- no im2col copies, each input element is loaded once per
+// strip.  Columns x >= W (2 per row) are computed and dropped (0.6 % waste at W = 320).
+//
+// Work unit = (image n, strip of R rows, N-split); persistent CTAs walk units.  Warp roles:
+//   warp 0      TMA producer  (bulk copies of the A row span + the B weight block per K-step)
+//   warp 1      TMEM allocator + single-thread tcgen05.mma issuer
+//   warps 2..5  epilogue: tcgen05.ld the fp32 accumulators, + bias, store NCHW fp32 (coalesced:
+//               TMEM lane = pixel, so a warp writes 32 consecutive pixels of one channel)
+// Pipelines: smem full/empty per K-step stage, TMEM accumulator full/empty (double-buffered when
+// 2*T*Npad <= 512 columns) so the epilogue of unit i overlaps the MMAs of unit i+1.
+#include <cuda_bf16.h>
+
+#include "san_common.cuh"
+#include "../../include/san_b200.h"
+
+namespace {
+
+// ------------------------------------------------------------------------------------------ PTX
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred P1;\n\t"
+      "WAIT_LOOP:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t"
+      "@P1 bra DONE;\n\t"
+      "bra WAIT_LOOP;\n\t"
+      "DONE:\n\t"
+      "}" ::"r"(bar),
+      "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+               "l"(src), "r"(bytes), "r"(bar)
+               : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_mma_bf16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                            uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "}" ::"r"(d_tmem),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void tc_ld8(uint32_t taddr, float* v) {
+  uint32_t r0, r1, r2, r3, r4, r5, r6, r7;
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3), "=r"(r4), "=r"(r5), "=r"(r6), "=r"(r7)
+               : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+  v[0] = __uint_as_float(r0); v[1] = __uint_as_float(r1); v[2] = __uint_as_float(r2); v[3] = __uint_as_float(r3);
+  v[4] = __uint_as_float(r4); v[5] = __uint_as_float(r5); v[6] = __uint_as_float(r6); v[7] = __uint_as_float(r7);
+}
+
+// UMMA shared-memory descriptor, no swizzle, K-major (cute::UMMA::SmemDescriptor): start address,
+// leading byte offset (between the two 8-element K groups of one K=16 step), stride byte offset
+// (between 8-row groups), all in 16 B units; version 1 (bit 46); layout type 0 (bits 61..63).
+__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16) |
+         ((uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32) | (1ull << 46);
+}
+// Instruction descriptor (cute::UMMA::InstrDescriptor): D fp32 (bit 4), A/B bf16 (bits 7, 10),
+// both K-major, N>>3 at bit 17, M>>4 at bit 24.
+__host__ __device__ inline uint32_t umma_idesc_bf16(int M, int N) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+// ------------------------------------------------------------------------------------ geometry
+constexpr int TC_THREADS = 192;
+constexpr int TC_SMEM_HEADER = 256;   // barriers + tmem pointer
+constexpr int TC_SMEM_MAX = 225 * 1024;
+constexpr int TC_NMAX = 160;          // largest UMMA N used per unit
+
+struct TcGeom {
+  int Cin_pad, KG, KS;     // input channels padded to 16; groups of 8; K-steps of 16
+  int nsplit, Npad;        // output channels split into nsplit units of Npad (multiple of 16)
+  int Wp, Hp, PS;          // padded width/height, pixel slots per image
+  int R, T, S_alloc;       // rows per strip, 128-pixel M-tiles per strip, smem slots per (hl, kk)
+  int strips, stages, acc_stages;
+  int a_bytes, b_bytes, stage_bytes, smem_bytes;
+};
+
+inline int pad16(int c) { return (c + 15) / 16 * 16; }
+
+bool tc_geometry(int H, int W, int Cin, int Cout, int K, TcGeom* g) {
+  if (K != 1 && K != 3) return false;
+  g->Cin_pad = pad16(Cin); g->KG = g->Cin_pad / 8; g->KS = g->Cin_pad / 16;
+  g->nsplit = (pad16(Cout) + TC_NMAX - 1) / TC_NMAX;
+  g->Npad = pad16((Cout + g->nsplit - 1) / g->nsplit);
+  g->Wp = W + 2; g->Hp = H + 2; g->PS = g->Hp * g->Wp;
+  const int ntaps = K * K;
+  g->b_bytes = ntaps * 4 * g->Npad * 16;
+  int bestR = 0;
+  double best = -1.0;
+  for (int R = 1; R <= H; ++R) {
+    const int T = (R * g->Wp + 127) / 128;
+    if (T * g->Npad > 512) break;
+    const int S = ((128 * T + 2 * g->Wp + 2) + 7) / 8 * 8;
+    const int stage = 4 * S * 16 + g->b_bytes;
+    if (2 * stage + TC_SMEM_HEADER > TC_SMEM_MAX) break;
+    // useful MMA rows x re-read factor of the input rows (halo) x tail waste of the last strip
+    const int strips = (H + R - 1) / R;
+    const double eff = ((double)R * W / (128.0 * T)) * ((double)R / (R + 2 * (K / 2))) * ((double)H / (strips * R));
+    if (eff > best + 1e-9) { best = eff; bestR = R; }
+  }
+  if (bestR == 0) return false;
+  g->R = bestR;
+  g->T = (g->R * g->Wp + 127) / 128;
+  g->S_alloc = ((128 * g->T + 2 * g->Wp + 2) + 7) / 8 * 8;
+  g->a_bytes = 4 * g->S_alloc * 16;
+  g->stage_bytes = g->a_bytes + g->b_bytes;
+  g->stages = (TC_SMEM_MAX - TC_SMEM_HEADER) / g->stage_bytes;
+  if (g->stages > 4) g->stages = 4;
+  if (g->stages < 2) return false;
+  g->strips = (H + g->R - 1) / g->R;
+  g->acc_stages = (2 * g->T * g->Npad <= 512) ? 2 : 1;
+  g->smem_bytes = TC_SMEM_HEADER + g->stages * g->stage_bytes;
+  if (g->smem_bytes < 120 * 1024) g->smem_bytes = 120 * 1024;  // one CTA per SM (each allocates all 512 TMEM columns)
+  return true;
+}
+
+struct ConvTcParams {
+  const __nv_bfloat16* xs;  // staged activations [N][2][KG][PS][8]
+  const __nv_bfloat16* ws;  // staged weights [nsplit][KS][ntaps][2][2][Npad][8]
+  const float* bias;        // [Cout] or null
+  float* y;                 // [N][Cout][H][W] (batch stride y_bs)
+  long long y_bs;
+  int N, H, W, Cout, ntaps;
+  int nunits;
+  TcGeom g;
+};
+
+// ---------------------------------------------------------------------------------- main kernel
+__global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const ConvTcParams p) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  const TcGeom& g = p.g;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // header: full[4] empty[4] acc_full[2] acc_empty[2] (8 B each) | tmem base (4 B)
+  const uint32_t hdr = smem_u32(smem);
+  const uint32_t bar_full = hdr, bar_empty = hdr + 32, bar_accf = hdr + 64, bar_acce = hdr + 80;
+  volatile uint32_t* tmem_slot = (volatile uint32_t*)(smem + 96);
+  const uint32_t stage0 = hdr + TC_SMEM_HEADER;
+
+  if (warp == 0 && lane == 0) {
+    for (int i = 0; i < g.stages; ++i) { mbar_init(bar_full + 8 * i, 1); mbar_init(bar_empty + 8 * i, 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(bar_accf + 8 * i, 1); mbar_init(bar_acce + 8 * i, 4); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32((void*)tmem_slot)),
+                 "r"(512)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int units_per_image = g.strips * g.nsplit;
+  const long long plane_elems = (long long)g.PS * 8;  // elements of one (n, hl, kg) plane
+
+  if (warp == 0) {
+    // ================================ TMA producer ================================
+    if (lane == 0) {
+      int s = 0;
+      uint32_t ph = 0;
+      for (int u = blockIdx.x; u < p.nunits; u += gridDim.x) {
+        const int n = u / units_per_image;
+        const int rem = u - n * units_per_image;
+        const int ns = rem / g.strips, st = rem - ns * g.strips;
+        const int y0 = st * g.R;
+        const int rows_in = min(g.R + 2, g.Hp - y0);
+        const uint32_t bytesA = (uint32_t)rows_in * g.Wp * 16;
+        for (int ks = 0; ks < g.KS; ++ks) {
+          mbar_wait(bar_empty + 8 * s, ph ^ 1);
+          const uint32_t sbase = stage0 + (uint32_t)s * g.stage_bytes;
+          mbar_expect_tx(bar_full + 8 * s, 4 * bytesA + (uint32_t)g.b_bytes);
+#pragma unroll
+          for (int hl = 0; hl < 2; ++hl)
+#pragma unroll
+            for (int kk = 0; kk < 2; ++kk) {
+              const __nv_bfloat16* src =
+                  p.xs + ((long long)(n * 2 + hl) * g.KG + 2 * ks + kk) * plane_elems + (long long)y0 * g.Wp * 8;
+              bulk_g2s(sbase + (uint32_t)(hl * 2 + kk) * g.S_alloc * 16, src, bytesA, bar_full + 8 * s);
+            }
+          const __nv_bfloat16* wsrc = p.ws + ((long long)ns * g.KS + ks) * (g.b_bytes / 2);
+          bulk_g2s(sbase + g.a_bytes, wsrc, (uint32_t)g.b_bytes, bar_full + 8 * s);
+          if (++s == g.stages) { s = 0; ph ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ================================ MMA issuer ==================================
+    if (lane == 0) {
+      const uint32_t idesc = umma_idesc_bf16(128, g.Npad);
+      const uint32_t lbo_a = (uint32_t)g.S_alloc * 16, lbo_b = (uint32_t)g.Npad * 16;
+      int s = 0, as = 0;
+      uint32_t ph = 0, aph = 0;
+      for (int u = blockIdx.x; u < p.nunits; u += gridDim.x) {
+        mbar_wait(bar_acce + 8 * as, aph ^ 1);
+        tc_fence_after();
+        const uint32_t acc0 = tmem_base + (uint32_t)(as * g.T * g.Npad);
+        for (int ks = 0; ks < g.KS; ++ks) {
+          mbar_wait(bar_full + 8 * s, ph);
+          tc_fence_after();
+          const uint32_t a_s = stage0 + (uint32_t)s * g.stage_bytes;
+          const uint32_t b_s = a_s + g.a_bytes;
+          for (int t = 0; t < g.T; ++t) {
+            const uint32_t d = acc0 + (uint32_t)(t * g.Npad);
+            for (int tap = 0; tap < p.ntaps; ++tap) {
+              const int off = (p.ntaps == 9) ? (tap / 3) * g.Wp + (tap % 3) : g.Wp + 1;
+              const uint32_t a_row = a_s + (uint32_t)(t * 128 + off) * 16;
+              const uint32_t b_tap = b_s + (uint32_t)(tap * 4) * g.Npad * 16;
+#pragma unroll
+              for (int sp = 0; sp < 3; ++sp) {
+                // hi*hi, lo*hi, hi*lo
+                const uint32_t a_addr = a_row + (sp == 1 ? 2u * g.S_alloc * 16 : 0u);
+                const uint32_t b_addr = b_tap + (sp == 2 ? 2u * g.Npad * 16 : 0u);
+                tc_mma_bf16(d, umma_desc(a_addr, lbo_a, 128), umma_desc(b_addr, lbo_b, 128), idesc,
+                            (ks | tap | sp) != 0);
+              }
+            }
+          }
+          tc_commit(bar_empty + 8 * s);  // frees the smem stage when these MMAs retire
+          if (++s == g.stages) { s = 0; ph ^= 1; }
+        }
+        tc_commit(bar_accf + 8 * as);    // accumulators of this unit complete
+        if (++as == g.acc_stages) { as = 0; aph ^= 1; }
+      }
+    }
+  } else {
+    // ================================ epilogue ====================================
+    const int wq = warp & 3;  // TMEM lane quarter this warp may access
+    int as = 0;
+    uint32_t aph = 0;
+    const long long HW = (long long)p.H * p.W;
+    for (int u = blockIdx.x; u < p.nunits; u += gridDim.x) {
+      const int n = u / units_per_image;
+      const int rem = u - n * units_per_image;
+      const int ns = rem / g.strips, st = rem - ns * g.strips;
+      const int y0 = st * g.R;
+      const int c_base = ns * g.Npad;
+      const int c_cnt = min(g.Npad, p.Cout - c_base);
+      mbar_wait(bar_accf + 8 * as, aph);
+      tc_fence_after();
+      float* yn = p.y + (long long)n * p.y_bs;
+      for (int t = 0; t < g.T; ++t) {
+        const int q = t * 128 + wq * 32 + lane;
+        const int r = q / g.Wp, x = q - r * g.Wp;
+        const int yy = y0 + r;
+        const bool valid = (r < g.R) && (x < p.W) && (yy < p.H);
+        float* dst = yn + (long long)yy * p.W + x;
+        const uint32_t trow = tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)(as * g.T * g.Npad + t * g.Npad);
+        for (int c0 = 0; c0 < c_cnt; c0 += 8) {
+          float v[8];
+          tc_ld8(trow + c0, v);
+          if (valid) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const int c = c0 + j;
+              if (c < c_cnt) {
+                const float bv = p.bias ? __ldg(p.bias + c_base + c) : 0.f;
+                dst[(long long)(c_base + c) * HW] = v[j] + bv;
+              }
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_acce + 8 * as);
+      if (++as == g.acc_stages) { as = 0; aph ^= 1; }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
+  }
+}
+
+// ------------------------------------------------------------------------- operand staging
+struct StageSrc {
+  const float* y;    // source tensor (fp32 NCHW at the source resolution)
+  const float* mu;   // per-plane centre, scale, shift (null = identity); plane = n*C + c
+  const float* a;
+  const float* b;
+  float slope;       // leaky slope (1 = none)
+  int C;             // channels this source contributes
+  int mode;          // 0 direct, 1 avg-pool 2x2 of the activated source (source is 2H x 2W),
+                     // 2 depth-to-space (source [N,4C,H/2,W/2]), 3 nearest x2 (source is H/2 x W/2)
+};
+struct StageArgs {
+  StageSrc s[3];
+  int nsrc;
+  __nv_bfloat16* xs;
+  int N, H, W, Wp, PS, KG;
+};
+
+__device__ __forceinline__ float act1(float v, float mu, float a, float b, float slope) {
+  const float z = fmaf(a, v - mu, b);
+  return z > 0.f ? z : z * slope;
+}
+
+// one thread = one pixel slot x one channel group of 8: two 16 B stores (hi, lo)
+__global__ void __launch_bounds__(256) stage_act_kernel(const StageArgs A) {
+  const long long total = (long long)A.N * A.KG * A.PS;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int slot = (int)(i % A.PS);
+    const long long t = i / A.PS;
+    const int kg = (int)(t % A.KG);
+    const int n = (int)(t / A.KG);
+    const int hp = slot / A.Wp, wp = slot - hp * A.Wp;
+    const int h = hp - 1, w = wp - 1;
+    float v[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = 0.f;
+    if (h >= 0 && h < A.H && w >= 0 && w < A.W) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        int c = kg * 8 + j;
+        int si = 0;
+        while (si < A.nsrc && c >= A.s[si].C) { c -= A.s[si].C; ++si; }
+        if (si >= A.nsrc) continue;
+        const StageSrc& S = A.s[si];
+        const long long plane = (long long)n * S.C + c;
+        float mu = 0.f, a = 1.f, b = 0.f;
+        if (S.a) { mu = S.mu ? __ldg(S.mu + plane) : 0.f; a = __ldg(S.a + plane); b = S.b ? __ldg(S.b + plane) : 0.f; }
+        if (S.mode == 0) {
+          v[j] = act1(__ldg(S.y + (plane * A.H + h) * A.W + w), mu, a, b, S.slope);
+        } else if (S.mode == 1) {
+          const int Ws2 = 2 * A.W;
+          const float* q = S.y + (plane * (2 * A.H) + 2 * h) * Ws2 + 2 * w;
+          const float2 r0 = __ldg((const float2*)q), r1 = __ldg((const float2*)(q + Ws2));
+          v[j] = 0.25f * ((act1(r0.x, mu, a, b, S.slope) + act1(r0.y, mu, a, b, S.slope)) +
+                          (act1(r1.x, mu, a, b, S.slope) + act1(r1.y, mu, a, b, S.slope)));
+        } else if (S.mode == 2) {
+          const int Hs = A.H / 2, Wsrc = A.W / 2;
+          const long long sp = ((long long)n * S.C * 4 + c * 4 + (h & 1) * 2 + (w & 1));
+          v[j] = act1(__ldg(S.y + (sp * Hs + (h >> 1)) * Wsrc + (w >> 1)), mu, a, b, S.slope);
+        } else {
+          const int Hs = A.H / 2, Wsrc = A.W / 2;
+          v[j] = act1(__ldg(S.y + (plane * Hs + (h >> 1)) * Wsrc + (w >> 1)), mu, a, b, S.slope);
+        }
+      }
+    }
+    __align__(16) __nv_bfloat16 hi[8], lo[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      hi[j] = __float2bfloat16_rn(v[j]);
+      lo[j] = __float2bfloat16_rn(v[j] - __bfloat162float(hi[j]));
+    }
+    const long long o_hi = (((long long)(n * 2 + 0) * A.KG + kg) * A.PS + slot) * 8;
+    const long long o_lo = (((long long)(n * 2 + 1) * A.KG + kg) * A.PS + slot) * 8;
+    *(uint4*)(A.xs + o_hi) = *(const uint4*)hi;
+    *(uint4*)(A.xs + o_lo) = *(const uint4*)lo;
+  }
+}
+
+// staged activations back to fp32 NCHW (x = hi + lo): feeds the fp32 weight-gradient kernel
+__global__ void __launch_bounds__(256) unstage_act_kernel(const __nv_bfloat16* __restrict__ xs, float* __restrict__ x,
+                                                          int N, int C, int H, int W, int KG) {
+  const int Wp = W + 2, PS = (H + 2) * Wp;
+  const long long total = (long long)N * C * H * W;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int w = (int)(i % W);
+    long long t = i / W;
+    const int h = (int)(t % H);
+    t /= H;
+    const int c = (int)(t % C);
+    const int n = (int)(t / C);
+    const int slot = (h + 1) * Wp + w + 1;
+    const long long o_hi = (((long long)(n * 2 + 0) * KG + (c >> 3)) * PS + slot) * 8 + (c & 7);
+    const long long o_lo = (((long long)(n * 2 + 1) * KG + (c >> 3)) * PS + slot) * 8 + (c & 7);
+    x[i] = __bfloat162float(xs[o_hi]) + __bfloat162float(xs[o_lo]);
+  }
+}
+
+// weights OIHW fp32 -> Ws[nsplit][KS][ntaps][hl][kk][Npad][8] bf16 hi/lo.
+// dgrad = 1: the transposed, spatially flipped filter (data gradient = the same conv run on dY):
+// "output" channel = original ci, "input" channel = original co.
+__global__ void stage_weights_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ ws, int Cout, int Cin,
+                                     int KK, int dgrad, int nsplit, int KS, int Npad) {
+  const int Co_k = dgrad ? Cin : Cout;   // kernel-view output channels
+  const int Ci_k = dgrad ? Cout : Cin;   // kernel-view input channels
+  const long long total = (long long)nsplit * KS * KK * 2 * 2 * Npad * 8;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    long long t = i;
+    const int j = (int)(t % 8); t /= 8;
+    const int nn = (int)(t % Npad); t /= Npad;
+    const int kk = (int)(t % 2); t /= 2;
+    const int hl = (int)(t % 2); t /= 2;
+    const int tap = (int)(t % KK); t /= KK;
+    const int ks = (int)(t % KS);
+    const int ns = (int)(t / KS);
+    const int co = ns * Npad + nn;
+    const int ci = ks * 16 + kk * 8 + j;
+    float v = 0.f;
+    if (co < Co_k && nn < Npad && ci < Ci_k) {
+      if (!dgrad) v = w[((long long)co * Cin + ci) * KK + tap];
+      else v = w[((long long)ci * Cin + co) * KK + (KK - 1 - tap)];
+    }
+    const __nv_bfloat16 hi = __float2bfloat16_rn(v);
+    ws[i] = hl ? __float2bfloat16_rn(v - __bfloat162float(hi)) : hi;
+  }
+}
+
+inline int ew_blocks(long long total) {
+  long long b = (total + 255) / 256;
+  const long long cap = (long long)san_num_sms() * 16;
+  return (int)(b < cap ? (b < 1 ? 1 : b) : cap);
+}
+
+}  // namespace
+
+extern "C" {
+
+long long san_tc_staged_act_elems(int N, int H, int W, int C) {
+  return (long long)N * 2 * (pad16(C) / 8) * (long long)(H + 2) * (W + 2) * 8;
+}
+
+long long san_tc_staged_weight_elems(int Cout, int Cin, int K) {
+  TcGeom g;
+  if (!tc_geometry(8, 8, Cin, Cout, K, &g)) return -1;
+  return (long long)g.nsplit * g.KS * K * K * 4 * g.Npad * 8;
+}
+
+int san_tc_supported(int H, int W, int Cin, int Cout, int K) {
+  TcGeom g;
+  return tc_geometry(H, W, Cin, Cout, K, &g) ? 1 : 0;
+}
+
+int san_tc_stage_act(void* xs, int N, int H, int W, int Cpad,
+                     const float* y0, const float* mu0, const float* a0, const float* b0, float slope0, int C0, int mode0,
+                     const float* y1, const float* mu1, const float* a1, const float* b1, float slope1, int C1, int mode1,
+                     const float* y2, const float* mu2, const float* a2, const float* b2, float slope2, int C2, int mode2,
+                     void* stream) {
+  SAN_CHECK_ARG(xs && y0 && N > 0 && H > 0 && W > 0 && Cpad % 16 == 0 && C0 > 0, "san_tc_stage_act: bad args");
+  StageArgs A{};
+  A.s[0] = StageSrc{y0, mu0, a0, b0, slope0, C0, mode0};
+  A.nsrc = 1;
+  if (y1) { A.s[1] = StageSrc{y1, mu1, a1, b1, slope1, C1, mode1}; A.nsrc = 2; }
+  if (y2) { SAN_CHECK_ARG(y1, "san_tc_stage_act: source 2 without source 1"); A.s[2] = StageSrc{y2, mu2, a2, b2, slope2, C2, mode2}; A.nsrc = 3; }
+  int ctot = 0;
+  for (int i = 0; i < A.nsrc; ++i) {
+    ctot += A.s[i].C;
+    SAN_CHECK_ARG(A.s[i].mode >= 0 && A.s[i].mode <= 3, "san_tc_stage_act: bad mode");
+    if (A.s[i].mode >= 2) SAN_CHECK_ARG(H % 2 == 0 && W % 2 == 0, "san_tc_stage_act: odd size with up-sampling source");
+  }
+  SAN_CHECK_ARG(ctot <= Cpad, "san_tc_stage_act: %d channels exceed Cpad %d", ctot, Cpad);
+  A.xs = (__nv_bfloat16*)xs;
+  A.N = N; A.H = H; A.W = W; A.Wp = W + 2; A.PS = (H + 2) * (W + 2); A.KG = Cpad / 8;
+  const long long total = (long long)N * A.KG * A.PS;
+  stage_act_kernel<<<ew_blocks(total), 256, 0, (cudaStream_t)stream>>>(A);
+  SAN_LAUNCH_CHECK();
+  return SAN_OK;
+}
+
+int san_tc_unstage_act(const void* xs, float* x, int N, int C, int H, int W, void* stream) {
+  SAN_CHECK_ARG(xs && x && N > 0 && C > 0 && H > 0 && W > 0, "san_tc_unstage_act: bad args");
+  const long long total = (long long)N * C * H * W;
+  unstage_act_kernel<<<ew_blocks(total), 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)xs, x, N, C, H, W,
+                                                                         pad16(C) / 8);
+  SAN_LAUNCH_CHECK();
+  return SAN_OK;
+}
+
+int san_tc_stage_weights(const float* w, void* ws, int Cout, int Cin, int K, int dgrad, void* stream) {
+  SAN_CHECK_ARG(w && ws && Cout > 0 && Cin > 0 && (K == 1 || K == 3), "san_tc_stage_weights: bad args");
+  TcGeom g;
+  const int Co_k = dgrad ? Cin : Cout, Ci_k = dgrad ? Cout : Cin;
+  SAN_CHECK_ARG(tc_geometry(8, 8, Ci_k, Co_k, K, &g), "san_tc_stage_weights: unsupported shape");
+  const long long total = (long long)g.nsplit * g.KS * K * K * 4 * g.Npad * 8;
+  stage_weights_kernel<<<ew_blocks(total), 256, 0, (cudaStream_t)stream>>>(w, (__nv_bfloat16*)ws, Cout, Cin, K * K, dgrad,
+                                                                           g.nsplit, g.KS, g.Npad);
+  SAN_LAUNCH_CHECK();
+  return SAN_OK;
+}
+
+int san_tc_conv(const void* xs, const void* ws, const float* bias, float* y, int N, int H, int W, int Cin, int Cout,
+                int K, long long y_bs, void* stream) {
+  SAN_CHECK_ARG(xs && ws && y && N > 0 && H > 0 && W > 0 && Cin > 0 && Cout > 0, "san_tc_conv: bad args");
+  ConvTcParams p{};
+  SAN_CHECK_ARG(tc_geometry(H, W, Cin, Cout, K, &p.g), "san_tc_conv: unsupported shape H=%d W=%d Cin=%d Cout=%d K=%d", H, W,
+                Cin, Cout, K);
+  p.xs = (const __nv_bfloat16*)xs; p.ws = (const __nv_bfloat16*)ws; p.bias = bias; p.y = y;
+  p.y_bs = y_bs > 0 ? y_bs : (long long)Cout * H * W;
+  p.N = N; p.H = H; p.W = W; p.Cout = Cout; p.ntaps = K * K;
+  p.nunits = N * p.g.strips * p.g.nsplit;
+  static bool attr_set = false;
+  if (!attr_set) {
+    SAN_CUDA(cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_MAX));
+    attr_set = true;
+  }
+  const int grid = p.nunits < san_num_sms() ? p.nunits : san_num_sms();
+  conv_tc_kernel<<<grid, TC_THREADS, p.g.smem_bytes, (cudaStream_t)stream>>>(p);
+  SAN_LAUNCH_CHECK();
+  return SAN_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,118 @@
+"""Parity of the tcgen05 BF16x3 convolution path (csrc/conv_tc.cu) through the C ABI: operand staging
+(fused norm + LeakyReLU + concat + pool / pixel-shuffle / nearest-up), forward, data gradient.
+Reference = torch fp64 of the same op (reference call sites varnet.py:98,116,139-146,176-181;
+unet.py:119-140).  Bar: BF16x3 keeps ~2^-16 relative operand error -> 2e-5 relative L2 on a conv."""
+import math
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+from conftest import rel_l2
+
+pytestmark = pytest.mark.gpu
+
+
+def _lib():
+    from spatialalignmentnetwork_b200 import _lib
+    return _lib
+
+
+def stage(x, Cpad=None):
+    """fp32 NCHW -> staged hi/lo tensor via san_tc_stage_act (single identity source)."""
+    L = _lib()
+    N, C, H, W = x.shape
+    xs = torch.empty(L.lib().san_tc_staged_act_elems(N, H, W, C), dtype=torch.bfloat16, device=x.device)
+    Cpad = (C + 15) // 16 * 16
+    L.call("tc_stage_act", xs, N, H, W, Cpad, x, None, None, None, 1.0, C, 0,
+           None, None, None, None, 1.0, 0, 0, None, None, None, None, 1.0, 0, 0)
+    return xs
+
+
+def conv_tc(x, w, bias=None, dgrad=False):
+    L = _lib()
+    N, Cin, H, W = x.shape
+    Cout, Cin_w, K, _ = w.shape
+    xs = stage(x)
+    ws = torch.empty(L.lib().san_tc_staged_weight_elems(Cin_w if dgrad else Cout, Cout if dgrad else Cin_w, K),
+                     dtype=torch.bfloat16, device=x.device)
+    L.call("tc_stage_weights", w, ws, Cout, Cin_w, K, int(dgrad))
+    co = Cin_w if dgrad else Cout
+    y = torch.empty(N, co, H, W, dtype=torch.float32, device=x.device)
+    L.call("tc_conv", xs, ws, bias, y, N, H, W, Cin, co, K, 0)
+    return y
+
+
+TC_CASES = [
+    # N, Cin, H, W, Cout, K, bias      (the layer shapes of the cascade / sens / align U-Nets, scaled down)
+    (2, 3, 32, 48, 18, 3, False), (1, 18, 64, 64, 18, 3, False), (2, 36, 40, 24, 36, 3, False),
+    (1, 72, 20, 20, 144, 3, False), (1, 144, 20, 20, 288, 3, False), (1, 288, 10, 12, 288, 3, False),
+    (2, 18, 32, 32, 2, 1, True), (1, 288, 10, 10, 576, 1, False), (2, 2, 33, 47, 32, 3, True),
+    (1, 96, 24, 40, 32, 3, True), (3, 64, 17, 23, 64, 1, True), (1, 18, 320, 320, 18, 3, False),
+]
+
+
+@pytest.mark.parametrize("case", TC_CASES)
+def test_tc_conv_fwd_and_dgrad(case):
+    N, Cin, H, W, Cout, K, has_bias = case
+    torch.manual_seed(21)
+    x = torch.randn(N, Cin, H, W)
+    w = torch.randn(Cout, Cin, K, K) / math.sqrt(Cin * K * K)
+    b = torch.randn(Cout) if has_bias else None
+    gy = torch.randn(N, Cout, H, W)
+    xr = x.double().requires_grad_(True)
+    yr = F.conv2d(xr, w.double(), b.double() if has_bias else None, padding=K // 2)
+    (yr * gy.double()).sum().backward()
+    y = conv_tc(x.cuda(), w.cuda(), b.cuda() if has_bias else None)
+    assert rel_l2(y, yr) < 2e-5
+    dx = conv_tc(gy.cuda(), w.cuda(), None, dgrad=True)
+    assert rel_l2(dx, xr.grad) < 2e-5
+
+
+def test_tc_stage_roundtrip_and_fused_sources():
+    """Staging = concat [InstanceNorm+LReLU(0.2) of a pixel-shuffled source, avg-pooled activated source,
+    identity source] with zero border / zero pad channels; un-staging returns hi + lo."""
+    L = _lib()
+    torch.manual_seed(22)
+    N, H, W = 2, 12, 20
+    ya = torch.randn(N, 4 * 5, H // 2, W // 2) * 2 + 1       # depth-to-space source, 5 channels
+    yb = torch.randn(N, 7, 2 * H, 2 * W) - 0.5               # pooled source, 7 channels
+    yc = torch.randn(N, 3, H, W)                             # identity source
+    # reference
+    a_sp = F.pixel_shuffle(ya.double(), 2)
+    ra = F.leaky_relu(F.instance_norm(a_sp, eps=1e-5), 0.2)
+    rb = F.avg_pool2d(F.leaky_relu(F.instance_norm(yb.double(), eps=1e-5), 0.2), 2)
+    ref = torch.cat([ra, rb, yc.double()], 1)
+    # coefficients (mu, a = rstd) per plane
+    mua, va = a_sp.mean((2, 3)), a_sp.var((2, 3), unbiased=False)
+    mub, vb = yb.double().mean((2, 3)), yb.double().var((2, 3), unbiased=False)
+    ca = [t.float().reshape(-1).cuda().contiguous() for t in (mua, 1 / torch.sqrt(va + 1e-5))]
+    cb = [t.float().reshape(-1).cuda().contiguous() for t in (mub, 1 / torch.sqrt(vb + 1e-5))]
+    C = 15
+    xs = torch.empty(L.lib().san_tc_staged_act_elems(N, H, W, C), dtype=torch.bfloat16, device="cuda")
+    L.call("tc_stage_act", xs, N, H, W, 16,
+           ya.cuda(), ca[0], ca[1], None, 0.2, 5, 2,
+           yb.cuda(), cb[0], cb[1], None, 0.2, 7, 1,
+           yc.cuda(), None, None, None, 1.0, 3, 0)
+    out = torch.empty(N, C, H, W, device="cuda")
+    L.call("tc_unstage_act", xs, out, N, C, H, W)
+    assert rel_l2(out, ref) < 2e-5
+    st = xs.view(N, 2, 2, H + 2, W + 2, 8).float()
+    assert st[:, :, :, 0].abs().max() == 0 and st[:, :, :, -1].abs().max() == 0      # zero border rows
+    assert st[:, :, :, :, 0].abs().max() == 0 and st[:, :, :, :, -1].abs().max() == 0  # zero border cols
+    assert st[:, :, 1, :, :, 7].abs().max() == 0                                       # pad channel 15
+
+
+def test_tc_conv_full_size_linearity():
+    """At the benchmark size (bs 8 here, 320x320, 18->18): conv(a*x1 + x2) = a*conv(x1) + conv(x2) and
+    agreement with the fp32 direct-conv kernel on the same inputs."""
+    L = _lib()
+    from spatialalignmentnetwork_b200 import ops
+    torch.manual_seed(23)
+    N, C, H, W = 8, 18, 320, 320
+    x1, x2 = torch.randn(N, C, H, W, device="cuda"), torch.randn(N, C, H, W, device="cuda")
+    w = torch.randn(C, C, 3, 3, device="cuda") / math.sqrt(C * 9)
+    y1, y2, y12 = conv_tc(x1, w), conv_tc(x2, w), conv_tc(0.5 * x1 + x2, w)
+    assert rel_l2(y12, 0.5 * y1 + y2) < 2e-5
+    yf = ops.Conv2d.apply(x1, w, None)
+    assert rel_l2(y1, yf) < 2e-5
