@@ -167,6 +167,56 @@ struct ConvTcParams {
   TcGeom g;
 };
 
+// ---------------------------------------------------------------------------------- MMA issue
+template <int NTAPS>
+__device__ __forceinline__ void mma_issue_loop(const ConvTcParams& p, const TcGeom& g, uint32_t tmem_base,
+                                               uint32_t stage0, uint32_t bar_full, uint32_t bar_empty,
+                                               uint32_t bar_accf, uint32_t bar_acce) {
+  const uint32_t idesc = umma_idesc_bf16(128, g.Npad);
+  // descriptor templates (address field = 0) and per-tap offsets in 16 B units
+  const uint64_t a_tmpl = umma_desc(0, (uint32_t)g.S_alloc * 16, 128);
+  const uint64_t b_tmpl = umma_desc(0, (uint32_t)g.Npad * 16, 128);
+  const uint32_t a_hi = (uint32_t)(a_tmpl >> 32), b_hi = (uint32_t)(b_tmpl >> 32);
+  const uint32_t a_lo0 = (uint32_t)a_tmpl, b_lo0 = (uint32_t)b_tmpl;
+  uint32_t tap_off[NTAPS];
+#pragma unroll
+  for (int tap = 0; tap < NTAPS; ++tap) tap_off[tap] = (NTAPS == 9) ? (uint32_t)((tap / 3) * g.Wp + (tap % 3)) : (uint32_t)(g.Wp + 1);
+  const uint32_t a_losplit = 2u * g.S_alloc;     // hi -> lo half of A, 16 B units
+  const uint32_t b_losplit = 2u * g.Npad;        // hi -> lo half of B
+  const uint32_t b_tapstride = 4u * g.Npad;
+  int s = 0, as = 0;
+  uint32_t ph = 0, aph = 0;
+  for (int u = blockIdx.x; u < p.nunits; u += gridDim.x) {
+    mbar_wait(bar_acce + 8 * as, aph ^ 1);
+    tc_fence_after();
+    const uint32_t acc0 = tmem_base + (uint32_t)(as * g.T * g.Npad);
+    for (int ks = 0; ks < g.KS; ++ks) {
+      mbar_wait(bar_full + 8 * s, ph);
+      tc_fence_after();
+      const uint32_t a_s = (stage0 + (uint32_t)s * g.stage_bytes) >> 4;   // 16 B units
+      const uint32_t b_s = a_s + ((uint32_t)g.a_bytes >> 4);
+      const uint32_t first = (ks != 0);
+      uint32_t d = acc0, a_t = a_lo0 + a_s;
+      for (int t = 0; t < g.T; ++t, d += g.Npad, a_t += 128) {
+#pragma unroll
+        for (int tap = 0; tap < NTAPS; ++tap) {
+          const uint32_t al = a_t + tap_off[tap];
+          const uint32_t bl = b_lo0 + b_s + tap * b_tapstride;
+          const uint64_t A_hi = ((uint64_t)a_hi << 32) | al, A_lo = ((uint64_t)a_hi << 32) | (al + a_losplit);
+          const uint64_t B_hi = ((uint64_t)b_hi << 32) | bl, B_lo = ((uint64_t)b_hi << 32) | (bl + b_losplit);
+          tc_mma_bf16(d, A_hi, B_hi, idesc, tap == 0 ? first : 1u);   // hi*hi
+          tc_mma_bf16(d, A_lo, B_hi, idesc, 1u);                      // lo*hi
+          tc_mma_bf16(d, A_hi, B_lo, idesc, 1u);                      // hi*lo
+        }
+      }
+      tc_commit(bar_empty + 8 * s);  // frees the smem stage when these MMAs retire
+      if (++s == g.stages) { s = 0; ph ^= 1; }
+    }
+    tc_commit(bar_accf + 8 * as);    // accumulators of this unit complete
+    if (++as == g.acc_stages) { as = 0; aph ^= 1; }
+  }
+}
+
 // ---------------------------------------------------------------------------------- main kernel
 __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const ConvTcParams p) {
   extern __shared__ __align__(128) uint8_t smem[];
@@ -229,42 +279,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const ConvTcPara
     }
   } else if (warp == 1) {
     // ================================ MMA issuer ==================================
+    // One thread issues every tcgen05.mma of the CTA, so the loop is written for issue rate: the
+    // shared-memory descriptors are built once and advanced by adding 16-byte-unit offsets to
+    // their low word; taps and the three hi/lo products are fully unrolled.
     if (lane == 0) {
-      const uint32_t idesc = umma_idesc_bf16(128, g.Npad);
-      const uint32_t lbo_a = (uint32_t)g.S_alloc * 16, lbo_b = (uint32_t)g.Npad * 16;
-      int s = 0, as = 0;
-      uint32_t ph = 0, aph = 0;
-      for (int u = blockIdx.x; u < p.nunits; u += gridDim.x) {
-        mbar_wait(bar_acce + 8 * as, aph ^ 1);
-        tc_fence_after();
-        const uint32_t acc0 = tmem_base + (uint32_t)(as * g.T * g.Npad);
-        for (int ks = 0; ks < g.KS; ++ks) {
-          mbar_wait(bar_full + 8 * s, ph);
-          tc_fence_after();
-          const uint32_t a_s = stage0 + (uint32_t)s * g.stage_bytes;
-          const uint32_t b_s = a_s + g.a_bytes;
-          for (int t = 0; t < g.T; ++t) {
-            const uint32_t d = acc0 + (uint32_t)(t * g.Npad);
-            for (int tap = 0; tap < p.ntaps; ++tap) {
-              const int off = (p.ntaps == 9) ? (tap / 3) * g.Wp + (tap % 3) : g.Wp + 1;
-              const uint32_t a_row = a_s + (uint32_t)(t * 128 + off) * 16;
-              const uint32_t b_tap = b_s + (uint32_t)(tap * 4) * g.Npad * 16;
-#pragma unroll
-              for (int sp = 0; sp < 3; ++sp) {
-                // hi*hi, lo*hi, hi*lo
-                const uint32_t a_addr = a_row + (sp == 1 ? 2u * g.S_alloc * 16 : 0u);
-                const uint32_t b_addr = b_tap + (sp == 2 ? 2u * g.Npad * 16 : 0u);
-                tc_mma_bf16(d, umma_desc(a_addr, lbo_a, 128), umma_desc(b_addr, lbo_b, 128), idesc,
-                            (ks | tap | sp) != 0);
-              }
-            }
-          }
-          tc_commit(bar_empty + 8 * s);  // frees the smem stage when these MMAs retire
-          if (++s == g.stages) { s = 0; ph ^= 1; }
-        }
-        tc_commit(bar_accf + 8 * as);    // accumulators of this unit complete
-        if (++as == g.acc_stages) { as = 0; aph ^= 1; }
-      }
+      if (p.ntaps == 9) mma_issue_loop<9>(p, g, tmem_base, stage0, bar_full, bar_empty, bar_accf, bar_acce);
+      else mma_issue_loop<1>(p, g, tmem_base, stage0, bar_full, bar_empty, bar_accf, bar_acce);
     }
   } else {
     // ================================ epilogue ====================================
@@ -341,15 +361,22 @@ __device__ __forceinline__ float act1(float v, float mu, float a, float b, float
   return z > 0.f ? z : z * slope;
 }
 
-// one thread = one pixel slot x one channel group of 8: two 16 B stores (hi, lo)
+// one thread = one pixel slot x one channel group of 8: two 16 B stores (hi, lo).
+// grid = (slot blocks, N*KG): no 64-bit divisions on the hot path.
 __global__ void __launch_bounds__(256) stage_act_kernel(const StageArgs A) {
-  const long long total = (long long)A.N * A.KG * A.PS;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
-       i += (long long)gridDim.x * blockDim.x) {
-    const int slot = (int)(i % A.PS);
-    const long long t = i / A.PS;
-    const int kg = (int)(t % A.KG);
-    const int n = (int)(t / A.KG);
+  const int n = blockIdx.y / A.KG, kg = blockIdx.y - n * A.KG;
+  // channel -> source lookup for the 8 channels of this group (uniform over the block)
+  int src_of[8], ch_of[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    int c = kg * 8 + j, si = 0;
+    while (si < A.nsrc && c >= A.s[si].C) { c -= A.s[si].C; ++si; }
+    src_of[j] = si < A.nsrc ? si : -1;
+    ch_of[j] = c;
+  }
+  const long long o_hi = ((long long)(n * 2 + 0) * A.KG + kg) * A.PS;
+  const long long o_lo = ((long long)(n * 2 + 1) * A.KG + kg) * A.PS;
+  for (int slot = blockIdx.x * blockDim.x + threadIdx.x; slot < A.PS; slot += gridDim.x * blockDim.x) {
     const int hp = slot / A.Wp, wp = slot - hp * A.Wp;
     const int h = hp - 1, w = wp - 1;
     float v[8];
@@ -358,11 +385,9 @@ __global__ void __launch_bounds__(256) stage_act_kernel(const StageArgs A) {
     if (h >= 0 && h < A.H && w >= 0 && w < A.W) {
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
-        int c = kg * 8 + j;
-        int si = 0;
-        while (si < A.nsrc && c >= A.s[si].C) { c -= A.s[si].C; ++si; }
-        if (si >= A.nsrc) continue;
-        const StageSrc& S = A.s[si];
+        if (src_of[j] < 0) continue;
+        const StageSrc& S = A.s[src_of[j]];
+        const int c = ch_of[j];
         const long long plane = (long long)n * S.C + c;
         float mu = 0.f, a = 1.f, b = 0.f;
         if (S.a) { mu = S.mu ? __ldg(S.mu + plane) : 0.f; a = __ldg(S.a + plane); b = S.b ? __ldg(S.b + plane) : 0.f; }
@@ -390,10 +415,8 @@ __global__ void __launch_bounds__(256) stage_act_kernel(const StageArgs A) {
       hi[j] = __float2bfloat16_rn(v[j]);
       lo[j] = __float2bfloat16_rn(v[j] - __bfloat162float(hi[j]));
     }
-    const long long o_hi = (((long long)(n * 2 + 0) * A.KG + kg) * A.PS + slot) * 8;
-    const long long o_lo = (((long long)(n * 2 + 1) * A.KG + kg) * A.PS + slot) * 8;
-    *(uint4*)(A.xs + o_hi) = *(const uint4*)hi;
-    *(uint4*)(A.xs + o_lo) = *(const uint4*)lo;
+    *(uint4*)(A.xs + (o_hi + slot) * 8) = *(const uint4*)hi;
+    *(uint4*)(A.xs + (o_lo + slot) * 8) = *(const uint4*)lo;
   }
 }
 
@@ -492,8 +515,11 @@ int san_tc_stage_act(void* xs, int N, int H, int W, int Cpad,
   SAN_CHECK_ARG(ctot <= Cpad, "san_tc_stage_act: %d channels exceed Cpad %d", ctot, Cpad);
   A.xs = (__nv_bfloat16*)xs;
   A.N = N; A.H = H; A.W = W; A.Wp = W + 2; A.PS = (H + 2) * (W + 2); A.KG = Cpad / 8;
-  const long long total = (long long)N * A.KG * A.PS;
-  stage_act_kernel<<<ew_blocks(total), 256, 0, (cudaStream_t)stream>>>(A);
+  SAN_CHECK_ARG((long long)N * A.KG <= 65535, "san_tc_stage_act: N*KG too large for grid.y");
+  int bx = (A.PS + 255) / 256;
+  const int want = (san_num_sms() * 8 + N * A.KG - 1) / (N * A.KG);   // >= 8 blocks per SM overall
+  if (bx > want) bx = want < 1 ? 1 : want;
+  stage_act_kernel<<<dim3(bx, N * A.KG), 256, 0, (cudaStream_t)stream>>>(A);
   SAN_LAUNCH_CHECK();
   return SAN_OK;
 }

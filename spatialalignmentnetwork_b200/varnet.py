@@ -13,8 +13,14 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
-from . import ops
+import os
+
+from . import ops, tc
 from .signal_utils import rss
+
+# SAN_TC=0 selects the fp32 CUDA-core conv kernels layer by layer (debug / A-B only); the default is
+# the fused tcgen05 path of tc.py.
+USE_TC = os.environ.get("SAN_TC", "1") != "0"
 
 _IN_EPS = 1e-5
 
@@ -94,6 +100,43 @@ class Unet(nn.Module):
 
     def forward(self, image: torch.Tensor) -> torch.Tensor:
         assert not torch.is_complex(image)
+        if USE_TC:
+            return self.forward_sources([image])
+        return self._forward_layerwise(image)
+
+    def forward_sources(self, images) -> torch.Tensor:
+        """Fused tcgen05 path.  ``images``: list of fp32 NCHW tensors whose channel concatenation is the
+        network input (so NormUnet never materialises ``cat([x, ref])``).  Every conv reads its operand
+        through ``tc.fused_conv``: InstanceNorm + LeakyReLU(0.2) of the producing layer, the 2x2 average
+        pooling (varnet.py:98), the ConvTranspose2d pixel shuffle (:176-179) and the skip concat (:116,
+        up-sampled first) are all applied while the operand tiles are staged."""
+        R = tc.Raw
+        h, w = images[0].shape[-2:]
+        assert h % (1 << self.num_pool_layers) == 0 and w % (1 << self.num_pool_layers) == 0, \
+            "fused path needs H, W divisible by 2**num_pool_layers (NormUnet pads to 16)"
+        srcs, modes = [R(im) for im in images], None
+        stack = []
+        for layer in self.down_sample_layers:
+            y1 = tc.fused_conv(srcs, layer.layers[0].weight, modes=modes)
+            y2 = R(tc.fused_conv([R(y1, "in", 0.2)], layer.layers[3].weight), "in", 0.2)
+            stack.append(y2)
+            srcs, modes = [y2], [tc.MODE_POOL]
+        y1 = tc.fused_conv(srcs, self.conv.layers[0].weight, modes=modes)
+        cur = R(tc.fused_conv([R(y1, "in", 0.2)], self.conv.layers[3].weight), "in", 0.2)
+        out = None
+        for transpose_conv, conv in zip(self.up_transpose_conv, self.up_conv):
+            skip = stack.pop()
+            wt = transpose_conv.layers[0].weight                       # [Cin, Cout, 2, 2]
+            w1 = wt.permute(1, 2, 3, 0).reshape(wt.shape[1] * 4, wt.shape[0], 1, 1)
+            y4 = R(tc.fused_conv([cur], w1), "in", 0.2, d2s=True)      # 1x1 conv to 4*Cout; shuffle on read
+            block = conv if isinstance(conv, ConvBlock) else conv[0]
+            y1 = tc.fused_conv([y4, skip], block.layers[0].weight)     # cat([up, skip]) (varnet.py:116)
+            cur = R(tc.fused_conv([R(y1, "in", 0.2)], block.layers[3].weight), "in", 0.2)
+            if not isinstance(conv, ConvBlock):
+                out = tc.fused_conv([cur], conv[1].weight, conv[1].bias)   # final 1x1 + bias (varnet.py:78)
+        return out
+
+    def _forward_layerwise(self, image: torch.Tensor) -> torch.Tensor:
         stack = []
         output = image
         for layer in self.down_sample_layers:
@@ -185,10 +228,10 @@ class NormUnet(nn.Module):
         if self.use_ref:
             assert ref_normed is not None
             r, _ = self.pad(ref_normed)
-            x = torch.cat([x, r], dim=1)
+            x = self.unet.forward_sources([x, r]) if USE_TC else self.unet(torch.cat([x, r], dim=1))
         else:
             assert ref_normed is None
-        x = self.unet(x)
+            x = self.unet(x)
         x = self.unpad(x, *pad_sizes)
         return self.unnorm(x, mean, std)
 

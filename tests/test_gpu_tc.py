@@ -116,3 +116,82 @@ def test_tc_conv_full_size_linearity():
     assert rel_l2(y12, 0.5 * y1 + y2) < 2e-5
     yf = ops.Conv2d.apply(x1, w, None)
     assert rel_l2(y1, yf) < 2e-5
+
+
+def _fused_case(kind):
+    """One fused block vs torch fp64: forward, gradients wrt every raw input, the weight and the bias."""
+    from spatialalignmentnetwork_b200 import tc
+    torch.manual_seed(31)
+    N, H, W = 2, 16, 24
+    if kind == "in_direct":          # conv(lrelu(IN(y)))
+        ys = [torch.randn(N, 18, H, W) * 2 + 0.5]
+        def ref(y):
+            return F.leaky_relu(F.instance_norm(y[0], eps=1e-5), 0.2)
+        def srcs(y):
+            return [tc.Raw(y[0], "in", 0.2)], None
+        Cin = 18
+    elif kind == "in_pool":          # conv(avgpool(lrelu(IN(y))))
+        ys = [torch.randn(N, 18, 2 * H, 2 * W) + 0.3]
+        def ref(y):
+            return F.avg_pool2d(F.leaky_relu(F.instance_norm(y[0], eps=1e-5), 0.2), 2)
+        def srcs(y):
+            return [tc.Raw(y[0], "in", 0.2)], [tc.MODE_POOL]
+        Cin = 18
+    elif kind == "d2s_skip":         # conv(cat[lrelu(IN(pixel_shuffle(y4))), lrelu(IN(skip))])
+        ys = [torch.randn(N, 4 * 18, H // 2, W // 2) - 0.2, torch.randn(N, 18, H, W) * 1.5]
+        def ref(y):
+            up = F.leaky_relu(F.instance_norm(F.pixel_shuffle(y[0], 2), eps=1e-5), 0.2)
+            return torch.cat([up, F.leaky_relu(F.instance_norm(y[1], eps=1e-5), 0.2)], 1)
+        def srcs(y):
+            return [tc.Raw(y[0], "in", 0.2, d2s=True), tc.Raw(y[1], "in", 0.2)], None
+        Cin = 36
+    else:                            # identity sources: conv(cat[x, r])
+        ys = [torch.randn(N, 2, H, W), torch.randn(N, 1, H, W)]
+        def ref(y):
+            return torch.cat(y, 1)
+        def srcs(y):
+            return [tc.Raw(t) for t in y], None
+        Cin = 3
+    Cout, K = 18, 3
+    w = torch.randn(Cout, Cin, K, K) / math.sqrt(Cin * K * K)
+    b = torch.randn(Cout)
+    gy = torch.randn(N, Cout, H, W)
+    yr = [t.double().requires_grad_(True) for t in ys]
+    wr, br = w.double().requires_grad_(True), b.double().requires_grad_(True)
+    outr = F.conv2d(ref(yr), wr, br, padding=1)
+    (outr * gy.double()).sum().backward()
+    yc = [t.cuda().requires_grad_(True) for t in ys]
+    wc, bc = w.cuda().requires_grad_(True), b.cuda().requires_grad_(True)
+    s, modes = srcs(yc)
+    outc = tc.fused_conv(s, wc, bc, modes=modes)
+    (outc * gy.cuda()).sum().backward()
+    assert rel_l2(outc, outr) < 2e-5
+    for a, r in zip(yc, yr):
+        assert rel_l2(a.grad, r.grad) < 5e-5
+    assert rel_l2(wc.grad, wr.grad) < 2e-5 and rel_l2(bc.grad, br.grad) < 2e-5
+
+
+@pytest.mark.parametrize("kind", ["in_direct", "in_pool", "d2s_skip", "identity"])
+def test_fused_conv_block(kind):
+    _fused_case(kind)
+
+
+def test_fused_unet_matches_layerwise_fp32():
+    """The fused tcgen05 U-Net against the layer-by-layer fp32 CUDA-core path on the same weights
+    (forward 2e-5; gradients within the kink noise documented in test_gpu_models.py)."""
+    from spatialalignmentnetwork_b200.varnet import Unet
+    torch.manual_seed(32)
+    net = Unet(3, 2, 18, 4).cuda()
+    x = torch.randn(2, 3, 64, 64, device="cuda")
+    g = torch.randn(2, 2, 64, 64, device="cuda")
+    res = []
+    for fused in (True, False):
+        xx = x.clone().requires_grad_(True)
+        net.zero_grad()
+        out = net.forward_sources([xx]) if fused else net._forward_layerwise(xx)
+        (out * g).sum().backward()
+        res.append((out.detach(), xx.grad.clone(), {k: p.grad.clone() for k, p in net.named_parameters()}))
+    assert rel_l2(res[0][0], res[1][0]) < 1e-4        # 23 layers of BF16x3 vs fp32 rounding
+    assert rel_l2(res[0][1], res[1][1]) < 2e-2
+    for k in res[0][2]:
+        assert rel_l2(res[0][2][k], res[1][2][k]) < 2e-2, k

@@ -1,0 +1,55 @@
+"""Micro-benchmark (GPU box): tcgen05 conv path vs the fp32 direct-conv kernel, per U-Net layer shape at bs=64."""
+import math
+import os
+import sys
+
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from spatialalignmentnetwork_b200 import _lib, ops  # noqa: E402
+
+L = _lib
+
+
+def timeit(fn, reps=5):
+    fn(); torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        fn()
+    e1.record(); torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / reps
+
+
+def main():
+    N = int(sys.argv[1]) if len(sys.argv) > 1 else 64
+    shapes = [(3, 18, 320, 3), (18, 18, 320, 3), (36, 18, 320, 3), (18, 36, 160, 3), (36, 36, 160, 3), (72, 36, 160, 3),
+              (36, 72, 80, 3), (72, 72, 80, 3), (144, 72, 80, 3), (72, 144, 40, 3), (144, 144, 40, 3), (288, 144, 40, 3),
+              (144, 288, 20, 3), (288, 288, 20, 3), (288, 576, 20, 1), (144, 288, 40, 1), (72, 144, 80, 1), (36, 72, 160, 1),
+              (18, 2, 320, 1), (2, 32, 320, 3), (32, 32, 320, 3), (64, 64, 160, 3), (128, 64, 160, 3)]
+    print(f"N={N}: Cin Cout HW K | stage ms | tc conv ms (TF/s algorithmic) | fp32 conv ms (TF/s) | speedup(conv only)")
+    for Cin, Cout, HW, K in shapes:
+        x = torch.randn(N, Cin, HW, HW, device="cuda")
+        w = torch.randn(Cout, Cin, K, K, device="cuda") / math.sqrt(Cin * K * K)
+        xs = torch.empty(L.lib().san_tc_staged_act_elems(N, HW, HW, Cin), dtype=torch.bfloat16, device="cuda")
+        ws = torch.empty(L.lib().san_tc_staged_weight_elems(Cout, Cin, K), dtype=torch.bfloat16, device="cuda")
+        y = torch.empty(N, Cout, HW, HW, device="cuda")
+        Cpad = (Cin + 15) // 16 * 16
+        st = lambda: L.call("tc_stage_act", xs, N, HW, HW, Cpad, x, None, None, None, 1.0, Cin, 0,
+                            None, None, None, None, 1.0, 0, 0, None, None, None, None, 1.0, 0, 0)
+        L.call("tc_stage_weights", w, ws, Cout, Cin, K, 0)
+        cv = lambda: L.call("tc_conv", xs, ws, None, y, N, HW, HW, Cin, Cout, K, 0)
+        wp = ops._pack(w, False)
+        y2 = torch.empty_like(y)
+        fp = lambda: L.call("conv2d_fwd", x, wp, None, y2, N, Cin, HW, HW, Cout, K, 0, 0)
+        t_st, t_cv, t_fp = timeit(st), timeit(cv), timeit(fp)
+        fl = 2.0 * N * Cout * HW * HW * Cin * K * K
+        err = ((y - y2).norm() / y2.norm()).item()
+        print(f"{Cin:4d} {Cout:4d} {HW:4d} {K} | {t_st:7.3f} | {t_cv:7.3f} ({fl / t_cv / 1e9:6.1f}) | {t_fp:7.3f} ({fl / t_fp / 1e9:6.1f}) | "
+              f"{t_fp / t_cv:5.2f}x  err {err:.1e}")
+        del x, xs, y, y2
+
+
+if __name__ == "__main__":
+    main()
