@@ -114,6 +114,12 @@ int san_tc_stage_weights(const float* w, void* ws, int Cout, int Cin, int K, int
 int san_tc_conv(const void* xs, const void* ws, const float* bias, float* y, int N, int H, int W, int Cin, int Cout,
                 int K, long long y_bs, void* stream);
 
+/* dW[Cout,Cin,K,K] (and dbias[Cout] from the fp32 dy, both optional-bias) from the staged dY and the staged
+ * input of the forward conv: tcgen05 GEMM over the pixel dimension, MN-major operands, BF16x3 */
+int san_tc_wgrad_supported(int H, int W, int Cin, int Cout, int K);
+int san_tc_wgrad(const void* dys, const void* xs, float* dw, float* dbias, const float* dy, int N, int H, int W, int Cin,
+                 int Cout, int K, void* stream);
+
 /* ---- normalisation / activation / resampling (varnet.py:98,139-146,235,257-273; unet.py:119-140) ---- */
 /* per-plane mean and centred sum of squares (two-pass) */
 int san_plane_stats(const float* x, float* mean, float* m2, int planes, int P, void* stream);

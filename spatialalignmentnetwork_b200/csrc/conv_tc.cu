@@ -26,81 +26,10 @@
 //               TMEM lane = pixel, so a warp writes 32 consecutive pixels of one channel)
 // Pipelines: smem full/empty per K-step stage, TMEM accumulator full/empty (double-buffered when
 // 2*T*Npad <= 512 columns) so the epilogue of unit i overlaps the MMAs of unit i+1.
-#include <cuda_bf16.h>
-
-#include "san_common.cuh"
+#include "tc_common.cuh"
 #include "../../include/san_b200.h"
 
 namespace {
-
-// ------------------------------------------------------------------------------------------ PTX
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-  asm volatile(
-      "{\n\t"
-      ".reg .pred P1;\n\t"
-      "WAIT_LOOP:\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t"
-      "@P1 bra DONE;\n\t"
-      "bra WAIT_LOOP;\n\t"
-      "DONE:\n\t"
-      "}" ::"r"(bar),
-      "r"(parity)
-      : "memory");
-}
-__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
-               "l"(src), "r"(bytes), "r"(bar)
-               : "memory");
-}
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_commit(uint32_t bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void tc_mma_bf16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
-                                            uint32_t accumulate) {
-  asm volatile(
-      "{\n\t"
-      ".reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
-      "}" ::"r"(d_tmem),
-      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
-__device__ __forceinline__ void tc_ld8(uint32_t taddr, float* v) {
-  uint32_t r0, r1, r2, r3, r4, r5, r6, r7;
-  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
-               : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3), "=r"(r4), "=r"(r5), "=r"(r6), "=r"(r7)
-               : "r"(taddr));
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-  v[0] = __uint_as_float(r0); v[1] = __uint_as_float(r1); v[2] = __uint_as_float(r2); v[3] = __uint_as_float(r3);
-  v[4] = __uint_as_float(r4); v[5] = __uint_as_float(r5); v[6] = __uint_as_float(r6); v[7] = __uint_as_float(r7);
-}
-
-// UMMA shared-memory descriptor, no swizzle, K-major (cute::UMMA::SmemDescriptor): start address,
-// leading byte offset (between the two 8-element K groups of one K=16 step), stride byte offset
-// (between 8-row groups), all in 16 B units; version 1 (bit 46); layout type 0 (bits 61..63).
-__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
-  return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16) |
-         ((uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32) | (1ull << 46);
-}
-// Instruction descriptor (cute::UMMA::InstrDescriptor): D fp32 (bit 4), A/B bf16 (bits 7, 10),
-// both K-major, N>>3 at bit 17, M>>4 at bit 24.
-__host__ __device__ inline uint32_t umma_idesc_bf16(int M, int N) {
-  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
-}
 
 // ------------------------------------------------------------------------------------ geometry
 constexpr int TC_THREADS = 192;
@@ -116,8 +45,6 @@ struct TcGeom {
   int strips, stages, acc_stages;
   int a_bytes, b_bytes, stage_bytes, smem_bytes;
 };
-
-inline int pad16(int c) { return (c + 15) / 16 * 16; }
 
 bool tc_geometry(int H, int W, int Cin, int Cout, int K, TcGeom* g) {
   if (K != 1 && K != 3) return false;
@@ -418,6 +345,12 @@ __global__ void __launch_bounds__(256) stage_act_kernel(const StageArgs A) {
     *(uint4*)(A.xs + (o_hi + slot) * 8) = *(const uint4*)hi;
     *(uint4*)(A.xs + (o_lo + slot) * 8) = *(const uint4*)lo;
   }
+  // zero lead-in / trailing slack of the buffer (see TC_LEAD / TC_TRAIL)
+  if (blockIdx.x == 0 && blockIdx.y == 0) {
+    const uint4 z = make_uint4(0, 0, 0, 0);
+    if (threadIdx.x == 0) *(uint4*)(A.xs - TC_LEAD) = z;
+    if (threadIdx.x < TC_TRAIL / 8) *(uint4*)(A.xs + (long long)A.N * 2 * A.KG * A.PS * 8 + threadIdx.x * 8) = z;
+  }
 }
 
 // staged activations back to fp32 NCHW (x = hi + lo): feeds the fp32 weight-gradient kernel
@@ -481,7 +414,7 @@ inline int ew_blocks(long long total) {
 extern "C" {
 
 long long san_tc_staged_act_elems(int N, int H, int W, int C) {
-  return (long long)N * 2 * (pad16(C) / 8) * (long long)(H + 2) * (W + 2) * 8;
+  return (long long)N * 2 * (pad16(C) / 8) * (long long)(H + 2) * (W + 2) * 8 + TC_LEAD + TC_TRAIL;
 }
 
 long long san_tc_staged_weight_elems(int Cout, int Cin, int K) {
@@ -513,7 +446,7 @@ int san_tc_stage_act(void* xs, int N, int H, int W, int Cpad,
     if (A.s[i].mode >= 2) SAN_CHECK_ARG(H % 2 == 0 && W % 2 == 0, "san_tc_stage_act: odd size with up-sampling source");
   }
   SAN_CHECK_ARG(ctot <= Cpad, "san_tc_stage_act: %d channels exceed Cpad %d", ctot, Cpad);
-  A.xs = (__nv_bfloat16*)xs;
+  A.xs = (__nv_bfloat16*)xs + TC_LEAD;
   A.N = N; A.H = H; A.W = W; A.Wp = W + 2; A.PS = (H + 2) * (W + 2); A.KG = Cpad / 8;
   SAN_CHECK_ARG((long long)N * A.KG <= 65535, "san_tc_stage_act: N*KG too large for grid.y");
   int bx = (A.PS + 255) / 256;
@@ -527,7 +460,7 @@ int san_tc_stage_act(void* xs, int N, int H, int W, int Cpad,
 int san_tc_unstage_act(const void* xs, float* x, int N, int C, int H, int W, void* stream) {
   SAN_CHECK_ARG(xs && x && N > 0 && C > 0 && H > 0 && W > 0, "san_tc_unstage_act: bad args");
   const long long total = (long long)N * C * H * W;
-  unstage_act_kernel<<<ew_blocks(total), 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)xs, x, N, C, H, W,
+  unstage_act_kernel<<<ew_blocks(total), 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)xs + TC_LEAD, x, N, C, H, W,
                                                                          pad16(C) / 8);
   SAN_LAUNCH_CHECK();
   return SAN_OK;
@@ -551,7 +484,7 @@ int san_tc_conv(const void* xs, const void* ws, const float* bias, float* y, int
   ConvTcParams p{};
   SAN_CHECK_ARG(tc_geometry(H, W, Cin, Cout, K, &p.g), "san_tc_conv: unsupported shape H=%d W=%d Cin=%d Cout=%d K=%d", H, W,
                 Cin, Cout, K);
-  p.xs = (const __nv_bfloat16*)xs; p.ws = (const __nv_bfloat16*)ws; p.bias = bias; p.y = y;
+  p.xs = (const __nv_bfloat16*)xs + TC_LEAD; p.ws = (const __nv_bfloat16*)ws; p.bias = bias; p.y = y;
   p.y_bs = y_bs > 0 ? y_bs : (long long)Cout * H * W;
   p.N = N; p.H = H; p.W = W; p.Cout = Cout; p.ntaps = K * K;
   p.nunits = N * p.g.strips * p.g.nsplit;

@@ -1,0 +1,270 @@
+// tcgen05 weight-gradient kernel for the U-Net convolutions (sm_100a only):
+//     dW[co][ci][dy][dx] = sum_{n, pixel p} dY[n][co][p] * X[n][ci][p + (dy-1)*Wp + (dx-1)]
+// (the backward-filter of the reference's cuDNN convs, varnet.py:139-146,176-179, unet.py:119-140).
+//
+// Both operands are the SAME staged BF16 hi/lo tensors the forward / data-gradient kernels use
+// (conv_tc.cu: Xs[n][hl][kg][slot][8], zero border), read here as MN-major UMMA operands: the GEMM's
+// K dimension is the pixel slot (16 B row pitch, 8-slot groups 128 B apart = LBO), its M (dY) / N (X)
+// dimension is the channel (8 contiguous, channel groups one staged plane apart = SBO).  A filter tap
+// is again only a shifted start address of the X tile.  Border pixels of dY are zero, so the padding
+// columns and the zero rows between images contribute nothing and need no masking.
+//
+// Decomposition: group = (block of <= 128 output channels, chunk of <= 160 input channels, filter
+// row dy); the CTAs of a group split the pixel range of all images into chunks of KC slots and keep
+// three [128 x Nn] fp32 accumulators (dx = 0, 1, 2) in TMEM for the whole kernel; one atomicAdd pass
+// per CTA at the end.  BF16x3 as in the forward: hi*hi + lo*hi + hi*lo.
+//   warp 0: TMA producer (bulk copies of the dY chunk and the X span per stage)
+//   warp 1: TMEM allocator + single-thread MMA issuer
+//   warps 2..5: final epilogue (tcgen05.ld -> atomicAdd into dW[Cout][Cin][K][K])
+#include "tc_common.cuh"
+#include "../../include/san_b200.h"
+
+namespace {
+
+constexpr int WG_THREADS = 192;
+constexpr int WG_HEADER = 256;
+constexpr int WG_SMEM_MAX = 225 * 1024;
+
+struct WgGeom {
+  int KGo, KGi;            // staged channel groups of dY / X
+  int nmb, nnc, ndy;       // M blocks (128 co), N chunks, filter rows
+  int Nn, KGn;             // input channels per chunk (multiple of 16), its groups
+  int KC, XS;              // pixel slots per chunk (multiple of 16), X slots per stage (KC + 16)
+  int a_bytes, b_bytes, stage_bytes, stages, smem_bytes;
+  int nchunks;             // pixel chunks per image
+  int Wp, PS, range0, range_len;
+};
+
+bool wg_geometry(int H, int W, int Cin, int Cout, int K, WgGeom* g) {
+  if (K != 1 && K != 3) return false;
+  if (W + 2 < 18) return false;   // the 16-slot tail padding must stay inside the zero border row
+  g->KGo = pad16(Cout) / 8; g->KGi = pad16(Cin) / 8;
+  g->nmb = (g->KGo + 15) / 16;
+  const int cip = pad16(Cin);
+  g->nnc = 0;
+  for (int k = 1; k <= 8; ++k)
+    if (cip % k == 0 && (cip / k) % 16 == 0 && cip / k <= 160) { g->nnc = k; break; }
+  if (!g->nnc) return false;
+  g->Nn = cip / g->nnc; g->KGn = g->Nn / 8;
+  g->ndy = K;
+  g->Wp = W + 2; g->PS = (H + 2) * g->Wp;
+  g->range0 = g->Wp;                                  // first slot of image row 0 (padded row 1)
+  g->range_len = (H * g->Wp + 15) / 16 * 16;          // tail runs into the zero border row
+  const int kga = g->KGo < 16 ? g->KGo : 16;          // groups actually loaded per M block (max)
+  int best = 0;
+  for (int kc = 512; kc >= 32; kc -= 16) {
+    const int a = kga * 2 * kc * 16, b = g->KGn * 2 * (kc + 16) * 16;
+    const int slack = 16 * kc * 16;                   // M = 128 always reads 16 channel groups
+    if (2 * (a + b) + slack + WG_HEADER <= WG_SMEM_MAX) { best = kc; break; }
+  }
+  if (!best) return false;
+  g->KC = best; g->XS = best + 16;
+  g->a_bytes = kga * 2 * g->KC * 16;
+  g->b_bytes = g->KGn * 2 * g->XS * 16;
+  g->stage_bytes = g->a_bytes + g->b_bytes;
+  const int slack = 16 * g->KC * 16;
+  g->stages = (WG_SMEM_MAX - WG_HEADER - slack) / g->stage_bytes;
+  if (g->stages > 4) g->stages = 4;
+  g->smem_bytes = WG_HEADER + g->stages * g->stage_bytes + slack;
+  if (g->smem_bytes < 120 * 1024) g->smem_bytes = 120 * 1024;
+  g->nchunks = (g->range_len + g->KC - 1) / g->KC;
+  return true;
+}
+
+struct WgParams {
+  const __nv_bfloat16* dys;   // staged dY (past the lead-in)
+  const __nv_bfloat16* xs;    // staged X
+  float* dw;                  // [Cout][Cin][K][K], pre-zeroed
+  int N, Cin, Cout, K;
+  int ngroups, ctas_per_group;
+  WgGeom g;
+};
+
+__global__ void __launch_bounds__(WG_THREADS, 1) wgrad_tc_kernel(const WgParams p) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  const WgGeom& g = p.g;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t hdr = smem_u32(smem);
+  const uint32_t bar_full = hdr, bar_empty = hdr + 32, bar_done = hdr + 64;
+  volatile uint32_t* tmem_slot = (volatile uint32_t*)(smem + 96);
+  const uint32_t stage0 = hdr + WG_HEADER;
+
+  if (warp == 0 && lane == 0) {
+    for (int i = 0; i < g.stages; ++i) { mbar_init(bar_full + 8 * i, 1); mbar_init(bar_empty + 8 * i, 1); }
+    mbar_init(bar_done, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32((void*)tmem_slot)),
+                 "r"(512)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  // group of this CTA
+  const int grp = blockIdx.x / p.ctas_per_group, cta = blockIdx.x - grp * p.ctas_per_group;
+  const int dyi = grp % g.ndy;
+  const int nc = (grp / g.ndy) % g.nnc;
+  const int mb = grp / (g.ndy * g.nnc);
+  const int kga = min(16, g.KGo - 16 * mb);          // channel groups of dY loaded for this M block
+  const int ndx = g.ndy;                             // 3 taps per filter row (1 for 1x1)
+  const int nunits = p.N * g.nchunks;
+  const long long plane = (long long)g.PS * 8;
+  // slot offset of the X span relative to the dY chunk start: (dy-1)*Wp - 1 for 3x3, 0 for 1x1
+  const int xoff = (p.K == 3) ? (dyi - 1) * g.Wp - 1 : 0;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int s = 0;
+      uint32_t ph = 0;
+      for (int u = cta; u < nunits; u += p.ctas_per_group) {
+        const int n = u / g.nchunks, ch = u - n * g.nchunks;
+        const int p0 = g.range0 + ch * g.KC;
+        const int kc = min(g.KC, g.range_len - ch * g.KC);      // multiple of 16
+        const uint32_t bytesA = (uint32_t)kc * 16, bytesB = (uint32_t)(kc + 2) * 16;   // X span: kc + 2 tap slots
+        mbar_wait(bar_empty + 8 * s, ph ^ 1);
+        const uint32_t sbase = stage0 + (uint32_t)s * g.stage_bytes;
+        mbar_expect_tx(bar_full + 8 * s, 2u * kga * bytesA + 2u * g.KGn * bytesB);
+        for (int hl = 0; hl < 2; ++hl) {
+          for (int kg = 0; kg < kga; ++kg) {
+            const __nv_bfloat16* src = p.dys + ((long long)(n * 2 + hl) * g.KGo + 16 * mb + kg) * plane + (long long)p0 * 8;
+            bulk_g2s(sbase + (uint32_t)((hl * kga + kg) * g.KC) * 16, src, bytesA, bar_full + 8 * s);
+          }
+          for (int kg = 0; kg < g.KGn; ++kg) {
+            const __nv_bfloat16* src =
+                p.xs + ((long long)(n * 2 + hl) * g.KGi + nc * g.KGn + kg) * plane + (long long)(p0 + xoff) * 8;
+            bulk_g2s(sbase + g.a_bytes + (uint32_t)((hl * g.KGn + kg) * g.XS) * 16, src, bytesB, bar_full + 8 * s);
+          }
+        }
+        if (++s == g.stages) { s = 0; ph ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t idesc = umma_idesc_bf16(128, g.Nn, /*mn_major=*/1);
+      // MN-major, no swizzle: LBO = 128 B between 8-slot K groups, SBO = one staged plane between channel groups
+      const uint64_t a_tmpl = umma_desc(0, 128, (uint32_t)g.KC * 16);
+      const uint64_t b_tmpl = umma_desc(0, 128, (uint32_t)g.XS * 16);
+      const uint32_t a_hiw = (uint32_t)(a_tmpl >> 32), b_hiw = (uint32_t)(b_tmpl >> 32);
+      const uint32_t a_low = (uint32_t)a_tmpl, b_low = (uint32_t)b_tmpl;
+      const uint32_t a_losplit = (uint32_t)(kga * g.KC);        // hi -> lo half, 16 B units
+      const uint32_t b_losplit = (uint32_t)(g.KGn * g.XS);
+      int s = 0;
+      uint32_t ph = 0;
+      uint32_t started = 0;
+      for (int u = cta; u < nunits; u += p.ctas_per_group) {
+        const int ch = u % g.nchunks;
+        const int kc = min(g.KC, g.range_len - ch * g.KC);
+        mbar_wait(bar_full + 8 * s, ph);
+        tc_fence_after();
+        const uint32_t a_s = ((stage0 + (uint32_t)s * g.stage_bytes) >> 4) + a_low;
+        const uint32_t b_s = ((stage0 + (uint32_t)s * g.stage_bytes + g.a_bytes) >> 4) + b_low;
+        for (int k = 0; k < kc; k += 16) {
+          const uint32_t al = a_s + k;                          // 16 slots = 16 units of 16 B
+          const uint64_t A_hi = ((uint64_t)a_hiw << 32) | al, A_lo = ((uint64_t)a_hiw << 32) | (al + a_losplit);
+#pragma unroll
+          for (int dx = 0; dx < 3; ++dx) {
+            if (dx < ndx) {
+              const uint32_t bl = b_s + k + dx;
+              const uint64_t B_hi = ((uint64_t)b_hiw << 32) | bl, B_lo = ((uint64_t)b_hiw << 32) | (bl + b_losplit);
+              const uint32_t d = tmem_base + (uint32_t)(dx * g.Nn);
+              tc_mma_bf16(d, A_hi, B_hi, idesc, started);
+              tc_mma_bf16(d, A_lo, B_hi, idesc, 1u);
+              tc_mma_bf16(d, A_hi, B_lo, idesc, 1u);
+            }
+          }
+          started = 1;
+        }
+        tc_commit(bar_empty + 8 * s);
+        if (++s == g.stages) { s = 0; ph ^= 1; }
+      }
+      tc_commit(bar_done);
+    }
+  } else {
+    // ---- final epilogue: D[dx][co][ci] -> atomicAdd dW[co][ci][dy][dx]
+    const int wq = warp & 3;
+    if (cta < nunits) {
+      mbar_wait(bar_done, 0);
+      tc_fence_after();
+      const int co = mb * 128 + wq * 32 + lane;
+      const int KK = p.K * p.K;
+      for (int dx = 0; dx < ndx; ++dx) {
+        const int tap = (p.K == 3) ? dyi * 3 + dx : 0;
+        for (int c0 = 0; c0 < g.Nn; c0 += 8) {
+          float v[8];
+          tc_ld8(tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)(dx * g.Nn + c0), v);
+          if (co < p.Cout) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const int ci = nc * g.Nn + c0 + j;
+              if (ci < p.Cin) atomicAdd(p.dw + ((long long)co * p.Cin + ci) * KK + tap, v[j]);
+            }
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
+  }
+}
+
+// dbias[c] = sum over n, pixels of dy[n][c][:]   (grid: (C, N))
+__global__ void __launch_bounds__(256) bias_grad_kernel(const float* __restrict__ dy, float* __restrict__ db, int C, int P) {
+  __shared__ float red[32];
+  const float* src = dy + ((long long)blockIdx.y * C + blockIdx.x) * P;
+  float s = 0.f;
+  for (int i = threadIdx.x; i < P; i += blockDim.x) s += src[i];
+  s = block_sum(s, red);
+  if (threadIdx.x == 0) atomicAdd(db + blockIdx.x, s);
+}
+
+}  // namespace
+
+extern "C" {
+
+int san_tc_wgrad_supported(int H, int W, int Cin, int Cout, int K) {
+  WgGeom g;
+  return wg_geometry(H, W, Cin, Cout, K, &g) ? 1 : 0;
+}
+
+int san_tc_wgrad(const void* dys, const void* xs, float* dw, float* dbias, const float* dy, int N, int H, int W, int Cin,
+                 int Cout, int K, void* stream) {
+  SAN_CHECK_ARG(dys && xs && dw && N > 0 && H > 0 && W > 0 && Cin > 0 && Cout > 0, "san_tc_wgrad: bad args");
+  WgParams p{};
+  SAN_CHECK_ARG(wg_geometry(H, W, Cin, Cout, K, &p.g), "san_tc_wgrad: unsupported shape H=%d W=%d Cin=%d Cout=%d K=%d", H, W,
+                Cin, Cout, K);
+  cudaStream_t st = (cudaStream_t)stream;
+  p.dys = (const __nv_bfloat16*)dys + TC_LEAD; p.xs = (const __nv_bfloat16*)xs + TC_LEAD; p.dw = dw;
+  p.N = N; p.Cin = Cin; p.Cout = Cout; p.K = K;
+  p.ngroups = p.g.nmb * p.g.nnc * p.g.ndy;
+  const int nunits = N * p.g.nchunks;
+  int cpg = san_num_sms() / p.ngroups;
+  if (cpg < 1) cpg = 1;
+  if (cpg > nunits) cpg = nunits;
+  p.ctas_per_group = cpg;
+  SAN_CUDA(cudaMemsetAsync(dw, 0, sizeof(float) * (size_t)Cout * Cin * K * K, st));
+  static bool attr_set = false;
+  if (!attr_set) {
+    SAN_CUDA(cudaFuncSetAttribute(wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, WG_SMEM_MAX));
+    attr_set = true;
+  }
+  wgrad_tc_kernel<<<p.ngroups * cpg, WG_THREADS, p.g.smem_bytes, st>>>(p);
+  SAN_LAUNCH_CHECK();
+  if (dbias) {
+    SAN_CHECK_ARG(dy, "san_tc_wgrad: dbias needs the fp32 dy");
+    SAN_CUDA(cudaMemsetAsync(dbias, 0, sizeof(float) * (size_t)Cout, st));
+    bias_grad_kernel<<<dim3(Cout, N), 256, 0, st>>>(dy, dbias, Cout, H * W);
+    SAN_LAUNCH_CHECK();
+  }
+  return SAN_OK;
+}
+
+}  // extern "C"

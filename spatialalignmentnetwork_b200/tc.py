@@ -128,20 +128,24 @@ class _FusedConv(Function):
         Cout, Cin = w.shape[0], w.shape[1]
         gy = gy if gy.is_contiguous() else gy.contiguous()
         dev = w.device
-        # ---- weight gradient (fp32 CUDA-core kernel on the un-staged operand; tcgen05 wgrad is next)
+        # dY staged once as BF16 hi/lo: the operand of both the data- and the weight-gradient GEMMs
+        gys = _staged_act(N, H, W, Cout, dev)
+        _stage(gys, N, H, W, _pad16(Cout), [(gy, None, 1.0, Cout, MODE_DIRECT)])
+        # ---- weight gradient: tcgen05 GEMM over the pixel dimension on the staged dY and the staged input
         dw = db = None
         if ctx.needs_input_grad[0] or (has_bias and ctx.needs_input_grad[1]):
-            x32 = torch.empty(N, Cin, H, W, dtype=torch.float32, device=dev)
-            call("tc_unstage_act", xs, x32, N, Cin, H, W)
             dw = torch.empty_like(w)
             db = torch.empty(Cout, dtype=torch.float32, device=dev) if has_bias else None
-            call("conv2d_wgrad", x32, gy, dw, db, N, Cin, H, W, Cout, K, 0, 0)
-            del x32
+            if lib().san_tc_wgrad_supported(H, W, Cin, Cout, K):
+                call("tc_wgrad", gys, xs, dw, db, gy if has_bias else None, N, H, W, Cin, Cout, K)
+            else:   # tiny images (W < 16): fp32 CUDA-core kernel on the un-staged operand
+                x32 = torch.empty(N, Cin, H, W, dtype=torch.float32, device=dev)
+                call("tc_unstage_act", xs, x32, N, Cin, H, W)
+                call("conv2d_wgrad", x32, gy, dw, db, N, Cin, H, W, Cout, K, 0, 0)
+                del x32
         # ---- data gradient: the same tcgen05 conv on the staged dY with the flipped filter
         grads = [None] * ns
         if any(ctx.needs_input_grad[3 + k] for k in range(ns)):
-            gys = _staged_act(N, H, W, Cout, dev)
-            _stage(gys, N, H, W, _pad16(Cout), [(gy, None, 1.0, Cout, MODE_DIRECT)])
             wsd = _stage_weights(w, True)
             dx = torch.empty(N, Cin, H, W, dtype=torch.float32, device=dev)
             call("tc_conv", gys, wsd, None, dx, N, H, W, Cout, Cin, K, 0)

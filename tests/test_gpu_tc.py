@@ -97,7 +97,8 @@ def test_tc_stage_roundtrip_and_fused_sources():
     out = torch.empty(N, C, H, W, device="cuda")
     L.call("tc_unstage_act", xs, out, N, C, H, W)
     assert rel_l2(out, ref) < 2e-5
-    st = xs.view(N, 2, 2, H + 2, W + 2, 8).float()
+    st = xs[8:-256].view(N, 2, 2, H + 2, W + 2, 8).float()      # [lead 8 | planes | trail 256]
+    assert xs[:8].float().abs().max() == 0 and xs[-256:].float().abs().max() == 0
     assert st[:, :, :, 0].abs().max() == 0 and st[:, :, :, -1].abs().max() == 0      # zero border rows
     assert st[:, :, :, :, 0].abs().max() == 0 and st[:, :, :, :, -1].abs().max() == 0  # zero border cols
     assert st[:, :, 1, :, :, 7].abs().max() == 0                                       # pad channel 15
@@ -195,3 +196,35 @@ def test_fused_unet_matches_layerwise_fp32():
     assert rel_l2(res[0][1], res[1][1]) < 2e-2
     for k in res[0][2]:
         assert rel_l2(res[0][2][k], res[1][2][k]) < 2e-2, k
+
+
+WG_CASES = [
+    # N, Cin, H, W, Cout, K, bias
+    (2, 3, 32, 48, 18, 3, False), (1, 18, 64, 64, 18, 3, False), (2, 36, 40, 24, 36, 3, False),
+    (1, 72, 20, 20, 144, 3, False), (1, 144, 20, 20, 288, 3, False), (1, 288, 16, 20, 288, 3, False),
+    (2, 18, 32, 32, 2, 1, True), (1, 288, 16, 16, 576, 1, False), (2, 2, 33, 47, 32, 3, True),
+    (1, 96, 24, 40, 32, 3, True), (3, 64, 17, 23, 64, 1, True), (2, 18, 320, 320, 18, 3, False),
+]
+
+
+@pytest.mark.parametrize("case", WG_CASES)
+def test_tc_wgrad(case):
+    """tcgen05 weight gradient from the staged operands vs torch fp64 conv2d backward."""
+    L = _lib()
+    N, Cin, H, W, Cout, K, has_bias = case
+    assert L.lib().san_tc_wgrad_supported(H, W, Cin, Cout, K) == 1
+    torch.manual_seed(41)
+    x = torch.randn(N, Cin, H, W)
+    w = torch.randn(Cout, Cin, K, K) / math.sqrt(Cin * K * K)
+    b = torch.randn(Cout) if has_bias else None
+    gy = torch.randn(N, Cout, H, W)
+    wr = w.double().requires_grad_(True)
+    br = b.double().requires_grad_(True) if has_bias else None
+    (F.conv2d(x.double(), wr, br, padding=K // 2) * gy.double()).sum().backward()
+    xs, gys = stage(x.cuda()), stage(gy.cuda())
+    dw = torch.empty(Cout, Cin, K, K, device="cuda")
+    db = torch.empty(Cout, device="cuda") if has_bias else None
+    L.call("tc_wgrad", gys, xs, dw, db, gy.cuda() if has_bias else None, N, H, W, Cin, Cout, K)
+    assert rel_l2(dw, wr.grad) < 2e-5
+    if has_bias:
+        assert rel_l2(db, br.grad) < 1e-5
