@@ -322,7 +322,7 @@ def run_b200(args):
 
     net = build_model(args)
     total_mem = torch.cuda.get_device_properties(dev).total_memory
-    est = args.batch * (args.cascades * 0.19 + 0.5) * 2 ** 30 * (args.shape / 320.0) ** 2
+    est = args.batch * (args.cascades * 0.08 + 0.45) * 2 ** 30 * (args.shape / 320.0) ** 2   # raw conv outputs only
     ckpt = {"auto": est > 0.7 * total_mem, "0": False, "1": True}[args.checkpoint]
     net.net_R.checkpoint_cascades = ckpt
     net.to(dev).train()

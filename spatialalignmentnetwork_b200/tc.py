@@ -112,7 +112,10 @@ class _FusedConv(Function):
         ws = _stage_weights(w, False)
         out = torch.empty(N, Cout, H, W, dtype=torch.float32, device=w.device)
         call("tc_conv", xs, ws, bias, out, N, H, W, Cin, Cout, K, 0)
-        ctx.save_for_backward(w, xs, *ys, *[m[4] for m in metas if m[4] is not None])
+        # The staged operand is NOT kept for the backward (it is as large as the fp32 activation and
+        # the padded channels make it larger): the weight gradient re-stages it from the raw tensors,
+        # which autograd holds anyway for the normalisation backward.
+        ctx.save_for_backward(w, *ys, *[m[4] for m in metas if m[4] is not None])
         ctx.meta = (K, [(m[0], m[1], m[2], m[3], m[4] is not None) for m in metas], (N, H, W), bias is not None)
         return out
 
@@ -121,10 +124,10 @@ class _FusedConv(Function):
     def backward(ctx, gy):
         K, metas, (N, H, W), has_bias = ctx.meta
         saved = ctx.saved_tensors
-        w, xs = saved[0], saved[1]
+        w = saved[0]
         ns = len(metas)
-        ys = saved[2:2 + ns]
-        coefs = list(saved[2 + ns:])
+        ys = saved[1:1 + ns]
+        coefs = list(saved[1 + ns:])
         Cout, Cin = w.shape[0], w.shape[1]
         gy = gy if gy.is_contiguous() else gy.contiguous()
         dev = w.device
@@ -136,6 +139,12 @@ class _FusedConv(Function):
         if ctx.needs_input_grad[0] or (has_bias and ctx.needs_input_grad[1]):
             dw = torch.empty_like(w)
             db = torch.empty(Cout, dtype=torch.float32, device=dev) if has_bias else None
+            xs = _staged_act(N, H, W, Cin, dev)          # re-stage the forward operand
+            ci, srcs = 0, []
+            for y, (norm, slope, d2s, mode, has_coef) in zip(ys, metas):
+                srcs.append((y, coefs[ci] if has_coef else None, slope, y.shape[1] // 4 if d2s else y.shape[1], mode))
+                ci += int(has_coef)
+            _stage(xs, N, H, W, _pad16(Cin), srcs)
             if lib().san_tc_wgrad_supported(H, W, Cin, Cout, K):
                 call("tc_wgrad", gys, xs, dw, db, gy if has_bias else None, N, H, W, Cin, Cout, K)
             else:   # tiny images (W < 16): fp32 CUDA-core kernel on the un-staged operand
@@ -143,6 +152,7 @@ class _FusedConv(Function):
                 call("tc_unstage_act", xs, x32, N, Cin, H, W)
                 call("conv2d_wgrad", x32, gy, dw, db, N, Cin, H, W, Cout, K, 0, 0)
                 del x32
+            del xs
         # ---- data gradient: the same tcgen05 conv on the staged dY with the flipped filter
         grads = [None] * ns
         if any(ctx.needs_input_grad[3 + k] for k in range(ns)):
