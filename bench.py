@@ -176,7 +176,7 @@ def algorithmic(name, a):
 
 CLASSES = {
     "conv": ("conv2d_fwd", "conv2d_wgrad", "conv_pack_weights", "tc_conv", "tc_wgrad", "tc_stage_weights"),
-    "operand_staging": ("tc_stage_act", "tc_unstage_act"),
+    "operand_staging": ("tc_stage_act", "tc_stage_terms", "tc_unstage_act"),
     "fft_dc": ("fft_expand_dc", "fft_reduce", "fft_rss", "fft2", "dc_bwd", "cmul_conj_planar"),
     "norm_act": ("plane_stats", "in_finalize_fwd", "bn_finalize_fwd", "affine_act_fwd", "act_bwd_reduce",
                  "in_finalize_bwd", "bn_finalize_bwd", "act_bwd_apply"),

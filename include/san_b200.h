@@ -92,7 +92,7 @@ int san_space_to_depth2(const float* y, float* x, int N, int Co, int H, int W, v
  * kg = groups of 8 channels, Cin padded to 16, one-pixel zero border); weights as
  * Ws[nsplit][KS][taps][hl][2][Npad][8].  Element counts of the caller-allocated buffers: */
 long long san_tc_staged_act_elems(int N, int H, int W, int C);
-long long san_tc_staged_weight_elems(int Cout, int Cin, int K);
+long long san_tc_staged_weight_elems(int H, int W, int Cout, int Cin, int K);   /* Cout/Cin of the LAUNCH */
 int san_tc_supported(int H, int W, int Cin, int Cout, int K);
 /* Fused operand producer: up to 3 channel-concatenated sources (varnet.py:116 concat order),
  * each out = leaky_relu(a[plane]*(y - mu[plane]) + b[plane], slope) (a NULL = identity), i.e. the
@@ -104,11 +104,26 @@ int san_tc_stage_act(void* xs, int N, int H, int W, int Cpad,
                      const float* y1, const float* mu1, const float* a1, const float* b1, float slope1, int C1, int mode1,
                      const float* y2, const float* mu2, const float* a2, const float* b2, float slope2, int C2, int mode2,
                      void* stream);
+/* General form: an ordered list of terms; a term with accumulate = 0 starts a new channel range right after
+ * the previous range (concatenation), accumulate = 1 ADDS onto the previous term's range (the residual sums of
+ * unet.py:15-24: x + subnet(x) of two activated tensors).  At most 6 terms; host memory. */
+typedef struct san_stage_term {
+  const float* y;   /* fp32 NCHW source at its own resolution */
+  const float* mu;  /* per-plane [N*C] centre / scale / shift; a == NULL: identity */
+  const float* a;
+  const float* b;
+  float slope;      /* LeakyReLU slope, 1 = none */
+  int C;            /* channels contributed (after the pixel shuffle for mode 2) */
+  int mode;         /* 0 direct, 1 avg-pool 2x2, 2 depth-to-space, 3 nearest x2 */
+  int accumulate;
+} san_stage_term;
+int san_tc_stage_terms(void* xs, int N, int H, int W, int Cpad, const san_stage_term* terms, int nterms, void* stream);
 /* x[N,C,H,W] = hi + lo of a staged tensor (input of the fp32 weight-gradient kernel) */
 int san_tc_unstage_act(const void* xs, float* x, int N, int C, int H, int W, void* stream);
-/* OIHW fp32 -> staged hi/lo; dgrad = 1 stages the flipped, transposed filter so that the data
- * gradient is san_tc_conv run on the staged dY (then Cout/Cin below are the ORIGINAL ones) */
-int san_tc_stage_weights(const float* w, void* ws, int Cout, int Cin, int K, int dgrad, void* stream);
+/* OIHW fp32 -> staged hi/lo for images of H x W (the output-channel split depends on the strip geometry);
+ * dgrad = 1 stages the flipped, transposed filter so that the data gradient is san_tc_conv run on the
+ * staged dY (Cout/Cin below are always the ORIGINAL ones of the OIHW tensor) */
+int san_tc_stage_weights(const float* w, void* ws, int H, int W, int Cout, int Cin, int K, int dgrad, void* stream);
 /* y[N,Cout,H,W] (+ bias) = conv2d(staged x, staged w), stride 1, padding K/2, K in {1,3};
  * Cin/Cout are the channel counts of THIS launch (for dgrad: Cin = original Cout, Cout = original Cin) */
 int san_tc_conv(const void* xs, const void* ws, const float* bias, float* y, int N, int H, int W, int Cin, int Cout,

@@ -4,7 +4,8 @@ alignment U-Net estimates a dense displacement field, added to the identity samp
 runs on the san_b200 kernels."""
 import torch
 
-from . import ops
+from . import ops, tc
+from . import unet as _unet
 from .unet import UNet, Conv2dB200
 
 
@@ -48,7 +49,13 @@ class SpatialTransformer(torch.nn.Module):
         torch.nn.init.zeros_(self.net[-1].bias)
 
     def forward(self, moving, fixed, features=None):
-        out = self.net(torch.cat([moving, fixed], 1))          # [N,2,H,W]
+        if _unet.USE_TC:
+            # fused tcgen05 path: no concat copy; LeakyReLU(0.01) (cross.py:14) folded into the operand
+            # staging of the zero-initialised head conv (cross.py:15)
+            y = self.net[0].forward_sources([moving.float().contiguous(), fixed.float().contiguous()])
+            out = tc.fused_conv([tc.Raw(y, None, self.net[1].negative_slope)], self.net[2].weight, self.net[2].bias)
+        else:
+            out = self.net(torch.cat([moving, fixed], 1))      # [N,2,H,W]
         offset = out.permute(0, 2, 3, 1)                        # view, (x, y) last
         grid = ops.GridFromOffset.apply(out)                    # identity + offset, [N,H,W,2]
         return offset, grid

@@ -46,26 +46,37 @@ struct TcGeom {
   int a_bytes, b_bytes, stage_bytes, smem_bytes;
 };
 
-bool tc_geometry(int H, int W, int Cin, int Cout, int K, TcGeom* g) {
-  if (K != 1 && K != 3) return false;
-  g->Cin_pad = pad16(Cin); g->KG = g->Cin_pad / 8; g->KS = g->Cin_pad / 16;
-  g->nsplit = (pad16(Cout) + TC_NMAX - 1) / TC_NMAX;
-  g->Npad = pad16((Cout + g->nsplit - 1) / g->nsplit);
-  g->Wp = W + 2; g->Hp = H + 2; g->PS = g->Hp * g->Wp;
-  const int ntaps = K * K;
-  g->b_bytes = ntaps * 4 * g->Npad * 16;
+// Rows per strip for a given output-channel split; 0 if nothing fits (shared memory / TMEM columns).
+static int tc_pick_rows(int H, int W, int K, int Npad, int b_bytes) {
+  const int Wp = W + 2;
   int bestR = 0;
   double best = -1.0;
   for (int R = 1; R <= H; ++R) {
-    const int T = (R * g->Wp + 127) / 128;
-    if (T * g->Npad > 512) break;
-    const int S = ((128 * T + 2 * g->Wp + 2) + 7) / 8 * 8;
-    const int stage = 4 * S * 16 + g->b_bytes;
+    const int T = (R * Wp + 127) / 128;
+    if (T * Npad > 512) break;
+    const int S = ((128 * T + 2 * Wp + 2) + 7) / 8 * 8;
+    const int stage = 4 * S * 16 + b_bytes;
     if (2 * stage + TC_SMEM_HEADER > TC_SMEM_MAX) break;
     // useful MMA rows x re-read factor of the input rows (halo) x tail waste of the last strip
     const int strips = (H + R - 1) / R;
     const double eff = ((double)R * W / (128.0 * T)) * ((double)R / (R + 2 * (K / 2))) * ((double)H / (strips * R));
     if (eff > best + 1e-9) { best = eff; bestR = R; }
+  }
+  return bestR;
+}
+
+bool tc_geometry(int H, int W, int Cin, int Cout, int K, TcGeom* g) {
+  if (K != 1 && K != 3) return false;
+  g->Cin_pad = pad16(Cin); g->KG = g->Cin_pad / 8; g->KS = g->Cin_pad / 16;
+  g->Wp = W + 2; g->Hp = H + 2; g->PS = g->Hp * g->Wp;
+  const int ntaps = K * K;
+  // split the output channels until a strip (A rows + the weight block of one K-step, two stages) fits
+  int bestR = 0;
+  for (g->nsplit = (pad16(Cout) + TC_NMAX - 1) / TC_NMAX; g->nsplit <= 16; ++g->nsplit) {
+    g->Npad = pad16((Cout + g->nsplit - 1) / g->nsplit);
+    g->b_bytes = ntaps * 4 * g->Npad * 16;
+    bestR = tc_pick_rows(H, W, K, g->Npad, g->b_bytes);
+    if (bestR || g->Npad == 16) break;
   }
   if (bestR == 0) return false;
   g->R = bestR;
@@ -266,19 +277,21 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const ConvTcPara
 }
 
 // ------------------------------------------------------------------------- operand staging
-struct StageSrc {
+constexpr int STAGE_MAX_TERMS = 6;
+struct StageTerm {
   const float* y;    // source tensor (fp32 NCHW at the source resolution)
-  const float* mu;   // per-plane centre, scale, shift (null = identity); plane = n*C + c
+  const float* mu;   // per-plane centre, scale, shift (a null = identity); plane = n*C + c
   const float* a;
   const float* b;
   float slope;       // leaky slope (1 = none)
-  int C;             // channels this source contributes
+  int C;             // channels of this term
   int mode;          // 0 direct, 1 avg-pool 2x2 of the activated source (source is 2H x 2W),
                      // 2 depth-to-space (source [N,4C,H/2,W/2]), 3 nearest x2 (source is H/2 x W/2)
+  int c0;            // first output channel this term writes / adds to
 };
 struct StageArgs {
-  StageSrc s[3];
-  int nsrc;
+  StageTerm s[STAGE_MAX_TERMS];
+  int nterms;
   __nv_bfloat16* xs;
   int N, H, W, Wp, PS, KG;
 };
@@ -288,19 +301,36 @@ __device__ __forceinline__ float act1(float v, float mu, float a, float b, float
   return z > 0.f ? z : z * slope;
 }
 
+__device__ __forceinline__ float stage_term_value(const StageTerm& S, int n, int c, int h, int w, int H, int W) {
+  const long long plane = (long long)n * S.C + c;
+  float mu = 0.f, a = 1.f, b = 0.f;
+  if (S.a) { mu = S.mu ? __ldg(S.mu + plane) : 0.f; a = __ldg(S.a + plane); b = S.b ? __ldg(S.b + plane) : 0.f; }
+  if (S.mode == 0) return act1(__ldg(S.y + (plane * H + h) * W + w), mu, a, b, S.slope);
+  if (S.mode == 1) {
+    const int Ws2 = 2 * W;
+    const float* q = S.y + (plane * (2 * H) + 2 * h) * Ws2 + 2 * w;
+    const float2 r0 = __ldg((const float2*)q), r1 = __ldg((const float2*)(q + Ws2));
+    return 0.25f * ((act1(r0.x, mu, a, b, S.slope) + act1(r0.y, mu, a, b, S.slope)) +
+                    (act1(r1.x, mu, a, b, S.slope) + act1(r1.y, mu, a, b, S.slope)));
+  }
+  const int Hs = H / 2, Wsrc = W / 2;
+  if (S.mode == 2) {
+    const long long sp = ((long long)n * S.C * 4 + c * 4 + (h & 1) * 2 + (w & 1));
+    return act1(__ldg(S.y + (sp * Hs + (h >> 1)) * Wsrc + (w >> 1)), mu, a, b, S.slope);
+  }
+  return act1(__ldg(S.y + (plane * Hs + (h >> 1)) * Wsrc + (w >> 1)), mu, a, b, S.slope);
+}
+
 // one thread = one pixel slot x one channel group of 8: two 16 B stores (hi, lo).
-// grid = (slot blocks, N*KG): no 64-bit divisions on the hot path.
+// grid = (slot blocks, N*KG): no 64-bit divisions on the hot path.  A channel is the SUM of every
+// term whose channel range [c0, c0 + C) contains it (residual adds of unet.py:15-24 are sums of two
+// activated tensors; concatenation = disjoint ranges).
 __global__ void __launch_bounds__(256) stage_act_kernel(const StageArgs A) {
   const int n = blockIdx.y / A.KG, kg = blockIdx.y - n * A.KG;
-  // channel -> source lookup for the 8 channels of this group (uniform over the block)
-  int src_of[8], ch_of[8];
-#pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    int c = kg * 8 + j, si = 0;
-    while (si < A.nsrc && c >= A.s[si].C) { c -= A.s[si].C; ++si; }
-    src_of[j] = si < A.nsrc ? si : -1;
-    ch_of[j] = c;
-  }
+  // which terms touch this channel group at all (uniform over the block)
+  unsigned live = 0;
+  for (int t = 0; t < A.nterms; ++t)
+    if (A.s[t].c0 < kg * 8 + 8 && A.s[t].c0 + A.s[t].C > kg * 8) live |= 1u << t;
   const long long o_hi = ((long long)(n * 2 + 0) * A.KG + kg) * A.PS;
   const long long o_lo = ((long long)(n * 2 + 1) * A.KG + kg) * A.PS;
   for (int slot = blockIdx.x * blockDim.x + threadIdx.x; slot < A.PS; slot += gridDim.x * blockDim.x) {
@@ -309,30 +339,14 @@ __global__ void __launch_bounds__(256) stage_act_kernel(const StageArgs A) {
     float v[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) v[j] = 0.f;
-    if (h >= 0 && h < A.H && w >= 0 && w < A.W) {
+    if (live && h >= 0 && h < A.H && w >= 0 && w < A.W) {
+      for (int t = 0; t < A.nterms; ++t) {
+        if (!(live >> t & 1)) continue;
+        const StageTerm& S = A.s[t];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        if (src_of[j] < 0) continue;
-        const StageSrc& S = A.s[src_of[j]];
-        const int c = ch_of[j];
-        const long long plane = (long long)n * S.C + c;
-        float mu = 0.f, a = 1.f, b = 0.f;
-        if (S.a) { mu = S.mu ? __ldg(S.mu + plane) : 0.f; a = __ldg(S.a + plane); b = S.b ? __ldg(S.b + plane) : 0.f; }
-        if (S.mode == 0) {
-          v[j] = act1(__ldg(S.y + (plane * A.H + h) * A.W + w), mu, a, b, S.slope);
-        } else if (S.mode == 1) {
-          const int Ws2 = 2 * A.W;
-          const float* q = S.y + (plane * (2 * A.H) + 2 * h) * Ws2 + 2 * w;
-          const float2 r0 = __ldg((const float2*)q), r1 = __ldg((const float2*)(q + Ws2));
-          v[j] = 0.25f * ((act1(r0.x, mu, a, b, S.slope) + act1(r0.y, mu, a, b, S.slope)) +
-                          (act1(r1.x, mu, a, b, S.slope) + act1(r1.y, mu, a, b, S.slope)));
-        } else if (S.mode == 2) {
-          const int Hs = A.H / 2, Wsrc = A.W / 2;
-          const long long sp = ((long long)n * S.C * 4 + c * 4 + (h & 1) * 2 + (w & 1));
-          v[j] = act1(__ldg(S.y + (sp * Hs + (h >> 1)) * Wsrc + (w >> 1)), mu, a, b, S.slope);
-        } else {
-          const int Hs = A.H / 2, Wsrc = A.W / 2;
-          v[j] = act1(__ldg(S.y + (plane * Hs + (h >> 1)) * Wsrc + (w >> 1)), mu, a, b, S.slope);
+        for (int j = 0; j < 8; ++j) {
+          const int c = kg * 8 + j - S.c0;
+          if (c >= 0 && c < S.C) v[j] += stage_term_value(S, n, c, h, w, A.H, A.W);
         }
       }
     }
@@ -417,15 +431,53 @@ long long san_tc_staged_act_elems(int N, int H, int W, int C) {
   return (long long)N * 2 * (pad16(C) / 8) * (long long)(H + 2) * (W + 2) * 8 + TC_LEAD + TC_TRAIL;
 }
 
-long long san_tc_staged_weight_elems(int Cout, int Cin, int K) {
+long long san_tc_staged_weight_elems(int H, int W, int Cout, int Cin, int K) {
   TcGeom g;
-  if (!tc_geometry(8, 8, Cin, Cout, K, &g)) return -1;
+  if (!tc_geometry(H, W, Cin, Cout, K, &g)) return -1;
   return (long long)g.nsplit * g.KS * K * K * 4 * g.Npad * 8;
 }
 
 int san_tc_supported(int H, int W, int Cin, int Cout, int K) {
   TcGeom g;
   return tc_geometry(H, W, Cin, Cout, K, &g) ? 1 : 0;
+}
+
+static int launch_stage(StageArgs& A, void* xs, int N, int H, int W, int Cpad, cudaStream_t st) {
+  int ctot = 0;
+  for (int i = 0; i < A.nterms; ++i) {
+    SAN_CHECK_ARG(A.s[i].y && A.s[i].C > 0, "san_tc_stage: term %d has no tensor / channels", i);
+    SAN_CHECK_ARG(A.s[i].mode >= 0 && A.s[i].mode <= 3, "san_tc_stage: bad mode");
+    if (A.s[i].mode >= 2) SAN_CHECK_ARG(H % 2 == 0 && W % 2 == 0, "san_tc_stage: odd size with up-sampling source");
+    if (A.s[i].c0 + A.s[i].C > ctot) ctot = A.s[i].c0 + A.s[i].C;
+  }
+  SAN_CHECK_ARG(ctot <= Cpad, "san_tc_stage: %d channels exceed Cpad %d", ctot, Cpad);
+  A.xs = (__nv_bfloat16*)xs + TC_LEAD;
+  A.N = N; A.H = H; A.W = W; A.Wp = W + 2; A.PS = (H + 2) * (W + 2); A.KG = Cpad / 8;
+  SAN_CHECK_ARG((long long)N * A.KG <= 65535, "san_tc_stage: N*KG too large for grid.y");
+  int bx = (A.PS + 255) / 256;
+  const int want = (san_num_sms() * 8 + N * A.KG - 1) / (N * A.KG);   // >= 8 blocks per SM overall
+  if (bx > want) bx = want < 1 ? 1 : want;
+  stage_act_kernel<<<dim3(bx, N * A.KG), 256, 0, st>>>(A);
+  SAN_LAUNCH_CHECK();
+  return SAN_OK;
+}
+
+int san_tc_stage_terms(void* xs, int N, int H, int W, int Cpad, const san_stage_term* terms, int nterms, void* stream) {
+  SAN_CHECK_ARG(xs && terms && nterms >= 1 && nterms <= STAGE_MAX_TERMS && N > 0 && H > 0 && W > 0 && Cpad % 16 == 0,
+                "san_tc_stage_terms: bad args");
+  StageArgs A{};
+  A.nterms = nterms;
+  int c_next = 0, c_prev = 0;
+  for (int i = 0; i < nterms; ++i) {
+    const san_stage_term& t = terms[i];
+    SAN_CHECK_ARG(!(t.accumulate && i == 0), "san_tc_stage_terms: first term cannot accumulate");
+    const int c0 = t.accumulate ? c_prev : c_next;
+    A.s[i] = StageTerm{t.y, t.mu, t.a, t.b, t.slope, t.C, t.mode, c0};
+    if (t.accumulate) SAN_CHECK_ARG(t.C == A.s[i - 1].C, "san_tc_stage_terms: accumulated term must match the channel count");
+    c_prev = c0;
+    if (!t.accumulate) c_next = c0 + t.C;
+  }
+  return launch_stage(A, xs, N, H, W, Cpad, (cudaStream_t)stream);
 }
 
 int san_tc_stage_act(void* xs, int N, int H, int W, int Cpad,
@@ -435,26 +487,11 @@ int san_tc_stage_act(void* xs, int N, int H, int W, int Cpad,
                      void* stream) {
   SAN_CHECK_ARG(xs && y0 && N > 0 && H > 0 && W > 0 && Cpad % 16 == 0 && C0 > 0, "san_tc_stage_act: bad args");
   StageArgs A{};
-  A.s[0] = StageSrc{y0, mu0, a0, b0, slope0, C0, mode0};
-  A.nsrc = 1;
-  if (y1) { A.s[1] = StageSrc{y1, mu1, a1, b1, slope1, C1, mode1}; A.nsrc = 2; }
-  if (y2) { SAN_CHECK_ARG(y1, "san_tc_stage_act: source 2 without source 1"); A.s[2] = StageSrc{y2, mu2, a2, b2, slope2, C2, mode2}; A.nsrc = 3; }
-  int ctot = 0;
-  for (int i = 0; i < A.nsrc; ++i) {
-    ctot += A.s[i].C;
-    SAN_CHECK_ARG(A.s[i].mode >= 0 && A.s[i].mode <= 3, "san_tc_stage_act: bad mode");
-    if (A.s[i].mode >= 2) SAN_CHECK_ARG(H % 2 == 0 && W % 2 == 0, "san_tc_stage_act: odd size with up-sampling source");
-  }
-  SAN_CHECK_ARG(ctot <= Cpad, "san_tc_stage_act: %d channels exceed Cpad %d", ctot, Cpad);
-  A.xs = (__nv_bfloat16*)xs + TC_LEAD;
-  A.N = N; A.H = H; A.W = W; A.Wp = W + 2; A.PS = (H + 2) * (W + 2); A.KG = Cpad / 8;
-  SAN_CHECK_ARG((long long)N * A.KG <= 65535, "san_tc_stage_act: N*KG too large for grid.y");
-  int bx = (A.PS + 255) / 256;
-  const int want = (san_num_sms() * 8 + N * A.KG - 1) / (N * A.KG);   // >= 8 blocks per SM overall
-  if (bx > want) bx = want < 1 ? 1 : want;
-  stage_act_kernel<<<dim3(bx, N * A.KG), 256, 0, (cudaStream_t)stream>>>(A);
-  SAN_LAUNCH_CHECK();
-  return SAN_OK;
+  A.s[0] = StageTerm{y0, mu0, a0, b0, slope0, C0, mode0, 0};
+  A.nterms = 1;
+  if (y1) { A.s[1] = StageTerm{y1, mu1, a1, b1, slope1, C1, mode1, C0}; A.nterms = 2; }
+  if (y2) { SAN_CHECK_ARG(y1, "san_tc_stage_act: source 2 without source 1"); A.s[2] = StageTerm{y2, mu2, a2, b2, slope2, C2, mode2, C0 + C1}; A.nterms = 3; }
+  return launch_stage(A, xs, N, H, W, Cpad, (cudaStream_t)stream);
 }
 
 int san_tc_unstage_act(const void* xs, float* x, int N, int C, int H, int W, void* stream) {
@@ -466,11 +503,11 @@ int san_tc_unstage_act(const void* xs, float* x, int N, int C, int H, int W, voi
   return SAN_OK;
 }
 
-int san_tc_stage_weights(const float* w, void* ws, int Cout, int Cin, int K, int dgrad, void* stream) {
+int san_tc_stage_weights(const float* w, void* ws, int H, int W, int Cout, int Cin, int K, int dgrad, void* stream) {
   SAN_CHECK_ARG(w && ws && Cout > 0 && Cin > 0 && (K == 1 || K == 3), "san_tc_stage_weights: bad args");
   TcGeom g;
   const int Co_k = dgrad ? Cin : Cout, Ci_k = dgrad ? Cout : Cin;
-  SAN_CHECK_ARG(tc_geometry(8, 8, Ci_k, Co_k, K, &g), "san_tc_stage_weights: unsupported shape");
+  SAN_CHECK_ARG(tc_geometry(H, W, Ci_k, Co_k, K, &g), "san_tc_stage_weights: unsupported shape");
   const long long total = (long long)g.nsplit * g.KS * K * K * 4 * g.Npad * 8;
   stage_weights_kernel<<<ew_blocks(total), 256, 0, (cudaStream_t)stream>>>(w, (__nv_bfloat16*)ws, Cout, Cin, K * K, dgrad,
                                                                            g.nsplit, g.KS, g.Npad);

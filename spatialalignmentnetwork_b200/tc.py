@@ -1,15 +1,17 @@
-"""Fused convolution blocks on the tcgen05 path (``csrc/conv_tc.cu``).
+"""Fused convolution blocks on the tcgen05 path (``csrc/conv_tc.cu``, ``csrc/wgrad_tc.cu``).
 
-The unit of the U-Nets is not "conv, then InstanceNorm, then LeakyReLU" but
-``conv(act(norm(raw_1)) ++ act(norm(raw_2)) ...)``: the normalisation + activation (+ 2x2 average
-pooling, pixel shuffle of the transposed conv, channel concat of the skip connection; reference
-varnet.py:98,116,139-146,176-181) of the *producing* layers is applied while the operand of the
-*consuming* convolution is staged as BF16 hi/lo tiles, so normalised / activated / concatenated /
-pooled tensors are never written to HBM.  What crosses an autograd edge is always a raw fp32 conv
-output; its per-plane statistics ride along in a ``Raw`` handle and their gradient is folded in
-analytically (the InstanceNorm backward is linear in the incoming gradient, so every consumer
-adds its own contribution).
+The unit of the U-Nets is not "conv, then norm, then LeakyReLU" but
+``conv(concat_k sum_j act(norm(raw_kj)))``: the normalisation + activation (+ 2x2 average pooling, pixel
+shuffle of the transposed conv, nearest up-sampling, channel concat of the skip connection, residual
+add; reference varnet.py:98,116,139-146,176-181, unet.py:6-24,119-140) of the *producing* layers is
+applied while the operand of the *consuming* convolution is staged as BF16 hi/lo tiles, so normalised /
+activated / concatenated / pooled / summed tensors are never written to HBM.  What crosses an autograd
+edge is always a raw fp32 conv output; its per-plane statistics ride along in a ``Raw`` handle and their
+gradient is folded in analytically (the InstanceNorm / BatchNorm backward is linear in the incoming
+gradient, so every consumer adds its own contribution).
 """
+import ctypes
+
 import torch
 from torch.autograd import Function
 from torch.autograd.function import once_differentiable
@@ -20,16 +22,27 @@ MODE_DIRECT, MODE_POOL, MODE_D2S, MODE_UP = 0, 1, 2, 3
 _IN_EPS = 1e-5
 
 
-class Raw:
-    """A raw fp32 NCHW tensor + how it is to be read by a consumer: ``norm`` in {None, 'in'}
-    (InstanceNorm2d, biased variance, eps 1e-5), LeakyReLU ``slope`` (1 = none), and for ``d2s`` the
-    tensor is the [N, 4C, h, w] output of the 1x1 form of ConvTranspose2d(2, stride 2), normalised
-    over all four sub-planes of a channel."""
+class _StageTerm(ctypes.Structure):
+    """``san_stage_term`` of include/san_b200.h."""
+    _fields_ = [("y", ctypes.c_void_p), ("mu", ctypes.c_void_p), ("a", ctypes.c_void_p), ("b", ctypes.c_void_p),
+                ("slope", ctypes.c_float), ("C", ctypes.c_int), ("mode", ctypes.c_int), ("accumulate", ctypes.c_int)]
 
-    def __init__(self, y, norm=None, slope=1.0, d2s=False):
+
+class Raw:
+    """One term of a conv operand: a raw fp32 NCHW tensor + how a consumer reads it.
+
+    ``norm``: None | 'in' (InstanceNorm2d, biased variance, eps 1e-5, varnet.py:141) | 'bn'
+    (``bn`` = the ``nn.BatchNorm2d`` whose affine parameters / running buffers apply, unet.py:125);
+    ``slope``: LeakyReLU slope (1 = none); ``d2s``: the tensor is the [N, 4C, h, w] output of the 1x1 form
+    of ConvTranspose2d(2, stride 2), normalised over all four sub-planes of a channel; ``up``: the tensor
+    is read through nearest x2 up-sampling (BatchNorm statistics of the up-sampled map = those of the
+    low-resolution map with 4x the element count)."""
+
+    def __init__(self, y, norm=None, slope=1.0, d2s=False, bn=None, up=False):
         assert y.dtype == torch.float32 and y.dim() == 4
+        assert (norm == "bn") == (bn is not None)
         self.y = y if y.is_contiguous() else y.contiguous()
-        self.norm, self.slope, self.d2s = norm, float(slope), bool(d2s)
+        self.norm, self.slope, self.d2s, self.bn, self.up = norm, float(slope), bool(d2s), bn, bool(up)
         self._coef = None
 
     @property
@@ -41,16 +54,30 @@ class Raw:
         return (N * C // 4, 4 * H * W) if self.d2s else (N * C, H * W)
 
     def coef(self):
-        """[4, planes] = mean, m2, a (= rstd), b (= 0): computed once per raw tensor, shared by
-        all its consumers (skip connection + pooled path)."""
+        """Per-plane coefficient table, computed once per raw tensor and shared by all its consumers:
+        'in': [4, planes] = mean, m2, a (= rstd), b (= 0);  'bn': [6, planes] = mean, m2, mu, a, b, sa."""
         if self.norm is None:
             return None
         if self._coef is None:
             planes, P = self.planes()
-            st = torch.empty(4, planes, dtype=torch.float32, device=self.y.device)
             yd = self.y.detach()
-            call("plane_stats", yd, st[0], st[1], planes, P)
-            call("in_finalize_fwd", st[0], st[1], st[2], st[3], planes, P, _IN_EPS)
+            if self.norm == "in":
+                st = torch.empty(4, planes, dtype=torch.float32, device=yd.device)
+                call("plane_stats", yd, st[0], st[1], planes, P)
+                call("in_finalize_fwd", st[0], st[1], st[2], st[3], planes, P, _IN_EPS)
+            else:
+                bn = self.bn
+                N, C = yd.shape[0], yd.shape[1]
+                training = bn.training or not bn.track_running_stats
+                st = torch.empty(6, planes, dtype=torch.float32, device=yd.device)
+                if training:
+                    call("plane_stats", yd, st[0], st[1], planes, P)
+                    if bn.track_running_stats:
+                        bn.num_batches_tracked.add_(1)
+                    if self.up:
+                        st[1].mul_(4.0)      # m2 of the up-sampled map
+                call("bn_finalize_fwd", st[0], st[1], bn.weight, bn.bias, bn.running_mean, bn.running_var,
+                     st[2], st[3], st[4], st[5], N, C, P * (4 if self.up else 1), bn.eps, bn.momentum, int(training))
             self._coef = st
         return self._coef
 
@@ -59,22 +86,24 @@ def _staged_act(N, H, W, C, device):
     return torch.empty(lib().san_tc_staged_act_elems(N, H, W, C), dtype=torch.bfloat16, device=device)
 
 
-def _stage(xs, N, H, W, Cpad, srcs):
-    """srcs: list of (y, coef | None, slope, C, mode), at most 3."""
-    assert 1 <= len(srcs) <= 3
-    flat = []
-    for y, st, slope, C, mode in srcs:
-        flat += [y, st[0] if st is not None else None, st[2] if st is not None else None, None, slope, C, mode]
-    for _ in range(3 - len(srcs)):
-        flat += [None, None, None, None, 1.0, 0, 0]
-    call("tc_stage_act", xs, N, H, W, Cpad, *flat)
+def _stage(xs, N, H, W, Cpad, terms):
+    """terms: list of (y, mu, a, b, slope, C, mode, accumulate)."""
+    arr = (_StageTerm * len(terms))()
+    for t, (y, mu, a, b, slope, C, mode, acc) in zip(arr, terms):
+        t.y = y.data_ptr()
+        t.mu = mu.data_ptr() if mu is not None else None
+        t.a = a.data_ptr() if a is not None else None
+        t.b = b.data_ptr() if b is not None else None
+        t.slope, t.C, t.mode, t.accumulate = slope, C, mode, int(acc)
+    call("tc_stage_terms", xs, N, H, W, Cpad, ctypes.addressof(arr), len(terms))
 
 
-def _stage_weights(w, dgrad):
+def _stage_weights(w, dgrad, H, W):
     Cout, Cin, K, _ = w.shape
-    n = lib().san_tc_staged_weight_elems(Cin if dgrad else Cout, Cout if dgrad else Cin, K)
+    n = lib().san_tc_staged_weight_elems(H, W, Cin if dgrad else Cout, Cout if dgrad else Cin, K)
+    assert n > 0, f"tcgen05 conv: unsupported shape H={H} W={W} {tuple(w.shape)}"
     ws = torch.empty(n, dtype=torch.bfloat16, device=w.device)
-    call("tc_stage_weights", w, ws, Cout, Cin, K, int(dgrad))
+    call("tc_stage_weights", w, ws, H, W, Cout, Cin, K, int(dgrad))
     return ws
 
 
@@ -82,16 +111,30 @@ def _pad16(c):
     return (c + 15) // 16 * 16
 
 
+def _coef_views(norm, st):
+    """-> (mu, a, b, sa) rows of a coefficient table."""
+    if st is None:
+        return None, None, None, None
+    if norm == "in":
+        return st[0], st[2], None, st[2]
+    return st[2], st[3], st[4], st[5]
+
+
 class _FusedConv(Function):
-    """y = conv2d(concat_k act_k(norm_k(resample_k(raw_k))), w) + bias on the tcgen05 kernels."""
+    """y = conv2d(concat_k sum_j act(norm(resample(raw_kj))), w) + bias on the tcgen05 kernels.
+
+    inputs: w, bias, spec, then per term: y [, gamma, beta when the term is BatchNorm-normalised]."""
 
     @staticmethod
-    def forward(ctx, w, bias, spec, *ys):
-        # spec: (K, [(norm, slope, d2s, mode, coef)] per source)
-        K, metas = spec
+    def forward(ctx, w, bias, spec, *tensors):
+        K, metas = spec        # metas[i] = (norm, slope, d2s, mode, accumulate, coef, bn_training)
         w = w.contiguous()
         Cout, Cin, Kw, _ = w.shape
         assert Kw == K
+        ys, ti = [], 0
+        for m in metas:
+            ys.append(tensors[ti])
+            ti += 3 if m[0] == "bn" else 1
         y0, m0 = ys[0], metas[0]
         N = y0.shape[0]
         if m0[3] == MODE_POOL:
@@ -100,51 +143,65 @@ class _FusedConv(Function):
             H, W = y0.shape[2] * 2, y0.shape[3] * 2
         else:
             H, W = y0.shape[2], y0.shape[3]
-        srcs, ctot = [], 0
-        for y, (norm, slope, d2s, mode, coef) in zip(ys, metas):
+        terms, ctot = [], 0
+        for y, (norm, slope, d2s, mode, acc, coef, _) in zip(ys, metas):
             C = y.shape[1] // 4 if d2s else y.shape[1]
-            srcs.append((y, coef, slope, C, mode))
-            ctot += C
+            mu, a, b, _sa = _coef_views(norm, coef)
+            terms.append((y, mu, a, b, slope, C, mode, acc))
+            if not acc:
+                ctot += C
         assert ctot == Cin, (ctot, Cin)
-        Cpad = _pad16(Cin)
         xs = _staged_act(N, H, W, Cin, w.device)
-        _stage(xs, N, H, W, Cpad, srcs)
-        ws = _stage_weights(w, False)
+        _stage(xs, N, H, W, _pad16(Cin), terms)
+        ws = _stage_weights(w, False, H, W)
         out = torch.empty(N, Cout, H, W, dtype=torch.float32, device=w.device)
         call("tc_conv", xs, ws, bias, out, N, H, W, Cin, Cout, K, 0)
-        # The staged operand is NOT kept for the backward (it is as large as the fp32 activation and
-        # the padded channels make it larger): the weight gradient re-stages it from the raw tensors,
-        # which autograd holds anyway for the normalisation backward.
-        ctx.save_for_backward(w, *ys, *[m[4] for m in metas if m[4] is not None])
-        ctx.meta = (K, [(m[0], m[1], m[2], m[3], m[4] is not None) for m in metas], (N, H, W), bias is not None)
+        # The staged operand is NOT kept for the backward (it is as large as the fp32 activation and the
+        # padded channels make it larger): the weight gradient re-stages it from the raw tensors, which
+        # autograd holds anyway for the normalisation backward.
+        coefs = [m[5] for m in metas if m[5] is not None]
+        ctx.save_for_backward(w, *tensors, *coefs)
+        ctx.meta = (K, [(m[0], m[1], m[2], m[3], m[4], m[5] is not None, m[6]) for m in metas], (N, H, W),
+                    bias is not None, len(tensors))
         return out
 
     @staticmethod
     @once_differentiable
     def backward(ctx, gy):
-        K, metas, (N, H, W), has_bias = ctx.meta
+        K, metas, (N, H, W), has_bias, ntens = ctx.meta
         saved = ctx.saved_tensors
         w = saved[0]
-        ns = len(metas)
-        ys = saved[1:1 + ns]
-        coefs = list(saved[1 + ns:])
+        tensors = saved[1:1 + ntens]
+        coef_list = list(saved[1 + ntens:])
         Cout, Cin = w.shape[0], w.shape[1]
         gy = gy if gy.is_contiguous() else gy.contiguous()
         dev = w.device
+        # unpack terms
+        terms, ti, ci, c_next, c_prev = [], 0, 0, 0, 0
+        for (norm, slope, d2s, mode, acc, has_coef, bn_training) in metas:
+            y = tensors[ti]
+            gamma = tensors[ti + 1] if norm == "bn" else None
+            C = y.shape[1] // 4 if d2s else y.shape[1]
+            st = coef_list[ci] if has_coef else None
+            ci += int(has_coef)
+            c0 = c_prev if acc else c_next
+            c_prev = c0
+            if not acc:
+                c_next = c0 + C
+            terms.append(dict(y=y, gamma=gamma, norm=norm, slope=slope, d2s=d2s, mode=mode, acc=acc, st=st, C=C, c0=c0,
+                              ti=ti, bn_training=bn_training))
+            ti += 3 if norm == "bn" else 1
         # dY staged once as BF16 hi/lo: the operand of both the data- and the weight-gradient GEMMs
         gys = _staged_act(N, H, W, Cout, dev)
-        _stage(gys, N, H, W, _pad16(Cout), [(gy, None, 1.0, Cout, MODE_DIRECT)])
-        # ---- weight gradient: tcgen05 GEMM over the pixel dimension on the staged dY and the staged input
+        _stage(gys, N, H, W, _pad16(Cout), [(gy, None, None, None, 1.0, Cout, MODE_DIRECT, False)])
+        # ---- weight gradient: tcgen05 GEMM over the pixel dimension on the staged dY and the re-staged input
         dw = db = None
         if ctx.needs_input_grad[0] or (has_bias and ctx.needs_input_grad[1]):
             dw = torch.empty_like(w)
             db = torch.empty(Cout, dtype=torch.float32, device=dev) if has_bias else None
-            xs = _staged_act(N, H, W, Cin, dev)          # re-stage the forward operand
-            ci, srcs = 0, []
-            for y, (norm, slope, d2s, mode, has_coef) in zip(ys, metas):
-                srcs.append((y, coefs[ci] if has_coef else None, slope, y.shape[1] // 4 if d2s else y.shape[1], mode))
-                ci += int(has_coef)
-            _stage(xs, N, H, W, _pad16(Cin), srcs)
+            xs = _staged_act(N, H, W, Cin, dev)
+            _stage(xs, N, H, W, _pad16(Cin),
+                   [(t["y"], *_coef_views(t["norm"], t["st"])[:3], t["slope"], t["C"], t["mode"], t["acc"]) for t in terms])
             if lib().san_tc_wgrad_supported(H, W, Cin, Cout, K):
                 call("tc_wgrad", gys, xs, dw, db, gy if has_bias else None, N, H, W, Cin, Cout, K)
             else:   # tiny images (W < 16): fp32 CUDA-core kernel on the un-staged operand
@@ -154,54 +211,73 @@ class _FusedConv(Function):
                 del x32
             del xs
         # ---- data gradient: the same tcgen05 conv on the staged dY with the flipped filter
-        grads = [None] * ns
-        if any(ctx.needs_input_grad[3 + k] for k in range(ns)):
-            wsd = _stage_weights(w, True)
+        grads = [None] * ntens
+        if any(ctx.needs_input_grad[3 + t["ti"]] for t in terms):
+            wsd = _stage_weights(w, True, H, W)
             dx = torch.empty(N, Cin, H, W, dtype=torch.float32, device=dev)
             call("tc_conv", gys, wsd, None, dx, N, H, W, Cout, Cin, K, 0)
             del gys
-            c0 = 0
-            for k, (norm, slope, d2s, mode, has_coef) in enumerate(metas):
-                y = ys[k]
-                C = y.shape[1] // 4 if d2s else y.shape[1]
-                if ctx.needs_input_grad[3 + k]:
-                    g = dx[:, c0:c0 + C]
-                    g = g if g.is_contiguous() else g.contiguous()
-                    # undo the resampling: gradient at the resolution / layout of the raw tensor
-                    if mode == MODE_POOL:
-                        gs = torch.empty_like(y)
-                        call("up2", g, gs, N * C, H, W, 0.25)
-                    elif mode == MODE_D2S:
-                        gs = torch.empty_like(y)
-                        call("space_to_depth2", g, gs, N, C, H // 2, W // 2)
-                    elif mode == MODE_UP:
-                        gs = torch.empty_like(y)
-                        call("pool2", g, gs, N * C, H, W, 1.0)
-                    else:
-                        gs = g
-                    if has_coef:
-                        st = coefs.pop(0)
-                        planes = st.shape[1]
-                        P = y.numel() // planes
-                        wk = torch.empty(5, planes, dtype=torch.float32, device=dev)
-                        call("act_bwd_reduce", gs, y, st[0], st[2], None, st[2], slope, wk[0], wk[1], planes, P)
-                        call("in_finalize_bwd", wk[0], wk[1], st[2], wk[2], wk[3], wk[4], planes, P)
-                        dy = torch.empty_like(y)
-                        call("act_bwd_apply", gs, y, st[0], st[2], None, slope, wk[2], wk[3], wk[4], dy, planes, P)
-                        grads[k] = dy
-                    else:
-                        assert slope == 1.0
-                        grads[k] = gs
-                elif has_coef:
-                    coefs.pop(0)
-                c0 += C
+            for t in terms:
+                if not ctx.needs_input_grad[3 + t["ti"]]:
+                    continue
+                y, C, mode, slope, st = t["y"], t["C"], t["mode"], t["slope"], t["st"]
+                g = dx[:, t["c0"]:t["c0"] + C]
+                g = g if g.is_contiguous() else g.contiguous()
+                # undo the resampling: gradient at the resolution / layout of the raw tensor
+                if mode == MODE_POOL:
+                    gs = torch.empty_like(y)
+                    call("up2", g, gs, N * C, H, W, 0.25)
+                elif mode == MODE_D2S:
+                    gs = torch.empty_like(y)
+                    call("space_to_depth2", g, gs, N, C, H // 2, W // 2)
+                elif mode == MODE_UP:
+                    gs = torch.empty_like(y)
+                    call("pool2", g, gs, N * C, H, W, 1.0)
+                else:
+                    gs = g
+                if st is None and slope == 1.0:
+                    grads[t["ti"]] = gs
+                    continue
+                if st is None:      # bare LeakyReLU (cross.py:14)
+                    planes = y.shape[0] * y.shape[1]
+                    P = y.numel() // planes
+                    ones = torch.ones(planes, dtype=torch.float32, device=dev)
+                    dy = torch.empty_like(y)
+                    call("act_bwd_apply", gs, y, None, ones, None, slope, ones, None, None, dy, planes, P)
+                    grads[t["ti"]] = dy
+                    continue
+                planes = st.shape[1]
+                P = y.numel() // planes
+                mu, a, b, sa = _coef_views(t["norm"], st)
+                wk = torch.empty(5, planes, dtype=torch.float32, device=dev)
+                call("act_bwd_reduce", gs, y, mu, a, b, sa, slope, wk[0], wk[1], planes, P)
+                if t["norm"] == "in":
+                    call("in_finalize_bwd", wk[0], wk[1], a, wk[2], wk[3], wk[4], planes, P)
+                else:
+                    gamma = t["gamma"]
+                    dgamma, dbeta = torch.empty_like(gamma), torch.empty_like(gamma)
+                    call("bn_finalize_bwd", wk[0], wk[1], gamma, sa, wk[2], wk[3], wk[4], dgamma, dbeta,
+                         y.shape[0], y.shape[1], P, int(t["bn_training"]))
+                    grads[t["ti"] + 1], grads[t["ti"] + 2] = dgamma, dbeta
+                dy = torch.empty_like(y)
+                call("act_bwd_apply", gs, y, mu, a, b, slope, wk[2], wk[3], wk[4], dy, planes, P)
+                grads[t["ti"]] = dy
         return (dw, db, None, *grads)
 
 
 def fused_conv(sources, weight, bias=None, modes=None):
-    """sources: list of ``Raw``; modes: per-source resampling mode (default direct; a ``d2s`` source
-    is read through the pixel shuffle).  Returns the raw fp32 conv output tensor."""
-    modes = modes or [MODE_D2S if s.d2s else MODE_DIRECT for s in sources]
-    metas = [(s.norm, s.slope, s.d2s, m, s.coef()) for s, m in zip(sources, modes)]
+    """sources: list whose items are a ``Raw`` or a list of ``Raw`` (their SUM); the items are
+    concatenated along channels.  modes: per-source resampling mode (default: direct; pixel shuffle for a
+    ``d2s`` term; nearest x2 for an ``up`` term).  Returns the raw fp32 conv output tensor."""
+    metas, tensors = [], []
+    for i, src in enumerate(sources):
+        group = src if isinstance(src, (list, tuple)) else [src]
+        for j, r in enumerate(group):
+            mode = modes[i] if modes is not None else (MODE_D2S if r.d2s else MODE_UP if r.up else MODE_DIRECT)
+            bn_training = bool(r.bn.training or not r.bn.track_running_stats) if r.norm == "bn" else False
+            metas.append((r.norm, r.slope, r.d2s, mode, j > 0, r.coef(), bn_training))
+            tensors.append(r.y)
+            if r.norm == "bn":
+                tensors += [r.bn.weight, r.bn.bias]
     K = weight.shape[-1]
-    return _FusedConv.apply(weight, bias, (K, metas), *[s.y for s in sources])
+    return _FusedConv.apply(weight, bias, (K, metas), *tensors)

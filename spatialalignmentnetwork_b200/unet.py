@@ -9,11 +9,14 @@ LeakyReLU(0.01), 2x2 average pooling, nearest up-sampling, residual add.
 ``Encoder`` / ``Decoder`` / ``ResNet`` of the reference are dead code (only referenced
 from commented-out lines) and are not provided.
 """
+import os
+
 import torch
 
-from . import ops
+from . import ops, tc
 
 _SLOPE = 0.01  # torch.nn.LeakyReLU default
+USE_TC = os.environ.get("SAN_TC", "1") != "0"   # 0: layer-by-layer fp32 CUDA-core kernels (debug / A-B)
 
 
 class CatSequential(torch.nn.Module):
@@ -146,4 +149,44 @@ class UNet(torch.nn.Module):
             Conv2dB200(current_layer, out_channels, 3, padding=1))
 
     def forward(self, x):
+        if USE_TC:
+            return self.forward_sources([x])
         return self.unet(x)
+
+    # ---- fused tcgen05 path -------------------------------------------------------------------------
+    # Every activated tensor of the reference graph is a SUM of at most two (raw conv output ->
+    # BatchNorm -> LeakyReLU) terms (ResSequential, unet.py:15-24) and every conv input a concatenation
+    # of such sums (CatSequential, unet.py:6-13), optionally average-pooled (Down) or nearest-up-sampled
+    # (Up).  tc.fused_conv applies all of that while staging the operand of the consuming conv.
+    @staticmethod
+    def _convbn(blk, srcs, modes=None):
+        y = tc.fused_conv(srcs, blk[0].weight, blk[0].bias, modes=modes)
+        return tc.Raw(y, "bn", _SLOPE, bn=blk[1])
+
+    @classmethod
+    def _res(cls, res, S):
+        assert res.sample is None
+        out = S
+        for blk in res.subnet:
+            out = [cls._convbn(blk, [out])]
+        return list(S) + out                                   # x + subnet(x)
+
+    @classmethod
+    def _cat(cls, cat, S):
+        """-> the two concatenated sources [module(x), x] of a CatSequential (module output first)."""
+        m = cat.module
+        yd = tc.fused_conv([S], m[0][1].weight, m[0][1].bias, modes=[tc.MODE_POOL])        # Down: pool -> 1x1
+        r = cls._res(m[1], [tc.Raw(yd, "bn", _SLOPE, bn=m[0][2])])
+        if len(m) > 3:
+            r = cls._res(m[4], [cls._convbn(m[3], cls._cat(m[2], r))])
+        up = m[len(m) - 1]
+        # Up: a 1x1 conv commutes with nearest up-sampling -> convolve at low resolution, replicate on read
+        yu = tc.fused_conv([r], up[1].weight, up[1].bias)
+        return [[tc.Raw(yu, "bn", _SLOPE, bn=up[2], up=True)], S]
+
+    def forward_sources(self, images):
+        """images: list of fp32 NCHW tensors whose channel concatenation is the network input."""
+        u = self.unet
+        a = self._res(u[1], [self._convbn(u[0], [tc.Raw(im) for im in images])])
+        r = self._res(u[4], [self._convbn(u[3], self._cat(u[2], a))])
+        return tc.fused_conv([r], u[5].weight, u[5].bias)

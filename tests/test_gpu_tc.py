@@ -34,9 +34,9 @@ def conv_tc(x, w, bias=None, dgrad=False):
     N, Cin, H, W = x.shape
     Cout, Cin_w, K, _ = w.shape
     xs = stage(x)
-    ws = torch.empty(L.lib().san_tc_staged_weight_elems(Cin_w if dgrad else Cout, Cout if dgrad else Cin_w, K),
+    ws = torch.empty(L.lib().san_tc_staged_weight_elems(H, W, Cin_w if dgrad else Cout, Cout if dgrad else Cin_w, K),
                      dtype=torch.bfloat16, device=x.device)
-    L.call("tc_stage_weights", w, ws, Cout, Cin_w, K, int(dgrad))
+    L.call("tc_stage_weights", w, ws, H, W, Cout, Cin_w, K, int(dgrad))
     co = Cin_w if dgrad else Cout
     y = torch.empty(N, co, H, W, dtype=torch.float32, device=x.device)
     L.call("tc_conv", xs, ws, bias, y, N, H, W, Cin, co, K, 0)
@@ -49,6 +49,7 @@ TC_CASES = [
     (1, 72, 20, 20, 144, 3, False), (1, 144, 20, 20, 288, 3, False), (1, 288, 10, 12, 288, 3, False),
     (2, 18, 32, 32, 2, 1, True), (1, 288, 10, 10, 576, 1, False), (2, 2, 33, 47, 32, 3, True),
     (1, 96, 24, 40, 32, 3, True), (3, 64, 17, 23, 64, 1, True), (1, 18, 320, 320, 18, 3, False),
+    (1, 96, 320, 320, 32, 3, True),     # dgrad = 32 -> 96 at full width: needs the output-channel split
 ]
 
 
@@ -228,3 +229,55 @@ def test_tc_wgrad(case):
     assert rel_l2(dw, wr.grad) < 2e-5
     if has_bias:
         assert rel_l2(db, br.grad) < 1e-5
+
+
+def test_fused_conv_batchnorm_sum_up_pool():
+    """net_T operands (unet.py:6-24,119-140): concat[ nearest-up(lrelu(BN(yu))), lrelu(BN(ya)) + lrelu(BN(yb)) ]
+    and avg-pool of a sum, BatchNorm in training mode (batch statistics, running-buffer update), vs torch fp64."""
+    from spatialalignmentnetwork_b200 import tc
+    torch.manual_seed(51)
+    N, H, W, C = 3, 16, 24, 8
+    ys = [torch.randn(N, C, H // 2, W // 2) + 0.4, torch.randn(N, C, H, W) * 1.3, torch.randn(N, C, H, W) - 0.2]
+    bns = [torch.nn.BatchNorm2d(C) for _ in range(3)]
+    for bn in bns:
+        with torch.no_grad():
+            bn.weight.uniform_(0.5, 1.5); bn.bias.uniform_(-0.3, 0.3)
+    w = torch.randn(12, 2 * C, 3, 3) / math.sqrt(2 * C * 9)
+    b = torch.randn(12)
+    gy = torch.randn(N, 12, H, W)
+    import copy
+    bnr = [copy.deepcopy(bn).double().train() for bn in bns]
+    yr = [t.double().requires_grad_(True) for t in ys]
+    wr, br = w.double().requires_grad_(True), b.double().requires_grad_(True)
+    act = lambda bn, t: F.leaky_relu(bn(t), 0.01)
+    up = act(bnr[0], yr[0].repeat_interleave(2, 2).repeat_interleave(2, 3))
+    outr = F.conv2d(torch.cat([up, act(bnr[1], yr[1]) + act(bnr[2], yr[2])], 1), wr, br, padding=1)
+    (outr * gy.double()).sum().backward()
+    bnc = [copy.deepcopy(bn).cuda().train() for bn in bns]
+    yc = [t.cuda().requires_grad_(True) for t in ys]
+    wc, bc = w.cuda().requires_grad_(True), b.cuda().requires_grad_(True)
+    srcs = [[tc.Raw(yc[0], "bn", 0.01, bn=bnc[0], up=True)],
+            [tc.Raw(yc[1], "bn", 0.01, bn=bnc[1]), tc.Raw(yc[2], "bn", 0.01, bn=bnc[2])]]
+    outc = tc.fused_conv(srcs, wc, bc)
+    (outc * gy.cuda()).sum().backward()
+    assert rel_l2(outc, outr) < 2e-5
+    for a, r in zip(yc, yr):
+        assert rel_l2(a.grad, r.grad) < 5e-5
+    assert rel_l2(wc.grad, wr.grad) < 2e-5 and rel_l2(bc.grad, br.grad) < 2e-5
+    for a, r in zip(bnc, bnr):
+        assert rel_l2(a.weight.grad, r.weight.grad) < 2e-5 and rel_l2(a.bias.grad, r.bias.grad) < 2e-5
+        assert rel_l2(a.running_mean, r.running_mean) < 1e-6 and rel_l2(a.running_var, r.running_var) < 1e-6
+        assert int(a.num_batches_tracked) == 1
+    # pooled sum + bare LeakyReLU term
+    yp = [torch.randn(N, C, 2 * H, 2 * W), torch.randn(N, C, 2 * H, 2 * W)]
+    w2 = torch.randn(5, C, 1, 1)
+    g2 = torch.randn(N, 5, H, W)
+    ypr = [t.double().requires_grad_(True) for t in yp]
+    o2 = F.conv2d(F.avg_pool2d(F.leaky_relu(ypr[0], 0.01) + ypr[1], 2), w2.double())
+    (o2 * g2.double()).sum().backward()
+    ypc = [t.cuda().requires_grad_(True) for t in yp]
+    o2c = tc.fused_conv([[tc.Raw(ypc[0], None, 0.01), tc.Raw(ypc[1])]], w2.cuda(), None, modes=[tc.MODE_POOL])
+    (o2c * g2.cuda()).sum().backward()
+    assert rel_l2(o2c, o2) < 2e-5
+    for a, r in zip(ypc, ypr):
+        assert rel_l2(a.grad, r.grad) < 5e-5

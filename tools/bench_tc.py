@@ -33,12 +33,12 @@ def main():
         x = torch.randn(N, Cin, HW, HW, device="cuda")
         w = torch.randn(Cout, Cin, K, K, device="cuda") / math.sqrt(Cin * K * K)
         xs = torch.empty(L.lib().san_tc_staged_act_elems(N, HW, HW, Cin), dtype=torch.bfloat16, device="cuda")
-        ws = torch.empty(L.lib().san_tc_staged_weight_elems(Cout, Cin, K), dtype=torch.bfloat16, device="cuda")
+        ws = torch.empty(L.lib().san_tc_staged_weight_elems(HW, HW, Cout, Cin, K), dtype=torch.bfloat16, device="cuda")
         y = torch.empty(N, Cout, HW, HW, device="cuda")
         Cpad = (Cin + 15) // 16 * 16
         st = lambda: L.call("tc_stage_act", xs, N, HW, HW, Cpad, x, None, None, None, 1.0, Cin, 0,
                             None, None, None, None, 1.0, 0, 0, None, None, None, None, 1.0, 0, 0)
-        L.call("tc_stage_weights", w, ws, Cout, Cin, K, 0)
+        L.call("tc_stage_weights", w, ws, HW, HW, Cout, Cin, K, 0)
         cv = lambda: L.call("tc_conv", xs, ws, None, y, N, HW, HW, Cin, Cout, K, 0)
         wp = ops._pack(w, False)
         y2 = torch.empty_like(y)
