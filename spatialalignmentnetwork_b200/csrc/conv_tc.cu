@@ -301,63 +301,135 @@ __device__ __forceinline__ float act1(float v, float mu, float a, float b, float
   return z > 0.f ? z : z * slope;
 }
 
-__device__ __forceinline__ float stage_term_value(const StageTerm& S, int n, int c, int h, int w, int H, int W) {
-  const long long plane = (long long)n * S.C + c;
-  float mu = 0.f, a = 1.f, b = 0.f;
-  if (S.a) { mu = S.mu ? __ldg(S.mu + plane) : 0.f; a = __ldg(S.a + plane); b = S.b ? __ldg(S.b + plane) : 0.f; }
-  if (S.mode == 0) return act1(__ldg(S.y + (plane * H + h) * W + w), mu, a, b, S.slope);
-  if (S.mode == 1) {
-    const int Ws2 = 2 * W;
-    const float* q = S.y + (plane * (2 * H) + 2 * h) * Ws2 + 2 * w;
-    const float2 r0 = __ldg((const float2*)q), r1 = __ldg((const float2*)(q + Ws2));
-    return 0.25f * ((act1(r0.x, mu, a, b, S.slope) + act1(r0.y, mu, a, b, S.slope)) +
-                    (act1(r1.x, mu, a, b, S.slope) + act1(r1.y, mu, a, b, S.slope)));
+// Per-block work list: for each of the 8 channels of the block's channel group, the (at most
+// STAGE_MAX_SUM) terms that contribute to it, with everything that does not depend on the pixel slot
+// resolved once (plane base pointer, coefficients).  Missing entries are neutral dummies (a = 0, a
+// valid address), so the slot loop has no data-dependent control flow: the 8 (x2 slots) loads of one
+// term level are issued back to back and their latencies overlap.  (The first version walked the terms
+// per channel with dynamic loops: 8 serialised global loads per pixel, latency-bound at 2.7 TB/s.)
+constexpr int STAGE_MAX_SUM = 3;
+struct StageEntry {
+  const float* base;   // plane base (mode 2: base of the 4 sub-planes of the channel)
+  float mu, a, b, slope;
+  int mode;            // 0 direct, 1 pool, 2 pixel shuffle, 3 nearest up, 4 dummy
+  int pad;
+};
+__device__ float g_stage_zero[4] = {0.f, 0.f, 0.f, 0.f};
+
+struct SlotOffs { int off0, offu, offs2, offp; bool inb; };
+__device__ __forceinline__ SlotOffs slot_offsets(int slot, const StageArgs& A, int Wh, int HWq, int W2) {
+  const int hp = slot / A.Wp, wp = slot - hp * A.Wp;
+  const int h = hp - 1, w = wp - 1;
+  SlotOffs o;
+  o.inb = (slot < A.PS) && h >= 0 && h < A.H && w >= 0 && w < A.W;
+  const int hh = o.inb ? h : 0, ww = o.inb ? w : 0;
+  o.off0 = hh * A.W + ww;
+  o.offu = (hh >> 1) * Wh + (ww >> 1);
+  o.offs2 = o.offu + ((hh & 1) * 2 + (ww & 1)) * HWq;
+  o.offp = (2 * hh) * W2 + 2 * ww;
+  return o;
+}
+__device__ __forceinline__ int pick_off(int mode, const SlotOffs& o) {
+  return mode == 0 ? o.off0 : (mode == 2 ? o.offs2 : (mode == 3 ? o.offu : 0));
+}
+__device__ __forceinline__ void store_split(__nv_bfloat16* xs, long long o_hi, long long o_lo, int slot, const float* v) {
+  uint32_t hw[4], lw[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const __nv_bfloat16 h0 = __float2bfloat16_rn(v[2 * j]), h1 = __float2bfloat16_rn(v[2 * j + 1]);
+    const __nv_bfloat16 l0 = __float2bfloat16_rn(v[2 * j] - __bfloat162float(h0));
+    const __nv_bfloat16 l1 = __float2bfloat16_rn(v[2 * j + 1] - __bfloat162float(h1));
+    hw[j] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
+    lw[j] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
   }
-  const int Hs = H / 2, Wsrc = W / 2;
-  if (S.mode == 2) {
-    const long long sp = ((long long)n * S.C * 4 + c * 4 + (h & 1) * 2 + (w & 1));
-    return act1(__ldg(S.y + (sp * Hs + (h >> 1)) * Wsrc + (w >> 1)), mu, a, b, S.slope);
-  }
-  return act1(__ldg(S.y + (plane * Hs + (h >> 1)) * Wsrc + (w >> 1)), mu, a, b, S.slope);
+  *(uint4*)(xs + (o_hi + slot) * 8) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
+  *(uint4*)(xs + (o_lo + slot) * 8) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
 }
 
-// one thread = one pixel slot x one channel group of 8: two 16 B stores (hi, lo).
-// grid = (slot blocks, N*KG): no 64-bit divisions on the hot path.  A channel is the SUM of every
-// term whose channel range [c0, c0 + C) contains it (residual adds of unet.py:15-24 are sums of two
-// activated tensors; concatenation = disjoint ranges).
-__global__ void __launch_bounds__(256) stage_act_kernel(const StageArgs A) {
+// one thread = two pixel slots x one channel group of 8 per iteration: four 16 B stores (hi, lo).
+// grid = (slot blocks, N*KG).  A channel is the SUM of every term whose channel range [c0, c0 + C)
+// contains it (residual adds of unet.py:15-24 are sums of two activated tensors; concatenation =
+// disjoint ranges).
+__global__ void __launch_bounds__(256, 3) stage_act_kernel(const StageArgs A) {
+  __shared__ StageEntry ent[STAGE_MAX_SUM][8];
+  __shared__ int s_kmax, s_pool;
   const int n = blockIdx.y / A.KG, kg = blockIdx.y - n * A.KG;
-  // which terms touch this channel group at all (uniform over the block)
-  unsigned live = 0;
-  for (int t = 0; t < A.nterms; ++t)
-    if (A.s[t].c0 < kg * 8 + 8 && A.s[t].c0 + A.s[t].C > kg * 8) live |= 1u << t;
+  if (threadIdx.x == 0) { s_kmax = 0; s_pool = 0; }
+  __syncthreads();
+  if (threadIdx.x < 8) {
+    const int j = threadIdx.x;
+    int k = 0;
+    for (int t = 0; t < A.nterms && k < STAGE_MAX_SUM; ++t) {
+      const StageTerm& S = A.s[t];
+      const int c = kg * 8 + j - S.c0;
+      if (c < 0 || c >= S.C) continue;
+      const long long plane = (long long)n * S.C + c;
+      StageEntry E;
+      E.mode = S.mode; E.slope = S.slope; E.pad = 0;
+      E.mu = 0.f; E.a = 1.f; E.b = 0.f;
+      if (S.a) { E.mu = S.mu ? S.mu[plane] : 0.f; E.a = S.a[plane]; E.b = S.b ? S.b[plane] : 0.f; }
+      const long long src_hw = (S.mode == 0) ? (long long)A.H * A.W : (S.mode == 1) ? 4LL * A.H * A.W : (long long)(A.H / 2) * (A.W / 2);
+      E.base = S.y + (S.mode == 2 ? plane * 4 : plane) * src_hw;
+      if (S.mode == 1) atomicOr(&s_pool, 1);
+      ent[k++][j] = E;
+    }
+    atomicMax(&s_kmax, k);
+    for (; k < STAGE_MAX_SUM; ++k) ent[k][j] = StageEntry{g_stage_zero, 0.f, 0.f, 0.f, 1.f, 4, 0};
+  }
+  __syncthreads();
+  const int kmax = s_kmax;
+  const bool pooled = s_pool != 0;
   const long long o_hi = ((long long)(n * 2 + 0) * A.KG + kg) * A.PS;
   const long long o_lo = ((long long)(n * 2 + 1) * A.KG + kg) * A.PS;
-  for (int slot = blockIdx.x * blockDim.x + threadIdx.x; slot < A.PS; slot += gridDim.x * blockDim.x) {
-    const int hp = slot / A.Wp, wp = slot - hp * A.Wp;
-    const int h = hp - 1, w = wp - 1;
-    float v[8];
+  const int Wh = A.W / 2, HWq = (A.H / 2) * Wh, W2 = 2 * A.W;
+  const int stride = gridDim.x * blockDim.x;
+  for (int slot = blockIdx.x * blockDim.x + threadIdx.x; slot < A.PS; slot += 2 * stride) {
+    const int slotB = slot + stride;
+    const SlotOffs oA = slot_offsets(slot, A, Wh, HWq, W2), oB = slot_offsets(slotB, A, Wh, HWq, W2);
+    float vA[8], vB[8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) v[j] = 0.f;
-    if (live && h >= 0 && h < A.H && w >= 0 && w < A.W) {
-      for (int t = 0; t < A.nterms; ++t) {
-        if (!(live >> t & 1)) continue;
-        const StageTerm& S = A.s[t];
+    for (int j = 0; j < 8; ++j) { vA[j] = 0.f; vB[j] = 0.f; }
+    if (!pooled) {
+      for (int k = 0; k < kmax; ++k) {
+        float rA[8], rB[8];
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-          const int c = kg * 8 + j - S.c0;
-          if (c >= 0 && c < S.C) v[j] += stage_term_value(S, n, c, h, w, A.H, A.W);
+          const StageEntry& E = ent[k][j];
+          rA[j] = __ldg(E.base + pick_off(E.mode, oA));
+          rB[j] = __ldg(E.base + pick_off(E.mode, oB));
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const StageEntry& E = ent[k][j];
+          vA[j] += act1(rA[j], E.mu, E.a, E.b, E.slope);
+          vB[j] += act1(rB[j], E.mu, E.a, E.b, E.slope);
+        }
+      }
+    } else {
+      for (int k = 0; k < kmax; ++k) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const StageEntry& E = ent[k][j];
+          if (E.mode == 1) {
+            const float* qa = E.base + oA.offp;
+            const float* qb = E.base + oB.offp;
+            const float2 a0 = __ldg((const float2*)qa), a1 = __ldg((const float2*)(qa + W2));
+            const float2 b0 = __ldg((const float2*)qb), b1 = __ldg((const float2*)(qb + W2));
+            vA[j] += 0.25f * ((act1(a0.x, E.mu, E.a, E.b, E.slope) + act1(a0.y, E.mu, E.a, E.b, E.slope)) +
+                              (act1(a1.x, E.mu, E.a, E.b, E.slope) + act1(a1.y, E.mu, E.a, E.b, E.slope)));
+            vB[j] += 0.25f * ((act1(b0.x, E.mu, E.a, E.b, E.slope) + act1(b0.y, E.mu, E.a, E.b, E.slope)) +
+                              (act1(b1.x, E.mu, E.a, E.b, E.slope) + act1(b1.y, E.mu, E.a, E.b, E.slope)));
+          } else {
+            vA[j] += act1(__ldg(E.base + pick_off(E.mode, oA)), E.mu, E.a, E.b, E.slope);
+            vB[j] += act1(__ldg(E.base + pick_off(E.mode, oB)), E.mu, E.a, E.b, E.slope);
+          }
         }
       }
     }
-    __align__(16) __nv_bfloat16 hi[8], lo[8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      hi[j] = __float2bfloat16_rn(v[j]);
-      lo[j] = __float2bfloat16_rn(v[j] - __bfloat162float(hi[j]));
-    }
-    *(uint4*)(A.xs + (o_hi + slot) * 8) = *(const uint4*)hi;
-    *(uint4*)(A.xs + (o_lo + slot) * 8) = *(const uint4*)lo;
+    for (int j = 0; j < 8; ++j) { vA[j] = oA.inb ? vA[j] : 0.f; vB[j] = oB.inb ? vB[j] : 0.f; }
+    store_split(A.xs, o_hi, o_lo, slot, vA);
+    if (slotB < A.PS) store_split(A.xs, o_hi, o_lo, slotB, vB);
   }
   // zero lead-in / trailing slack of the buffer (see TC_LEAD / TC_TRAIL)
   if (blockIdx.x == 0 && blockIdx.y == 0) {
@@ -454,9 +526,10 @@ static int launch_stage(StageArgs& A, void* xs, int N, int H, int W, int Cpad, c
   A.xs = (__nv_bfloat16*)xs + TC_LEAD;
   A.N = N; A.H = H; A.W = W; A.Wp = W + 2; A.PS = (H + 2) * (W + 2); A.KG = Cpad / 8;
   SAN_CHECK_ARG((long long)N * A.KG <= 65535, "san_tc_stage: N*KG too large for grid.y");
-  int bx = (A.PS + 255) / 256;
-  const int want = (san_num_sms() * 8 + N * A.KG - 1) / (N * A.KG);   // >= 8 blocks per SM overall
-  if (bx > want) bx = want < 1 ? 1 : want;
+  // ~4 pixel slots per thread: the per-block work-list setup is amortised over 1024 slots and there are
+  // enough blocks for dozens of waves (no tail effect)
+  int bx = (A.PS + 1023) / 1024;
+  if (bx < 1) bx = 1;
   stage_act_kernel<<<dim3(bx, N * A.KG), 256, 0, st>>>(A);
   SAN_LAUNCH_CHECK();
   return SAN_OK;
