@@ -134,23 +134,26 @@ __device__ __forceinline__ void mma_issue_loop(const ConvTcParams& p, const TcGe
       const uint32_t a_s = (stage0 + (uint32_t)s * g.stage_bytes) >> 4;   // 16 B units
       const uint32_t b_s = a_s + ((uint32_t)g.a_bytes >> 4);
       const uint32_t first = (ks != 0);
-      uint32_t d = acc0, a_t = a_lo0 + a_s;
-      for (int t = 0; t < g.T; ++t, d += g.Npad, a_t += 128) {
+      if (elect_one_sync()) {
+        uint32_t d = acc0, a_t = a_lo0 + a_s;
+        for (int t = 0; t < g.T; ++t, d += g.Npad, a_t += 128) {
 #pragma unroll
-        for (int tap = 0; tap < NTAPS; ++tap) {
-          const uint32_t al = a_t + tap_off[tap];
-          const uint32_t bl = b_lo0 + b_s + tap * b_tapstride;
-          const uint64_t A_hi = ((uint64_t)a_hi << 32) | al, A_lo = ((uint64_t)a_hi << 32) | (al + a_losplit);
-          const uint64_t B_hi = ((uint64_t)b_hi << 32) | bl, B_lo = ((uint64_t)b_hi << 32) | (bl + b_losplit);
-          tc_mma_bf16(d, A_hi, B_hi, idesc, tap == 0 ? first : 1u);   // hi*hi
-          tc_mma_bf16(d, A_lo, B_hi, idesc, 1u);                      // lo*hi
-          tc_mma_bf16(d, A_hi, B_lo, idesc, 1u);                      // hi*lo
+          for (int tap = 0; tap < NTAPS; ++tap) {
+            const uint32_t al = a_t + tap_off[tap];
+            const uint32_t bl = b_lo0 + b_s + tap * b_tapstride;
+            const uint64_t A_hi = ((uint64_t)a_hi << 32) | al, A_lo = ((uint64_t)a_hi << 32) | (al + a_losplit);
+            const uint64_t B_hi = ((uint64_t)b_hi << 32) | bl, B_lo = ((uint64_t)b_hi << 32) | (bl + b_losplit);
+            tc_mma_bf16(d, A_hi, B_hi, idesc, tap == 0 ? first : 1u);   // hi*hi
+            tc_mma_bf16(d, A_lo, B_hi, idesc, 1u);                      // lo*hi
+            tc_mma_bf16(d, A_hi, B_lo, idesc, 1u);                      // hi*lo
+          }
         }
+        tc_commit(bar_empty + 8 * s);  // frees the smem stage when these MMAs retire
+        if (ks == g.KS - 1) tc_commit(bar_accf + 8 * as);   // accumulators of this unit complete
       }
-      tc_commit(bar_empty + 8 * s);  // frees the smem stage when these MMAs retire
+      __syncwarp();
       if (++s == g.stages) { s = 0; ph ^= 1; }
     }
-    tc_commit(bar_accf + 8 * as);    // accumulators of this unit complete
     if (++as == g.acc_stages) { as = 0; aph ^= 1; }
   }
 }
@@ -180,7 +183,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const ConvTcPara
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);   // warp-uniform by construction
 
   const int units_per_image = g.strips * g.nsplit;
   const long long plane_elems = (long long)g.PS * 8;  // elements of one (n, hl, kg) plane
@@ -220,10 +223,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const ConvTcPara
     // One thread issues every tcgen05.mma of the CTA, so the loop is written for issue rate: the
     // shared-memory descriptors are built once and advanced by adding 16-byte-unit offsets to
     // their low word; taps and the three hi/lo products are fully unrolled.
-    if (lane == 0) {
-      if (p.ntaps == 9) mma_issue_loop<9>(p, g, tmem_base, stage0, bar_full, bar_empty, bar_accf, bar_acce);
-      else mma_issue_loop<1>(p, g, tmem_base, stage0, bar_full, bar_empty, bar_accf, bar_acce);
-    }
+    // (whole warp: the loops are warp-uniform, one elected lane issues)
+    if (p.ntaps == 9) mma_issue_loop<9>(p, g, tmem_base, stage0, bar_full, bar_empty, bar_accf, bar_acce);
+    else mma_issue_loop<1>(p, g, tmem_base, stage0, bar_full, bar_empty, bar_accf, bar_acce);
   } else {
     // ================================ epilogue ====================================
     const int wq = warp & 3;  // TMEM lane quarter this warp may access

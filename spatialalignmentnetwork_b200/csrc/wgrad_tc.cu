@@ -13,6 +13,13 @@
 // row dy); the CTAs of a group split the pixel range of all images into chunks of KC slots and keep
 // three [128 x Nn] fp32 accumulators (dx = 0, 1, 2) in TMEM for the whole kernel; one atomicAdd pass
 // per CTA at the end.  BF16x3 as in the forward: hi*hi + lo*hi + hi*lo.
+//
+// Narrow layers (<= 64 padded output channels) would leave most of the 128 UMMA rows empty while the
+// MMA still reads a full A tile from shared memory (the A read, not the tensor pipe, bounds N <= 64
+// MMAs).  There the hi and lo halves of dY - adjacent in the smem tile - are used as ONE stacked A
+// operand [hi; lo]: D = [hi; lo] * X_hi + [hi; lo] * X_lo gives all four partial products in 2 MMAs
+// (rows co and co + Cpad are both added into dW[co]); with <= 32 padded channels the stack is 64 rows
+// and the M = 64 UMMA shape halves the A read again.
 //   warp 0: TMA producer (bulk copies of the dY chunk and the X span per stage)
 //   warp 1: TMEM allocator + single-thread MMA issuer
 //   warps 2..5: final epilogue (tcgen05.ld -> atomicAdd into dW[Cout][Cin][K][K])
@@ -103,7 +110,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_tc_kernel(const WgParams 
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);   // warp-uniform by construction
 
   // group of this CTA
   const int grp = blockIdx.x / p.ctas_per_group, cta = blockIdx.x - grp * p.ctas_per_group;
@@ -144,25 +151,29 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_tc_kernel(const WgParams 
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      const uint32_t idesc = umma_idesc_bf16(128, g.Nn, /*mn_major=*/1);
-      // MN-major, no swizzle: LBO = 128 B between 8-slot K groups, SBO = one staged plane between channel groups
-      const uint64_t a_tmpl = umma_desc(0, 128, (uint32_t)g.KC * 16);
-      const uint64_t b_tmpl = umma_desc(0, 128, (uint32_t)g.XS * 16);
-      const uint32_t a_hiw = (uint32_t)(a_tmpl >> 32), b_hiw = (uint32_t)(b_tmpl >> 32);
-      const uint32_t a_low = (uint32_t)a_tmpl, b_low = (uint32_t)b_tmpl;
-      const uint32_t a_losplit = (uint32_t)(kga * g.KC);        // hi -> lo half, 16 B units
-      const uint32_t b_losplit = (uint32_t)(g.KGn * g.XS);
-      int s = 0;
-      uint32_t ph = 0;
-      uint32_t started = 0;
-      for (int u = cta; u < nunits; u += p.ctas_per_group) {
-        const int ch = u % g.nchunks;
-        const int kc = min(g.KC, g.range_len - ch * g.KC);
-        mbar_wait(bar_full + 8 * s, ph);
-        tc_fence_after();
-        const uint32_t a_s = ((stage0 + (uint32_t)s * g.stage_bytes) >> 4) + a_low;
-        const uint32_t b_s = ((stage0 + (uint32_t)s * g.stage_bytes + g.a_bytes) >> 4) + b_low;
+    // whole warp runs the (warp-uniform) loops; one elected lane issues the tcgen05 instructions
+    const bool stacked = 2 * kga <= 16;                // [hi; lo] of dY as one A operand
+    const int M = (2 * kga <= 8) ? 64 : 128;
+    const uint32_t idesc = umma_idesc_bf16(M, g.Nn, /*mn_major=*/1);
+    // MN-major, no swizzle: LBO = 128 B between 8-slot K groups, SBO = one staged plane between channel groups
+    const uint64_t a_tmpl = umma_desc(0, 128, (uint32_t)g.KC * 16);
+    const uint64_t b_tmpl = umma_desc(0, 128, (uint32_t)g.XS * 16);
+    const uint32_t a_hiw = (uint32_t)(a_tmpl >> 32), b_hiw = (uint32_t)(b_tmpl >> 32);
+    const uint32_t a_low = (uint32_t)a_tmpl, b_low = (uint32_t)b_tmpl;
+    const uint32_t a_losplit = (uint32_t)(kga * g.KC);        // hi -> lo half, 16 B units
+    const uint32_t b_losplit = (uint32_t)(g.KGn * g.XS);
+    int s = 0;
+    uint32_t ph = 0;
+    uint32_t started = 0;
+    for (int u = cta; u < nunits; u += p.ctas_per_group) {
+      const int ch = u % g.nchunks;
+      const int kc = min(g.KC, g.range_len - ch * g.KC);
+      mbar_wait(bar_full + 8 * s, ph);
+      tc_fence_after();
+      const uint32_t a_s = ((stage0 + (uint32_t)s * g.stage_bytes) >> 4) + a_low;
+      const uint32_t b_s = ((stage0 + (uint32_t)s * g.stage_bytes + g.a_bytes) >> 4) + b_low;
+      if (elect_one_sync()) {
+        uint32_t st = started;
         for (int k = 0; k < kc; k += 16) {
           const uint32_t al = a_s + k;                          // 16 slots = 16 units of 16 B
           const uint64_t A_hi = ((uint64_t)a_hiw << 32) | al, A_lo = ((uint64_t)a_hiw << 32) | (al + a_losplit);
@@ -172,17 +183,19 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_tc_kernel(const WgParams 
               const uint32_t bl = b_s + k + dx;
               const uint64_t B_hi = ((uint64_t)b_hiw << 32) | bl, B_lo = ((uint64_t)b_hiw << 32) | (bl + b_losplit);
               const uint32_t d = tmem_base + (uint32_t)(dx * g.Nn);
-              tc_mma_bf16(d, A_hi, B_hi, idesc, started);
-              tc_mma_bf16(d, A_lo, B_hi, idesc, 1u);
+              tc_mma_bf16(d, A_hi, B_hi, idesc, st);
+              if (!stacked) tc_mma_bf16(d, A_lo, B_hi, idesc, 1u);
               tc_mma_bf16(d, A_hi, B_lo, idesc, 1u);
             }
           }
-          started = 1;
+          st = 1;
         }
         tc_commit(bar_empty + 8 * s);
-        if (++s == g.stages) { s = 0; ph ^= 1; }
+        if (u + p.ctas_per_group >= nunits) tc_commit(bar_done);
       }
-      tc_commit(bar_done);
+      __syncwarp();
+      started = 1;
+      if (++s == g.stages) { s = 0; ph ^= 1; }
     }
   } else {
     // ---- final epilogue: D[dx][co][ci] -> atomicAdd dW[co][ci][dy][dx]
@@ -190,7 +203,14 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_tc_kernel(const WgParams 
     if (cta < nunits) {
       mbar_wait(bar_done, 0);
       tc_fence_after();
-      const int co = mb * 128 + wq * 32 + lane;
+      // accumulator row of this lane: M = 128 -> row = TMEM lane; M = 64 -> rows 16*w + (lane < 16)
+      // (cute::UMMA tmem_frg "half subpartition" atom).  Stacked rows r and r + 8*kga both belong to
+      // output channel r.
+      const bool stacked = 2 * kga <= 16;
+      const bool m64 = 2 * kga <= 8;
+      int row = m64 ? (lane < 16 ? wq * 16 + lane : -1) : wq * 32 + lane;
+      if (stacked && row >= 8 * kga) row = (row < 16 * kga) ? row - 8 * kga : -1;
+      const int co = row < 0 ? p.Cout : mb * 128 + row;
       const int KK = p.K * p.K;
       for (int dx = 0; dx < ndx; ++dx) {
         const int tap = (p.K == 3) ? dyi * 3 + dx : 0;

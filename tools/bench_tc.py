@@ -43,12 +43,19 @@ def main():
         wp = ops._pack(w, False)
         y2 = torch.empty_like(y)
         fp = lambda: L.call("conv2d_fwd", x, wp, None, y2, N, Cin, HW, HW, Cout, K, 0, 0)
+        gy = torch.randn(N, Cout, HW, HW, device="cuda")
+        gys = torch.empty(L.lib().san_tc_staged_act_elems(N, HW, HW, Cout), dtype=torch.bfloat16, device="cuda")
+        L.call("tc_stage_act", gys, N, HW, HW, (Cout + 15) // 16 * 16, gy, None, None, None, 1.0, Cout, 0,
+               None, None, None, None, 1.0, 0, 0, None, None, None, None, 1.0, 0, 0)
+        dw = torch.empty_like(w)
+        wg = lambda: L.call("tc_wgrad", gys, xs, dw, None, None, N, HW, HW, Cin, Cout, K)
+        t_wg = timeit(wg)
         t_st, t_cv, t_fp = timeit(st), timeit(cv), timeit(fp)
         fl = 2.0 * N * Cout * HW * HW * Cin * K * K
         err = ((y - y2).norm() / y2.norm()).item()
         print(f"{Cin:4d} {Cout:4d} {HW:4d} {K} | {t_st:7.3f} | {t_cv:7.3f} ({fl / t_cv / 1e9:6.1f}) | {t_fp:7.3f} ({fl / t_fp / 1e9:6.1f}) | "
-              f"{t_fp / t_cv:5.2f}x  err {err:.1e}")
-        del x, xs, y, y2
+              f"{t_fp / t_cv:5.2f}x  err {err:.1e} | wgrad {t_wg:7.3f} ms ({fl / t_wg / 1e9:6.1f} TF/s)")
+        del x, xs, y, y2, gy, gys
 
 
 if __name__ == "__main__":
