@@ -351,7 +351,7 @@ int run_fft(FftArgs& a, int inverse, int load, int store, cudaStream_t st) {
   if ((rc = get_twiddles(a.H, &a.twH)) != SAN_OK) return rc;
   a.scale *= (float)(1.0 / sqrt((double)a.H * (double)a.W));
   a.rpb = 2560 / a.W; if (a.rpb < 1) a.rpb = 1; if (a.rpb > 16) a.rpb = 16;
-  a.ct = a.H <= 336 ? 16 : (a.H <= 672 ? 8 : 4);
+  a.ct = a.H <= 672 ? 8 : 4;   // 8 columns = 64 B row segments; 41 KB per CTA at H = 320 -> 5 CTAs per SM overlap load / FFT / store
   SAN_CHECK_ARG((size_t)3 * a.ct * (a.H + 1) * sizeof(float2) <= 200 * 1024 && (size_t)2 * a.rpb * a.W * sizeof(float2) <= 200 * 1024,
                 "fft: line too long for shared memory H=%d W=%d", a.H, a.W);
 #define ROWS(L) (inverse ? launch_rows<true, L>(a, st) : launch_rows<false, L>(a, st))

@@ -140,12 +140,36 @@ __global__ void __launch_bounds__(256) act_bwd_reduce_kernel(const float* __rest
   const float ca = a[blockIdx.x], cb = b ? b[blockIdx.x] : 0.f;
   const float csa = sa ? sa[blockIdx.x] : 1.f;
   float t1 = 0.f, t2 = 0.f;
-  for (int i = threadIdx.x; i < P; i += blockDim.x) {
-    const float yc = y[base + i] - cm;
-    float gg = g[base + i];
-    if (fmaf(ca, yc, cb) <= 0.f) gg *= slope;
-    t1 += gg;
-    t2 += gg * (csa * yc);
+  if ((P & 3) == 0) {
+    // 16 B loads, two independent float4 pairs in flight per thread
+    const float4* y4 = (const float4*)(y + base);
+    const float4* g4 = (const float4*)(g + base);
+    const int n4 = P >> 2;
+    for (int i = threadIdx.x; i < n4; i += 2 * blockDim.x) {
+      const int i2 = i + blockDim.x;
+      const bool has2 = i2 < n4;
+      const float4 ya = __ldg(y4 + i), ga = __ldg(g4 + i);
+      const float4 yb = has2 ? __ldg(y4 + i2) : make_float4(cm, cm, cm, cm);
+      const float4 gb = has2 ? __ldg(g4 + i2) : make_float4(0.f, 0.f, 0.f, 0.f);
+      const float yv[8] = {ya.x, ya.y, ya.z, ya.w, yb.x, yb.y, yb.z, yb.w};
+      const float gv[8] = {ga.x, ga.y, ga.z, ga.w, gb.x, gb.y, gb.z, gb.w};
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const float yc = yv[k] - cm;
+        float gg = gv[k];
+        if (fmaf(ca, yc, cb) <= 0.f) gg *= slope;
+        t1 += gg;
+        t2 += gg * (csa * yc);
+      }
+    }
+  } else {
+    for (int i = threadIdx.x; i < P; i += blockDim.x) {
+      const float yc = y[base + i] - cm;
+      float gg = g[base + i];
+      if (fmaf(ca, yc, cb) <= 0.f) gg *= slope;
+      t1 += gg;
+      t2 += gg * (csa * yc);
+    }
   }
   const double r1 = block_sum_d((double)t1, red);
   const double r2 = block_sum_d((double)t2, red);
@@ -199,6 +223,31 @@ __global__ void __launch_bounds__(256) act_bwd_apply_kernel(const float* __restr
   const float cm = mu ? mu[blockIdx.x] : 0.f;
   const float ca = a[blockIdx.x], cb = b ? b[blockIdx.x] : 0.f;
   const float cp = p[blockIdx.x], cq = q ? q[blockIdx.x] : 0.f, cr = r ? r[blockIdx.x] : 0.f;
+  if ((P & 3) == 0) {
+    const float4* y4 = (const float4*)(y + base);
+    const float4* g4 = (const float4*)(g + base);
+    float4* d4 = (float4*)(dy + base);
+    const int n4 = P >> 2, stride = gridDim.y * blockDim.x;
+    for (int i = blockIdx.y * blockDim.x + threadIdx.x; i < n4; i += 2 * stride) {
+      const int i2 = i + stride;
+      const bool has2 = i2 < n4;
+      const float4 ya = __ldg(y4 + i), ga = __ldg(g4 + i);
+      float4 yb = ya, gb = ga;
+      if (has2) { yb = __ldg(y4 + i2); gb = __ldg(g4 + i2); }
+      float yv[8] = {ya.x, ya.y, ya.z, ya.w, yb.x, yb.y, yb.z, yb.w};
+      float gv[8] = {ga.x, ga.y, ga.z, ga.w, gb.x, gb.y, gb.z, gb.w};
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const float yc = yv[k] - cm;
+        float gg = gv[k];
+        if (fmaf(ca, yc, cb) <= 0.f) gg *= slope;
+        yv[k] = fmaf(cp, gg, fmaf(cq, yc, cr));
+      }
+      d4[i] = make_float4(yv[0], yv[1], yv[2], yv[3]);
+      if (has2) d4[i2] = make_float4(yv[4], yv[5], yv[6], yv[7]);
+    }
+    return;
+  }
   for (int i = blockIdx.y * blockDim.x + threadIdx.x; i < P; i += gridDim.y * blockDim.x) {
     const float yc = y[base + i] - cm;
     float gg = g[base + i];

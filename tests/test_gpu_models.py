@@ -113,14 +113,15 @@ def test_align_fwd_bwd():
     loss = ((warped - g["tgt"].cuda()) ** 2).mean() + 1000.0 * ls
     loss.backward()
     assert rel_l2(img.grad, g["g_img"]) < GTOL
-    # bar = max(GTOL_KINK, 4 x the CPU fp32 oracle's own error against the fp64 oracle)
+    # bar = max(GTOL_TINY, 4 x the CPU fp32 oracle's own error against the fp64 oracle): the golden case is
+    # 2 x 32 x 48, its deep levels hold ~1.5e3 activations per layer, where one kink flip is 2.5e-2
     ours = {"g_img": img.grad, **{k: p.grad for k, p in st.named_parameters()}}
-    assert_close_to_fp64(ours, _align_oracle(g, torch.float32), _align_oracle(g, torch.float64), GTOL_KINK)
+    assert_close_to_fp64(ours, _align_oracle(g, torch.float32), _align_oracle(g, torch.float64), GTOL_TINY)
     # and against the reference's own dump, at the (looser) bar that the chaos allows
     grads = sub(g, "g.")
     fl = grad_floor(grads)
     for name, gg in grads.items():
-        assert rel_l2(ours[name], gg, fl) < GTOL_KINK, name
+        assert rel_l2(ours[name], gg, fl) < GTOL_TINY, name
     sd = st.state_dict()
     for name, v in sub(g, "sd_after.").items():           # BatchNorm running-stat side effect
         assert rel_l2(sd[name].double(), v.double()) < 1e-5, name
