@@ -24,6 +24,8 @@ struct FftPlan {
   int n;
   int ns;
   int radix[12];
+  int shift[12];    // log2(Ns) of the stage when Ns (product of the previous radices) is a power of two, else -1
+  int twstep[12];   // n / (Ns * R): twiddle index step of the stage
 };
 
 bool make_plan(int n, FftPlan* p) {
@@ -40,6 +42,14 @@ bool make_plan(int n, FftPlan* p) {
     }
   }
   if (n == 1) { p->ns = 0; }
+  int Ns = 1;
+  for (int s = 0; s < p->ns; ++s) {
+    int sh = 0;
+    while ((1 << sh) < Ns) ++sh;
+    p->shift[s] = ((1 << sh) == Ns) ? sh : -1;
+    p->twstep[s] = n / (Ns * p->radix[s]);
+    Ns *= p->radix[s];
+  }
   return true;
 }
 
@@ -83,12 +93,12 @@ __device__ __forceinline__ float2 mul_mi(float2 a) {
 // Ns = product of the radices of the previous stages; j in [0, n/R).
 template <bool INV>
 __device__ __forceinline__ void butterfly(const float2* __restrict__ in, float2* __restrict__ out,
-                                          int n, int R, int Ns, int j,
+                                          int n, int R, int T, int Ns, int shift, int twstep, int j,
                                           const float2* __restrict__ tw) {
-  const int T = n / R;
-  const int k = j % Ns;
-  const int base = k * (n / (Ns * R));
-  const int j0 = (j / Ns) * Ns * R + k;
+  const int k = shift >= 0 ? (j & (Ns - 1)) : (j % Ns);
+  const int jq = shift >= 0 ? (j >> shift) : (j / Ns);
+  const int base = k * twstep;
+  const int j0 = jq * Ns * R + k;
   if (R == 4) {
     float2 v0 = in[j], v1 = in[j + T], v2 = in[j + 2 * T], v3 = in[j + 3 * T];
     if (k) {
@@ -157,23 +167,29 @@ __device__ __forceinline__ void butterfly(const float2* __restrict__ in, float2*
   }
 }
 
-// Runs `nfft` independent FFTs (line f at a + f*stride) cooperatively; returns the
-// buffer holding the result.  Caller must __syncthreads() after filling `a`.
+// Runs `nfft` independent FFTs (line f at a + f*stride); returns the buffer holding the result.
+// Each WARP owns whole lines (f = warp, warp + nwarps, ...), so the Stockham stages of a line only need
+// __syncwarp() between them, and the line / butterfly indices need no divisions.  Caller must
+// __syncthreads() after filling `a` and before reading the result.
 template <bool INV>
 __device__ float2* block_fft(float2* a, float2* b, int nfft, int stride, const FftPlan& pl,
                              const float2* __restrict__ tw) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
   int Ns = 1;
   for (int s = 0; s < pl.ns; ++s) {
     const int R = pl.radix[s];
     const int T = pl.n / R;
-    for (int i = threadIdx.x; i < nfft * T; i += blockDim.x) {
-      const int f = i / T, j = i - f * T;
-      butterfly<INV>(a + f * stride, b + f * stride, pl.n, R, Ns, j, tw);
+    const int shift = pl.shift[s], twstep = pl.twstep[s];
+    for (int f = warp; f < nfft; f += nw) {
+      const float2* in = a + f * stride;
+      float2* out = b + f * stride;
+      for (int j = lane; j < T; j += 32) butterfly<INV>(in, out, pl.n, R, T, Ns, shift, twstep, j, tw);
     }
-    __syncthreads();
+    __syncwarp();
     float2* t = a; a = b; b = t;
     Ns *= R;
   }
+  __syncthreads();
   return a;
 }
 

@@ -28,6 +28,8 @@ def main():
               (36, 72, 80, 3), (72, 72, 80, 3), (144, 72, 80, 3), (72, 144, 40, 3), (144, 144, 40, 3), (288, 144, 40, 3),
               (144, 288, 20, 3), (288, 288, 20, 3), (288, 576, 20, 1), (144, 288, 40, 1), (72, 144, 80, 1), (36, 72, 160, 1),
               (18, 2, 320, 1), (2, 32, 320, 3), (32, 32, 320, 3), (64, 64, 160, 3), (128, 64, 160, 3)]
+    if len(sys.argv) > 2:      # e.g. "18,18,320,3;36,72,160,1"
+        shapes = [tuple(int(v) for v in t.split(",")) for t in sys.argv[2].split(";")]
     print(f"N={N}: Cin Cout HW K | stage ms | tc conv ms (TF/s algorithmic) | fp32 conv ms (TF/s) | speedup(conv only)")
     for Cin, Cout, HW, K in shapes:
         x = torch.randn(N, Cin, HW, HW, device="cuda")
