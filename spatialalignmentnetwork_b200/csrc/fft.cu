@@ -76,9 +76,10 @@ int get_twiddles(int n, const float2** out) {
   return SAN_OK;
 }
 
+// twiddles are read from the block's shared-memory copy of the table
 template <bool INV>
 __device__ __forceinline__ float2 twid(const float2* __restrict__ tw, int idx) {
-  float2 t = __ldg(tw + idx);
+  float2 t = tw[idx];
   if (INV) t.y = -t.y;
   return t;
 }
@@ -91,10 +92,11 @@ __device__ __forceinline__ float2 mul_mi(float2 a) {
 
 // One radix-R butterfly of a Stockham stage.  `in`/`out` are one line of length n;
 // Ns = product of the radices of the previous stages; j in [0, n/R).
-template <bool INV>
+template <bool INV, int RT>
 __device__ __forceinline__ void butterfly(const float2* __restrict__ in, float2* __restrict__ out,
-                                          int n, int R, int T, int Ns, int shift, int twstep, int j,
+                                          int n, int Rrt, int T, int Ns, int shift, int twstep, int j,
                                           const float2* __restrict__ tw) {
+  const int R = RT ? RT : Rrt;   // RT = 0: generic odd radix known only at run time
   const int k = shift >= 0 ? (j & (Ns - 1)) : (j % Ns);
   const int jq = shift >= 0 ? (j >> shift) : (j / Ns);
   const int base = k * twstep;
@@ -167,30 +169,45 @@ __device__ __forceinline__ void butterfly(const float2* __restrict__ in, float2*
   }
 }
 
+template <bool INV, int RT>
+__device__ __forceinline__ void fft_stage(const float2* a, float2* b, int nfft, int stride, int n, int R, int Ns, int shift,
+                                          int twstep, const float2* __restrict__ tw) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  const int T = n / R;
+  for (int f = warp; f < nfft; f += nw) {
+    const float2* in = a + f * stride;
+    float2* out = b + f * stride;
+    for (int j = lane; j < T; j += 32) butterfly<INV, RT>(in, out, n, R, T, Ns, shift, twstep, j, tw);
+  }
+}
+
 // Runs `nfft` independent FFTs (line f at a + f*stride); returns the buffer holding the result.
 // Each WARP owns whole lines (f = warp, warp + nwarps, ...), so the Stockham stages of a line only need
-// __syncwarp() between them, and the line / butterfly indices need no divisions.  Caller must
-// __syncthreads() after filling `a` and before reading the result.
+// __syncwarp() between them, and the line / butterfly indices need no divisions; the radix of a stage
+// is a template parameter.  `tw` = shared-memory twiddle table.  Caller must __syncthreads() after
+// filling `a`; the result is visible to the whole block on return.
 template <bool INV>
 __device__ float2* block_fft(float2* a, float2* b, int nfft, int stride, const FftPlan& pl,
                              const float2* __restrict__ tw) {
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
   int Ns = 1;
   for (int s = 0; s < pl.ns; ++s) {
     const int R = pl.radix[s];
-    const int T = pl.n / R;
     const int shift = pl.shift[s], twstep = pl.twstep[s];
-    for (int f = warp; f < nfft; f += nw) {
-      const float2* in = a + f * stride;
-      float2* out = b + f * stride;
-      for (int j = lane; j < T; j += 32) butterfly<INV>(in, out, pl.n, R, T, Ns, shift, twstep, j, tw);
-    }
+    if (R == 4) fft_stage<INV, 4>(a, b, nfft, stride, pl.n, R, Ns, shift, twstep, tw);
+    else if (R == 2) fft_stage<INV, 2>(a, b, nfft, stride, pl.n, R, Ns, shift, twstep, tw);
+    else if (R == 5) fft_stage<INV, 5>(a, b, nfft, stride, pl.n, R, Ns, shift, twstep, tw);
+    else fft_stage<INV, 0>(a, b, nfft, stride, pl.n, R, Ns, shift, twstep, tw);
     __syncwarp();
     float2* t = a; a = b; b = t;
     Ns *= R;
   }
   __syncthreads();
   return a;
+}
+
+// copy the twiddle table of length n into shared memory (all threads)
+__device__ __forceinline__ void load_twiddles(float2* dst, const float2* __restrict__ src, int n) {
+  for (int i = threadIdx.x; i < n; i += blockDim.x) dst[i] = __ldg(src + i);
 }
 
 enum { LD_C64 = 0, LD_C64_COLMASK = 1, LD_PLANAR = 2, LD_PLANAR_S = 3 };
@@ -227,42 +244,50 @@ __global__ void __launch_bounds__(256) fft_rows_kernel(const FftArgs a) {
   const int nr = (int)min((long long)a.rpb, nrows - row0);
   float2* bufA = sm;
   float2* bufB = sm + a.rpb * W;
+  float2* tws = sm + 2 * a.rpb * W;
+  load_twiddles(tws, a.twW, W);
   const long long HW = (long long)a.H * W;
-  for (int i = threadIdx.x; i < nr * W; i += blockDim.x) {
-    const int r = i / W, w = i - r * W;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  // one warp per row: no per-element divisions
+  for (int r = warp; r < nr; r += nw) {
     const long long row = row0 + r;           // = b*H + h
-    const long long off = row * W + w;        // offset in [B,H,W]
-    float2 v;
-    if (LOAD == LD_C64) {
-      v = a.in_c[off];
-    } else if (LOAD == LD_C64_COLMASK) {
-      v = a.in_c[off];
-      const float m = a.colmask[w];
-      v.x *= m; v.y *= m;
-    } else {
-      const long long b = row / a.H;
-      const long long hw = off - b * HW;
-      const long long g = (LOAD == LD_PLANAR_S) ? b / a.C : b;
-      v.x = a.in_p[(g * 2) * HW + hw];
-      v.y = a.in_p[(g * 2 + 1) * HW + hw];
-      if (LOAD == LD_PLANAR_S) v = cmul(v, a.sens[off]);
+    const long long rowoff = row * W;         // offset in [B,H,W]
+    const long long b = row / a.H;
+    const long long g = (LOAD == LD_PLANAR_S) ? b / a.C : b;
+    const long long hw0 = rowoff - b * HW;
+    float2* dst = bufA + r * W;
+    for (int w = lane; w < W; w += 32) {
+      float2 v;
+      if (LOAD == LD_C64) {
+        v = a.in_c[rowoff + w];
+      } else if (LOAD == LD_C64_COLMASK) {
+        v = a.in_c[rowoff + w];
+        const float m = a.colmask[w];
+        v.x *= m; v.y *= m;
+      } else {
+        v.x = a.in_p[(g * 2) * HW + hw0 + w];
+        v.y = a.in_p[(g * 2 + 1) * HW + hw0 + w];
+        if (LOAD == LD_PLANAR_S) v = cmul(v, a.sens[rowoff + w]);
+      }
+      dst[w] = v;
     }
-    bufA[i] = v;
   }
   __syncthreads();
-  float2* res = block_fft<INV>(bufA, bufB, nr, W, a.planW, a.twW);
+  float2* res = block_fft<INV>(bufA, bufB, nr, W, a.planW, tws);
   for (int i = threadIdx.x; i < nr * W; i += blockDim.x) a.tmp[row0 * W + i] = res[i];
 }
 
 // grid: (ceil(W/ct), G) where G = N for the coil-reducing stores and B otherwise.
-template <bool INV, int STORE>
+template <bool INV, int STORE, int CT>
 __global__ void __launch_bounds__(256) fft_cols_kernel(const FftArgs a) {
   extern __shared__ float2 sm[];
-  const int H = a.H, W = a.W, CT = a.ct;
+  const int H = a.H, W = a.W;
   const int ld = H + 1;
   float2* bufA = sm;
   float2* bufB = sm + CT * ld;
-  float2* acc = sm + 2 * CT * ld;  // only for coil-reducing stores with C > 1
+  float2* tws = sm + 2 * CT * ld;
+  float2* acc = tws + H;           // only for coil-reducing stores with C > 1
+  load_twiddles(tws, a.twH, H);
   const int w0 = blockIdx.x * CT;
   const int ncol = min(CT, W - w0);
   const long long HW = (long long)H * W;
@@ -281,7 +306,7 @@ __global__ void __launch_bounds__(256) fft_cols_kernel(const FftArgs a) {
       bufA[col * ld + h] = v;
     }
     __syncthreads();
-    const float2* res = block_fft<INV>(bufA, bufB, ncol, ld, a.planH, a.twH);
+    const float2* res = block_fft<INV>(bufA, bufB, ncol, ld, a.planH, tws);
     for (int i = threadIdx.x; i < nel; i += blockDim.x) {
       const int h = i / CT, col = i - h * CT;
       if (col >= ncol) continue;
@@ -334,7 +359,7 @@ __global__ void __launch_bounds__(256) fft_cols_kernel(const FftArgs a) {
 
 template <bool INV, int LOAD>
 int launch_rows(const FftArgs& a, cudaStream_t st) {
-  const size_t smem = (size_t)2 * a.rpb * a.W * sizeof(float2);
+  const size_t smem = ((size_t)2 * a.rpb * a.W + a.W) * sizeof(float2);
   auto kern = fft_rows_kernel<INV, LOAD>;
   if (smem > 48 * 1024)
     SAN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -348,12 +373,19 @@ template <bool INV, int STORE>
 int launch_cols(const FftArgs& a, cudaStream_t st) {
   const bool reducing = (STORE == ST_REDUCE || STORE == ST_RSS);
   const int nbuf = (reducing && a.C > 1) ? 3 : 2;
-  const size_t smem = (size_t)nbuf * a.ct * (a.H + 1) * sizeof(float2);
-  auto kern = fft_cols_kernel<INV, STORE>;
-  if (smem > 48 * 1024)
-    SAN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const size_t smem = ((size_t)nbuf * a.ct * (a.H + 1) + a.H) * sizeof(float2);
   dim3 grid(san_cdiv(a.W, a.ct), reducing ? a.B / a.C : a.B);
-  kern<<<grid, 256, smem, st>>>(a);
+  if (a.ct == 8) {
+    auto kern = fft_cols_kernel<INV, STORE, 8>;
+    if (smem > 48 * 1024)
+      SAN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<grid, 256, smem, st>>>(a);
+  } else {
+    auto kern = fft_cols_kernel<INV, STORE, 4>;
+    if (smem > 48 * 1024)
+      SAN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<grid, 256, smem, st>>>(a);
+  }
   SAN_LAUNCH_CHECK();
   return SAN_OK;
 }
