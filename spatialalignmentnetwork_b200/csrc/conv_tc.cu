@@ -59,7 +59,9 @@ static int tc_pick_rows(int H, int W, int K, int Npad, int b_bytes) {
     if (2 * stage + TC_SMEM_HEADER > TC_SMEM_MAX) break;
     // useful MMA rows x re-read factor of the input rows (halo) x tail waste of the last strip
     const int strips = (H + R - 1) / R;
-    const double eff = ((double)R * W / (128.0 * T)) * ((double)R / (R + 2 * (K / 2))) * ((double)H / (strips * R));
+    // ... x a penalty when the accumulators cannot be double-buffered (epilogue then serialises with the MMAs)
+    const double eff = ((double)R * W / (128.0 * T)) * ((double)R / (R + 2 * (K / 2))) * ((double)H / (strips * R)) *
+                       (2 * T * Npad <= 512 ? 1.0 : 0.75);
     if (eff > best + 1e-9) { best = eff; bestR = R; }
   }
   return bestR;
