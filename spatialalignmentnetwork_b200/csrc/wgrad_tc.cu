@@ -31,6 +31,7 @@ namespace {
 constexpr int WG_THREADS = 192;
 constexpr int WG_HEADER = 256;
 constexpr int WG_SMEM_MAX = 225 * 1024;
+constexpr int WG_KC_MAX = 512;   // pixel slots per stage (measured: fewer, larger stages win; per-stage TMA issue + barrier cost)
 
 struct WgGeom {
   int KGo, KGi;            // staged channel groups of dY / X
@@ -58,21 +59,26 @@ bool wg_geometry(int H, int W, int Cin, int Cout, int K, WgGeom* g) {
   g->range0 = g->Wp;                                  // first slot of image row 0 (padded row 1)
   g->range_len = (H * g->Wp + 15) / 16 * 16;          // tail runs into the zero border row
   const int kga = g->KGo < 16 ? g->KGo : 16;          // groups actually loaded per M block (max)
-  int best = 0;
-  for (int kc = 512; kc >= 32; kc -= 16) {
+  // The UMMA reads M/8 channel groups from the A start (and again from the lo half when hi/lo are not
+  // stacked) whether or not they were loaded: the over-read must stay inside the allocation.
+  const bool stacked = 2 * kga <= 16;
+  const int mg = (2 * kga <= 8) ? 8 : 16;
+  const int reach_groups = (stacked ? 0 : kga) + mg;  // groups spanned from the A start of a stage
+  int best = 0, best_slack = 0;
+  for (int kc = WG_KC_MAX; kc >= 32; kc -= 16) {
     const int a = kga * 2 * kc * 16, b = g->KGn * 2 * (kc + 16) * 16;
-    const int slack = 16 * kc * 16;                   // M = 128 always reads 16 channel groups
-    if (2 * (a + b) + slack + WG_HEADER <= WG_SMEM_MAX) { best = kc; break; }
+    int slack = reach_groups * kc * 16 - (a + b);
+    if (slack < 0) slack = 0;
+    if (2 * (a + b) + slack + WG_HEADER <= WG_SMEM_MAX) { best = kc; best_slack = slack; break; }
   }
   if (!best) return false;
   g->KC = best; g->XS = best + 16;
   g->a_bytes = kga * 2 * g->KC * 16;
   g->b_bytes = g->KGn * 2 * g->XS * 16;
   g->stage_bytes = g->a_bytes + g->b_bytes;
-  const int slack = 16 * g->KC * 16;
-  g->stages = (WG_SMEM_MAX - WG_HEADER - slack) / g->stage_bytes;
+  g->stages = (WG_SMEM_MAX - WG_HEADER - best_slack) / g->stage_bytes;
   if (g->stages > 4) g->stages = 4;
-  g->smem_bytes = WG_HEADER + g->stages * g->stage_bytes + slack;
+  g->smem_bytes = WG_HEADER + g->stages * g->stage_bytes + best_slack;
   if (g->smem_bytes < 120 * 1024) g->smem_bytes = 120 * 1024;
   g->nchunks = (g->range_len + g->KC - 1) / g->KC;
   return true;
