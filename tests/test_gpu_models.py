@@ -190,3 +190,38 @@ def test_update_and_test_api():
     net.set_input(full, aux)
     r = net.test()
     assert r == -net.metric_PSNR and 0.0 <= net.metric_SSIM <= 1.0
+
+
+@pytest.mark.parametrize("shape", [(2, 4, 32, 46), (1, 15, 64, 46)])
+def test_varnet_multicoil_nonsquare_vs_oracle(shape):
+    """BASELINE config 4 in miniature: multi-coil k-space, non-square image whose width has the prime
+    factor 23 (368 = 16 * 23 in the full config; 46 = 2 * 23 here -> generic-radix FFT butterfly + the
+    NormUnet pad-to-16 path), sensitivity-map estimation, use_ref.  Forward against the CPU oracle (fp32),
+    gradients within the kink noise bar."""
+    from oracle import varnet as ov
+    from spatialalignmentnetwork_b200.varnet import VarNet
+    N, C, H, W = shape
+    torch.manual_seed(61)
+    net = VarNet(num_cascades=2, sens_chans=4, sens_pools=2, chans=6, pools=2, use_ref=True)
+    sd = {k: v.detach().clone() for k, v in net.state_dict().items()}
+    img = torch.complex(torch.rand(N, C, H, W), torch.rand(N, C, H, W))
+    pruned = torch.ones(W, dtype=torch.bool)
+    pruned[::3] = False
+    pruned[:4] = False
+    pruned[-4:] = False
+    ks = torch.fft.fft2(img, norm="ortho") * (~pruned).float()
+    ref = torch.rand(N, C, H, W)
+    nlf = 8
+    sdo = {k: v.clone().requires_grad_(v.is_floating_point()) for k, v in sd.items()}
+    rec_o = ov.varnet(sdo, "", ks, ~pruned, ref, nlf, 2, 2, 2, use_ref=True)
+    tgt = torch.rand_like(rec_o)
+    ((rec_o - tgt) ** 2).mean().backward()
+    net.cuda()
+    rec = net(ks.cuda(), (~pruned).cuda(), ref.cuda(), nlf)
+    assert rec.shape == rec_o.shape
+    assert rel_l2(rec, rec_o) < TOL
+    ((rec - tgt.cuda()) ** 2).mean().backward()
+    grads = {k: v.grad for k, v in sdo.items() if v.grad is not None}
+    fl = grad_floor(grads)
+    for name, p in net.named_parameters():
+        assert rel_l2(p.grad, grads[name], fl) < GTOL_TINY, name
