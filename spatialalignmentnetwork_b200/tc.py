@@ -21,6 +21,20 @@ from ._lib import call, lib
 MODE_DIRECT, MODE_POOL, MODE_D2S, MODE_UP = 0, 1, 2, 3
 _IN_EPS = 1e-5
 
+# Staged operands are as large as the activations they come from.  They are re-created in the backward
+# pass (for the weight gradient) unless HBM is plentiful: while live tensors take less than
+# this fraction of the device memory, the forward keeps them (a B200 has 180 GB; the benchmark step
+# needs 65 GB without them).
+KEEP_STAGED_BELOW = 0.55
+_total_mem = {}
+
+
+def _keep_staged(device):
+    idx = device.index if device.index is not None else torch.cuda.current_device()
+    if idx not in _total_mem:
+        _total_mem[idx] = torch.cuda.get_device_properties(idx).total_memory
+    return torch.cuda.memory_allocated(idx) < KEEP_STAGED_BELOW * _total_mem[idx]
+
 
 class _StageTerm(ctypes.Structure):
     """``san_stage_term`` of include/san_b200.h."""
@@ -156,23 +170,25 @@ class _FusedConv(Function):
         ws = _stage_weights(w, False, H, W)
         out = torch.empty(N, Cout, H, W, dtype=torch.float32, device=w.device)
         call("tc_conv", xs, ws, bias, out, N, H, W, Cin, Cout, K, 0)
-        # The staged operand is NOT kept for the backward (it is as large as the fp32 activation and the
-        # padded channels make it larger): the weight gradient re-stages it from the raw tensors, which
-        # autograd holds anyway for the normalisation backward.
+        # The staged operand is kept for the backward only while HBM is plentiful (_keep_staged); otherwise
+        # the weight gradient re-stages it from the raw tensors, which autograd holds anyway for the
+        # normalisation backward.
         coefs = [m[5] for m in metas if m[5] is not None]
-        ctx.save_for_backward(w, *tensors, *coefs)
+        keep = _keep_staged(w.device) and (ctx.needs_input_grad[0] or ctx.needs_input_grad[1])
+        ctx.save_for_backward(w, *tensors, *coefs, *([xs] if keep else []))
         ctx.meta = (K, [(m[0], m[1], m[2], m[3], m[4], m[5] is not None, m[6]) for m in metas], (N, H, W),
-                    bias is not None, len(tensors))
+                    bias is not None, len(tensors), keep)
         return out
 
     @staticmethod
     @once_differentiable
     def backward(ctx, gy):
-        K, metas, (N, H, W), has_bias, ntens = ctx.meta
+        K, metas, (N, H, W), has_bias, ntens, kept = ctx.meta
         saved = ctx.saved_tensors
         w = saved[0]
         tensors = saved[1:1 + ntens]
-        coef_list = list(saved[1 + ntens:])
+        coef_list = list(saved[1 + ntens:len(saved) - (1 if kept else 0)])
+        xs_kept = saved[-1] if kept else None
         Cout, Cin = w.shape[0], w.shape[1]
         gy = gy if gy.is_contiguous() else gy.contiguous()
         dev = w.device
@@ -199,9 +215,12 @@ class _FusedConv(Function):
         if ctx.needs_input_grad[0] or (has_bias and ctx.needs_input_grad[1]):
             dw = torch.empty_like(w)
             db = torch.empty(Cout, dtype=torch.float32, device=dev) if has_bias else None
-            xs = _staged_act(N, H, W, Cin, dev)
-            _stage(xs, N, H, W, _pad16(Cin),
-                   [(t["y"], *_coef_views(t["norm"], t["st"])[:3], t["slope"], t["C"], t["mode"], t["acc"]) for t in terms])
+            if xs_kept is not None:
+                xs = xs_kept
+            else:
+                xs = _staged_act(N, H, W, Cin, dev)
+                _stage(xs, N, H, W, _pad16(Cin),
+                       [(t["y"], *_coef_views(t["norm"], t["st"])[:3], t["slope"], t["C"], t["mode"], t["acc"]) for t in terms])
             if lib().san_tc_wgrad_supported(H, W, Cin, Cout, K):
                 call("tc_wgrad", gys, xs, dw, db, gy if has_bias else None, N, H, W, Cin, Cout, K)
             else:   # tiny images (W < 16): fp32 CUDA-core kernel on the un-staged operand
