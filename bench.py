@@ -175,6 +175,18 @@ def algorithmic(name, a):
     return 0.0, 0.0
 
 
+# dram__bytes_read.sum + dram__bytes_write.sum of ONE launch from the committed `ncu --set full` capture
+# (profiles/r1d_tc_ncu_summary.txt: 3x3 conv 18->18, 320x320, bs 64).  The roofline's `achieved` averages over
+# all launches of the step, so the traffic figure is given for that named launch together with its algorithmic
+# bytes (staged BF16 hi/lo operand in + fp32 result out): no re-reads reach DRAM.
+NCU_TRAFFIC = {
+    "tc_conv": {"launch": "3x3 18->18 @320x320 bs64", "dram_bytes": 849.5e6 + 436.5e6,
+                "algorithmic_bytes": 64 * 2 * 4 * 322 * 322 * 16.0 + 64 * 18 * 320 * 320 * 4.0,
+                "source": "profiles/r1d_tc_ncu_summary.txt"},
+    "tc_wgrad": {"launch": "3x3 18->18 @320x320 bs64", "dram_bytes": 1693.6e6 + 4.1e6,
+                 "algorithmic_bytes": 2 * 64 * 2 * 4 * 322 * 322 * 16.0, "source": "profiles/r1d_tc_ncu_summary.txt"},
+}
+
 CLASSES = {
     "conv": ("conv2d_fwd", "conv2d_wgrad", "conv_pack_weights", "tc_conv", "tc_wgrad", "tc_stage_weights"),
     "operand_staging": ("tc_stage_act", "tc_stage_terms", "tc_unstage_act"),
@@ -218,7 +230,8 @@ def summarise_profile(records, step_ms, peaks):
         ach = c["flops"] / c["ms"] / 1e9  # TFLOP/s, algorithmic (1x) FLOPs: the BF16x3 split issues 3x this
         roof = dict(kernel=labels[key], bound="tensor", achieved=round(ach, 2),
                     peak=peaks["tf_sust"], unit="TFLOP/s", frac=round(ach / peaks["tf_sust"], 5),
-                    peak_source=f"bf16 dense sustained, {peaks['src']}", traffic=None,
+                    peak_source=f"bf16 dense sustained, {peaks['src']}",
+                    traffic=NCU_TRAFFIC.get(key),
                     launches=c["launches"], avg_launch_ms=round(c["ms"] / c["launches"], 4),
                     share_of_kernel_time=round(c["ms"] / total, 4),
                     issued_mma_frac=round(3 * ach / peaks["tf_sust"], 5) if key.startswith("tc_") else None,

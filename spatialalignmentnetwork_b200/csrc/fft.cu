@@ -364,7 +364,7 @@ int launch_rows(const FftArgs& a, cudaStream_t st) {
   if (smem > 48 * 1024)
     SAN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const long long nrows = (long long)a.B * a.H;
-  kern<<<san_cdiv(nrows, a.rpb), 256, smem, st>>>(a);
+  kern<<<san_cdiv(nrows, a.rpb), a.rpb >= 8 ? 256 : 32 * a.rpb, smem, st>>>(a);
   SAN_LAUNCH_CHECK();
   return SAN_OK;
 }
