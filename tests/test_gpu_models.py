@@ -225,3 +225,31 @@ def test_varnet_multicoil_nonsquare_vs_oracle(shape):
     fl = grad_floor(grads)
     for name, p in net.named_parameters():
         assert rel_l2(p.grad, grads[name], fl) < GTOL_TINY, name
+
+
+def test_train_and_eval_entry_points(tmp_path):
+    """train.py / eval.py (reference CLI, synthetic data): a few optimiser steps, a checkpoint in the reference's
+    directory format, and evaluation of that checkpoint."""
+    import json
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    logdir = str(tmp_path / "run")
+    cmd = [sys.executable, os.path.join(root, "train.py"), "--logdir", logdir, "--reg", "Rec", "--smooth_weight", "1000",
+           "--sim_weight", "1", "--mask", "equispaced", "--sparsity", "0.25", "--train", "synthetic:8", "--val",
+           "synthetic:4", "--crop", "64", "--batch_size", "4", "--epoch", "3", "--num_cascades", "2", "--log_every", "1",
+           "--force_gpu"]
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=root)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [json.loads(l) for l in out.stdout.splitlines() if l.startswith("{")]
+    its = [l for l in lines if "iter" in l]
+    assert len(its) == 6 and all(l["loss_all"] == l["loss_all"] for l in its)        # finite
+    assert its[-1]["loss_sim"] < its[0]["loss_sim"]                                   # it learns
+    ck = [d for d in os.listdir(logdir) if d.endswith("_final.pt")]
+    assert len(ck) == 1 and {"config", "net_T", "net_R", "net_mask"} <= set(os.listdir(os.path.join(logdir, ck[0])))
+    ev = subprocess.run([sys.executable, os.path.join(root, "eval.py"), "--resume", os.path.join(logdir, ck[0]), "--val",
+                         "synthetic:4", "--batch_size", "4"], capture_output=True, text=True, timeout=600, cwd=root)
+    assert ev.returncode == 0, ev.stderr[-2000:]
+    m = json.loads(ev.stdout.strip().splitlines()[-1])
+    assert m["metric_PSNR"] > 5 and 0 <= m["metric_SSIM"] <= 1
