@@ -160,6 +160,16 @@ int san_bn_finalize_bwd(const float* s1, const float* s2, const float* gamma, co
 /* dy = p*g' + q*(y - mu) + r (q, r may be NULL) */
 int san_act_bwd_apply(const float* g, const float* y, const float* mu, const float* a, const float* b, float slope,
                       const float* p, const float* q, const float* r, float* dy, int planes, int P, void* stream);
+/* the same two passes with g read IN PLACE from the data gradient dx[N, Ctot, Hd, Wd] of the consuming conv:
+ * channel offset c0 of a concatenated source, and the adjoint of the resampling applied while staging
+ * (mode 0 direct: Hd x Wd = Hy x Wy; 1 avg-pool: dx is Hy/2 x Wy/2; 2 pixel shuffle: y is [N, 4*Cy, Hy, Wy], dx is
+ * 2Hy x 2Wy; 3 nearest x2: dx is 2Hy x 2Wy).  No slice copies, no up2 / space_to_depth2 / pool2 temporaries. */
+int san_act_bwd_reduce_map(const float* g, int Ctot, int c0, int mode, const float* y, const float* mu, const float* a,
+                           const float* b, const float* sa, float slope, float* s1, float* s2, int N, int Cy, int Hy,
+                           int Wy, void* stream);
+int san_act_bwd_apply_map(const float* g, int Ctot, int c0, int mode, const float* y, const float* mu, const float* a,
+                          const float* b, float slope, const float* p, const float* q, const float* r, float* dy, int N,
+                          int Cy, int Hy, int Wy, void* stream);
 /* y = scale * (2x2 block sum of x): avg_pool2d (scale .25) and the adjoint of nearest up-sampling (scale 1) */
 int san_pool2(const float* x, float* y, long long planes, int H, int W, float scale, void* stream);
 /* y[2h+a,2w+b] = scale * x[h,w]: nearest x2 (scale 1) and the adjoint of avg_pool2d (scale .25) */

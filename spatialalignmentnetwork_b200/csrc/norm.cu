@@ -176,6 +176,148 @@ __global__ void __launch_bounds__(256) act_bwd_reduce_kernel(const float* __rest
   if (threadIdx.x == 0) { s1[blockIdx.x] = (float)r1; s2[blockIdx.x] = (float)r2; }
 }
 
+// ---- the same two passes reading the incoming gradient IN PLACE from the data gradient of the consuming
+// conv (dx [N, Ctot, Hd, Wd]): channel offset c0 of a concatenated source, batch stride, and the adjoint of
+// the resampling the consumer applied while staging (MODE 0 direct, 1 avg-pool 2x2, 2 pixel shuffle, 3 nearest
+// x2).  Replaces slice copies + up2 / space_to_depth2 / pool2 kernels + their intermediate tensors.
+struct GMap {
+  const float* g;     // dx of the consumer
+  long long g_bs;     // floats per image of dx (Ctot * Hd * Wd)
+  int c0, Cy;         // first dx channel of this term, channels of the term (planes per image)
+  int Hy, Wy;         // spatial size of one y (sub-)plane: MODE 2: y is [N, 4*Cy, Hy, Wy]
+};
+template <int MODE>
+__device__ __forceinline__ float gmap_load(const float* __restrict__ gp, int e, int Hy, int Wy) {
+  if (MODE == 0) return __ldg(gp + e);
+  if (MODE == 1) {              // y plane Hy x Wy, dx plane Hy/2 x Wy/2
+    const int h = e / Wy, w = e - h * Wy;
+    return 0.25f * __ldg(gp + (h >> 1) * (Wy >> 1) + (w >> 1));
+  }
+  if (MODE == 2) {              // y planes 4 x (Hy x Wy), dx plane 2Hy x 2Wy
+    const int hw = Hy * Wy;
+    const int sub = e / hw, r = e - sub * hw;
+    const int h = r / Wy, w = r - h * Wy;
+    return __ldg(gp + (2 * h + (sub >> 1)) * (2 * Wy) + 2 * w + (sub & 1));
+  }
+  const int h = e / Wy, w = e - h * Wy;   // MODE 3: y plane Hy x Wy, dx plane 2Hy x 2Wy
+  const float* q = gp + (2 * h) * (2 * Wy) + 2 * w;
+  const float2 r0 = __ldg((const float2*)q), r1 = __ldg((const float2*)(q + 2 * Wy));
+  return (r0.x + r0.y) + (r1.x + r1.y);
+}
+template <int MODE>
+__device__ __forceinline__ const float* gmap_plane(const GMap& m, int plane) {
+  const int n = plane / m.Cy, c = plane - n * m.Cy;
+  const long long hwd = MODE == 0 ? (long long)m.Hy * m.Wy : MODE == 1 ? (long long)(m.Hy >> 1) * (m.Wy >> 1) : 4LL * m.Hy * m.Wy;
+  return m.g + (long long)n * m.g_bs + (long long)(m.c0 + c) * hwd;
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(256) act_bwd_reduce_map_kernel(const GMap m, const float* __restrict__ y,
+                                                                 const float* __restrict__ mu, const float* __restrict__ a,
+                                                                 const float* __restrict__ b, const float* __restrict__ sa,
+                                                                 float slope, float* __restrict__ s1, float* __restrict__ s2,
+                                                                 int P) {
+  __shared__ double red[32];
+  const long long base = (long long)blockIdx.x * P;
+  const float* gp = gmap_plane<MODE>(m, blockIdx.x);
+  const float cm = mu ? mu[blockIdx.x] : 0.f;
+  const float ca = a[blockIdx.x], cb = b ? b[blockIdx.x] : 0.f;
+  const float csa = sa ? sa[blockIdx.x] : 1.f;
+  float t1 = 0.f, t2 = 0.f;
+  if (MODE == 0 && (P & 3) == 0) {
+    const float4* y4 = (const float4*)(y + base);
+    const float4* g4 = (const float4*)gp;
+    const int n4 = P >> 2;
+    for (int i = threadIdx.x; i < n4; i += 2 * blockDim.x) {
+      const int i2 = i + blockDim.x;
+      const bool has2 = i2 < n4;
+      const float4 ya = __ldg(y4 + i), ga = __ldg(g4 + i);
+      const float4 yb = has2 ? __ldg(y4 + i2) : make_float4(cm, cm, cm, cm);
+      const float4 gb = has2 ? __ldg(g4 + i2) : make_float4(0.f, 0.f, 0.f, 0.f);
+      const float yv[8] = {ya.x, ya.y, ya.z, ya.w, yb.x, yb.y, yb.z, yb.w};
+      const float gv[8] = {ga.x, ga.y, ga.z, ga.w, gb.x, gb.y, gb.z, gb.w};
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const float yc = yv[k] - cm;
+        float gg = gv[k];
+        if (fmaf(ca, yc, cb) <= 0.f) gg *= slope;
+        t1 += gg;
+        t2 += gg * (csa * yc);
+      }
+    }
+  } else {
+    for (int i = threadIdx.x; i < P; i += 2 * blockDim.x) {
+      const int i2 = i + blockDim.x;
+      const bool has2 = i2 < P;
+      const float ya = __ldg(y + base + i), ga = gmap_load<MODE>(gp, i, m.Hy, m.Wy);
+      const float yb = has2 ? __ldg(y + base + i2) : cm, gb = has2 ? gmap_load<MODE>(gp, i2, m.Hy, m.Wy) : 0.f;
+      float yc = ya - cm, gg = ga;
+      if (fmaf(ca, yc, cb) <= 0.f) gg *= slope;
+      t1 += gg; t2 += gg * (csa * yc);
+      yc = yb - cm; gg = gb;
+      if (fmaf(ca, yc, cb) <= 0.f) gg *= slope;
+      t1 += gg; t2 += gg * (csa * yc);
+    }
+  }
+  const double r1 = block_sum_d((double)t1, red);
+  const double r2 = block_sum_d((double)t2, red);
+  if (threadIdx.x == 0) { s1[blockIdx.x] = (float)r1; s2[blockIdx.x] = (float)r2; }
+}
+
+// dy = p * g' + q * (y - mu) + r with g read through the map; grid (planes, chunks)
+template <int MODE>
+__global__ void __launch_bounds__(256) act_bwd_apply_map_kernel(const GMap m, const float* __restrict__ y,
+                                                                const float* __restrict__ mu, const float* __restrict__ a,
+                                                                const float* __restrict__ b, float slope,
+                                                                const float* __restrict__ p, const float* __restrict__ q,
+                                                                const float* __restrict__ r, float* __restrict__ dy, int P) {
+  const long long base = (long long)blockIdx.x * P;
+  const float* gp = gmap_plane<MODE>(m, blockIdx.x);
+  const float cm = mu ? mu[blockIdx.x] : 0.f;
+  const float ca = a[blockIdx.x], cb = b ? b[blockIdx.x] : 0.f;
+  const float cp = p[blockIdx.x], cq = q ? q[blockIdx.x] : 0.f, cr = r ? r[blockIdx.x] : 0.f;
+  const int stride = gridDim.y * blockDim.x;
+  if (MODE == 0 && (P & 3) == 0) {
+    const float4* y4 = (const float4*)(y + base);
+    const float4* g4 = (const float4*)gp;
+    float4* d4 = (float4*)(dy + base);
+    const int n4 = P >> 2;
+    for (int i = blockIdx.y * blockDim.x + threadIdx.x; i < n4; i += 2 * stride) {
+      const int i2 = i + stride;
+      const bool has2 = i2 < n4;
+      const float4 ya = __ldg(y4 + i), ga = __ldg(g4 + i);
+      float4 yb = ya, gb = ga;
+      if (has2) { yb = __ldg(y4 + i2); gb = __ldg(g4 + i2); }
+      float yv[8] = {ya.x, ya.y, ya.z, ya.w, yb.x, yb.y, yb.z, yb.w};
+      float gv[8] = {ga.x, ga.y, ga.z, ga.w, gb.x, gb.y, gb.z, gb.w};
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const float yc = yv[k] - cm;
+        float gg = gv[k];
+        if (fmaf(ca, yc, cb) <= 0.f) gg *= slope;
+        yv[k] = fmaf(cp, gg, fmaf(cq, yc, cr));
+      }
+      d4[i] = make_float4(yv[0], yv[1], yv[2], yv[3]);
+      if (has2) d4[i2] = make_float4(yv[4], yv[5], yv[6], yv[7]);
+    }
+    return;
+  }
+  for (int i = blockIdx.y * blockDim.x + threadIdx.x; i < P; i += 2 * stride) {
+    const int i2 = i + stride;
+    const bool has2 = i2 < P;
+    const float ya = __ldg(y + base + i), ga = gmap_load<MODE>(gp, i, m.Hy, m.Wy);
+    const float yb = has2 ? __ldg(y + base + i2) : cm, gb = has2 ? gmap_load<MODE>(gp, i2, m.Hy, m.Wy) : 0.f;
+    float yc = ya - cm, gg = ga;
+    if (fmaf(ca, yc, cb) <= 0.f) gg *= slope;
+    dy[base + i] = fmaf(cp, gg, fmaf(cq, yc, cr));
+    if (has2) {
+      yc = yb - cm; gg = gb;
+      if (fmaf(ca, yc, cb) <= 0.f) gg *= slope;
+      dy[base + i2] = fmaf(cp, gg, fmaf(cq, yc, cr));
+    }
+  }
+}
+
 // dx = rstd * (g' - mean(g') - xhat * mean(g' xhat)), xhat = rstd*(y - mu)  ->  dy = p g' + q (y - mu) + r
 __global__ void in_finalize_bwd_kernel(const float* __restrict__ s1, const float* __restrict__ s2,
                                        const float* __restrict__ a, float* __restrict__ p,
@@ -388,6 +530,56 @@ int san_act_bwd_apply(const float* g, const float* y, const float* mu, const flo
   SAN_CHECK_ARG(g && y && a && p && dy && planes > 0 && P > 0, "san_act_bwd_apply: bad args");
   dim3 grid(planes, chunks_for(planes, P));
   act_bwd_apply_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(g, y, mu, a, b, slope, p, q, r, dy, P);
+  SAN_LAUNCH_CHECK();
+  return SAN_OK;
+}
+
+static int gmap_check(const float* g, int N, int Ctot, int c0, int Cy, int Hy, int Wy, int mode, const char* who) {
+  SAN_CHECK_ARG(g && N > 0 && Ctot > 0 && c0 >= 0 && Cy > 0 && c0 + Cy <= Ctot && Hy > 0 && Wy > 0 && mode >= 0 && mode <= 3,
+                "%s: bad gradient map", who);
+  if (mode == 1) SAN_CHECK_ARG(Hy % 2 == 0 && Wy % 2 == 0, "%s: pooled source needs even size", who);
+  return SAN_OK;
+}
+static GMap make_gmap(const float* g, int Ctot, int c0, int Cy, int Hy, int Wy, int mode) {
+  const long long hwd = mode == 0 ? (long long)Hy * Wy : mode == 1 ? (long long)(Hy / 2) * (Wy / 2) : 4LL * Hy * Wy;
+  return GMap{g, (long long)Ctot * hwd, c0, Cy, Hy, Wy};
+}
+
+int san_act_bwd_reduce_map(const float* g, int Ctot, int c0, int mode, const float* y, const float* mu, const float* a,
+                           const float* b, const float* sa, float slope, float* s1, float* s2, int N, int Cy, int Hy,
+                           int Wy, void* stream) {
+  SAN_CHECK_ARG(y && a && s1 && s2, "san_act_bwd_reduce_map: bad args");
+  int rc = gmap_check(g, N, Ctot, c0, Cy, Hy, Wy, mode, "san_act_bwd_reduce_map");
+  if (rc != SAN_OK) return rc;
+  const GMap m = make_gmap(g, Ctot, c0, Cy, Hy, Wy, mode);
+  const int planes = N * Cy, P = (mode == 2 ? 4 : 1) * Hy * Wy;
+  cudaStream_t st = (cudaStream_t)stream;
+  switch (mode) {
+    case 0: act_bwd_reduce_map_kernel<0><<<planes, 256, 0, st>>>(m, y, mu, a, b, sa, slope, s1, s2, P); break;
+    case 1: act_bwd_reduce_map_kernel<1><<<planes, 256, 0, st>>>(m, y, mu, a, b, sa, slope, s1, s2, P); break;
+    case 2: act_bwd_reduce_map_kernel<2><<<planes, 256, 0, st>>>(m, y, mu, a, b, sa, slope, s1, s2, P); break;
+    default: act_bwd_reduce_map_kernel<3><<<planes, 256, 0, st>>>(m, y, mu, a, b, sa, slope, s1, s2, P); break;
+  }
+  SAN_LAUNCH_CHECK();
+  return SAN_OK;
+}
+
+int san_act_bwd_apply_map(const float* g, int Ctot, int c0, int mode, const float* y, const float* mu, const float* a,
+                          const float* b, float slope, const float* p, const float* q, const float* r, float* dy, int N,
+                          int Cy, int Hy, int Wy, void* stream) {
+  SAN_CHECK_ARG(y && a && p && dy, "san_act_bwd_apply_map: bad args");
+  int rc = gmap_check(g, N, Ctot, c0, Cy, Hy, Wy, mode, "san_act_bwd_apply_map");
+  if (rc != SAN_OK) return rc;
+  const GMap m = make_gmap(g, Ctot, c0, Cy, Hy, Wy, mode);
+  const int planes = N * Cy, P = (mode == 2 ? 4 : 1) * Hy * Wy;
+  dim3 grid(planes, chunks_for(planes, P));
+  cudaStream_t st = (cudaStream_t)stream;
+  switch (mode) {
+    case 0: act_bwd_apply_map_kernel<0><<<grid, 256, 0, st>>>(m, y, mu, a, b, slope, p, q, r, dy, P); break;
+    case 1: act_bwd_apply_map_kernel<1><<<grid, 256, 0, st>>>(m, y, mu, a, b, slope, p, q, r, dy, P); break;
+    case 2: act_bwd_apply_map_kernel<2><<<grid, 256, 0, st>>>(m, y, mu, a, b, slope, p, q, r, dy, P); break;
+    default: act_bwd_apply_map_kernel<3><<<grid, 256, 0, st>>>(m, y, mu, a, b, slope, p, q, r, dy, P); break;
+  }
   SAN_LAUNCH_CHECK();
   return SAN_OK;
 }

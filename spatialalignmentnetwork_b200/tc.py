@@ -239,37 +239,39 @@ class _FusedConv(Function):
             for t in terms:
                 if not ctx.needs_input_grad[3 + t["ti"]]:
                     continue
-                y, C, mode, slope, st = t["y"], t["C"], t["mode"], t["slope"], t["st"]
-                g = dx[:, t["c0"]:t["c0"] + C]
-                g = g if g.is_contiguous() else g.contiguous()
-                # undo the resampling: gradient at the resolution / layout of the raw tensor
-                if mode == MODE_POOL:
-                    gs = torch.empty_like(y)
-                    call("up2", g, gs, N * C, H, W, 0.25)
-                elif mode == MODE_D2S:
-                    gs = torch.empty_like(y)
-                    call("space_to_depth2", g, gs, N, C, H // 2, W // 2)
-                elif mode == MODE_UP:
-                    gs = torch.empty_like(y)
-                    call("pool2", g, gs, N * C, H, W, 1.0)
-                else:
-                    gs = g
+                y, C, mode, slope, st, c0 = t["y"], t["C"], t["mode"], t["slope"], t["st"], t["c0"]
+                Hy, Wy = y.shape[2], y.shape[3]
                 if st is None and slope == 1.0:
+                    # identity term: the gradient is the channel slice of dx, resampled back if need be
+                    g = dx[:, c0:c0 + C]
+                    if mode == MODE_DIRECT:
+                        grads[t["ti"]] = g
+                        continue
+                    g = g if g.is_contiguous() else g.contiguous()
+                    gs = torch.empty_like(y)
+                    if mode == MODE_POOL:
+                        call("up2", g, gs, N * C, H, W, 0.25)
+                    elif mode == MODE_D2S:
+                        call("space_to_depth2", g, gs, N, C, H // 2, W // 2)
+                    else:
+                        call("pool2", g, gs, N * C, H, W, 1.0)
                     grads[t["ti"]] = gs
                     continue
+                # normalised / activated terms read their gradient IN PLACE from dx (channel offset + adjoint
+                # of the resampling): no slice copy, no up2 / space_to_depth2 / pool2 temporaries
+                dy = torch.empty_like(y)
                 if st is None:      # bare LeakyReLU (cross.py:14)
-                    planes = y.shape[0] * y.shape[1]
-                    P = y.numel() // planes
+                    planes = N * C
                     ones = torch.ones(planes, dtype=torch.float32, device=dev)
-                    dy = torch.empty_like(y)
-                    call("act_bwd_apply", gs, y, None, ones, None, slope, ones, None, None, dy, planes, P)
+                    call("act_bwd_apply_map", dx, Cin, c0, mode, y, None, ones, None, slope, ones, None, None, dy,
+                         N, C, Hy, Wy)
                     grads[t["ti"]] = dy
                     continue
                 planes = st.shape[1]
                 P = y.numel() // planes
                 mu, a, b, sa = _coef_views(t["norm"], st)
                 wk = torch.empty(5, planes, dtype=torch.float32, device=dev)
-                call("act_bwd_reduce", gs, y, mu, a, b, sa, slope, wk[0], wk[1], planes, P)
+                call("act_bwd_reduce_map", dx, Cin, c0, mode, y, mu, a, b, sa, slope, wk[0], wk[1], N, C, Hy, Wy)
                 if t["norm"] == "in":
                     call("in_finalize_bwd", wk[0], wk[1], a, wk[2], wk[3], wk[4], planes, P)
                 else:
@@ -278,8 +280,7 @@ class _FusedConv(Function):
                     call("bn_finalize_bwd", wk[0], wk[1], gamma, sa, wk[2], wk[3], wk[4], dgamma, dbeta,
                          y.shape[0], y.shape[1], P, int(t["bn_training"]))
                     grads[t["ti"] + 1], grads[t["ti"] + 2] = dgamma, dbeta
-                dy = torch.empty_like(y)
-                call("act_bwd_apply", gs, y, mu, a, b, slope, wk[2], wk[3], wk[4], dy, planes, P)
+                call("act_bwd_apply_map", dx, Cin, c0, mode, y, mu, a, b, slope, wk[2], wk[3], wk[4], dy, N, C, Hy, Wy)
                 grads[t["ti"]] = dy
         return (dw, db, None, *grads)
 
