@@ -22,7 +22,7 @@
 // Work unit = (image n, strip of R rows, N-split); persistent CTAs walk units.  Warp roles:
 //   warp 0      TMA producer  (bulk copies of the A row span + the B weight block per K-step)
 //   warp 1      TMEM allocator + single-thread tcgen05.mma issuer
-//   warps 2..5  epilogue: tcgen05.ld the fp32 accumulators, + bias, store NCHW fp32 (coalesced:
+//   warps 2..9  epilogue (two warps per TMEM lane quarter, alternating tiles): tcgen05.ld the fp32 accumulators, + bias, store NCHW fp32 (coalesced:
 //               TMEM lane = pixel, so a warp writes 32 consecutive pixels of one channel)
 // Pipelines: smem full/empty per K-step stage, TMEM accumulator full/empty (double-buffered when
 // 2*T*Npad <= 512 columns) so the epilogue of unit i overlaps the MMAs of unit i+1.
@@ -32,7 +32,9 @@
 namespace {
 
 // ------------------------------------------------------------------------------------ geometry
-constexpr int TC_THREADS = 192;
+constexpr int TC_EPI_WARPS = 16;      // epilogue warps: 2 per TMEM lane quarter, alternating tiles (a single warp per
+                                      // quarter was instruction-latency bound: ~1450 dependent instructions per unit)
+constexpr int TC_THREADS = 64 + 32 * TC_EPI_WARPS;
 constexpr int TC_SMEM_HEADER = 256;   // barriers + tmem pointer
 constexpr int TC_SMEM_MAX = 225 * 1024;
 constexpr int TC_NMAX = 160;          // largest UMMA N used per unit
@@ -173,7 +175,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const ConvTcPara
 
   if (warp == 0 && lane == 0) {
     for (int i = 0; i < g.stages; ++i) { mbar_init(bar_full + 8 * i, 1); mbar_init(bar_empty + 8 * i, 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(bar_accf + 8 * i, 1); mbar_init(bar_acce + 8 * i, 4); }
+    for (int i = 0; i < 2; ++i) { mbar_init(bar_accf + 8 * i, 1); mbar_init(bar_acce + 8 * i, TC_EPI_WARPS); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
@@ -230,7 +232,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const ConvTcPara
     else mma_issue_loop<1>(p, g, tmem_base, stage0, bar_full, bar_empty, bar_accf, bar_acce);
   } else {
     // ================================ epilogue ====================================
-    const int wq = warp & 3;  // TMEM lane quarter this warp may access
+    const int wq = warp & 3;            // TMEM lane quarter this warp may access
+    const int egrp = (warp - 2) >> 2;   // which of the warps sharing that quarter: takes tiles t = egrp, egrp + G, ...
+    constexpr int EG = TC_EPI_WARPS / 4;
     int as = 0;
     uint32_t aph = 0;
     const long long HW = (long long)p.H * p.W;
@@ -244,7 +248,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const ConvTcPara
       mbar_wait(bar_accf + 8 * as, aph);
       tc_fence_after();
       float* yn = p.y + (long long)n * p.y_bs;
-      for (int t = 0; t < g.T; ++t) {
+      for (int t = egrp; t < g.T; t += EG) {
         const int q = t * 128 + wq * 32 + lane;
         const int r = q / g.Wp, x = q - r * g.Wp;
         const int yy = y0 + r;
