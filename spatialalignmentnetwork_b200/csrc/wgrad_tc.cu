@@ -93,6 +93,27 @@ struct WgParams {
   WgGeom g;
 };
 
+template <int NDX, bool STACKED>
+__device__ __forceinline__ void wg_issue(uint32_t a_s, uint32_t b_s, uint32_t a_hiw, uint32_t b_hiw, uint32_t a_losplit,
+                                         uint32_t b_losplit, uint32_t tmem_base, int Nn, uint32_t idesc, int kc,
+                                         uint32_t started) {
+  uint32_t st = started;
+  for (int k = 0; k < kc; k += 16) {
+    const uint32_t al = a_s + k;                          // 16 slots = 16 units of 16 B
+    const uint64_t A_hi = ((uint64_t)a_hiw << 32) | al, A_lo = ((uint64_t)a_hiw << 32) | (al + a_losplit);
+#pragma unroll
+    for (int dx = 0; dx < NDX; ++dx) {
+      const uint32_t bl = b_s + k + dx;
+      const uint64_t B_hi = ((uint64_t)b_hiw << 32) | bl, B_lo = ((uint64_t)b_hiw << 32) | (bl + b_losplit);
+      const uint32_t d = tmem_base + (uint32_t)(dx * Nn);
+      tc_mma_bf16(d, A_hi, B_hi, idesc, st);
+      if (!STACKED) tc_mma_bf16(d, A_lo, B_hi, idesc, 1u);
+      tc_mma_bf16(d, A_hi, B_lo, idesc, 1u);
+    }
+    st = 1;
+  }
+}
+
 __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_tc_kernel(const WgParams p) {
   extern __shared__ __align__(128) uint8_t smem[];
   const WgGeom& g = p.g;
@@ -131,30 +152,35 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_tc_kernel(const WgParams 
   const int xoff = (p.K == 3) ? (dyi - 1) * g.Wp - 1 : 0;
 
   if (warp == 0) {
-    if (lane == 0) {
-      int s = 0;
-      uint32_t ph = 0;
-      for (int u = cta; u < nunits; u += p.ctas_per_group) {
-        const int n = u / g.nchunks, ch = u - n * g.nchunks;
-        const int p0 = g.range0 + ch * g.KC;
-        const int kc = min(g.KC, g.range_len - ch * g.KC);      // multiple of 16
-        const uint32_t bytesA = (uint32_t)kc * 16, bytesB = (uint32_t)(kc + 2) * 16;   // X span: kc + 2 tap slots
-        mbar_wait(bar_empty + 8 * s, ph ^ 1);
-        const uint32_t sbase = stage0 + (uint32_t)s * g.stage_bytes;
-        mbar_expect_tx(bar_full + 8 * s, 2u * kga * bytesA + 2u * g.KGn * bytesB);
-        for (int hl = 0; hl < 2; ++hl) {
-          for (int kg = 0; kg < kga; ++kg) {
-            const __nv_bfloat16* src = p.dys + ((long long)(n * 2 + hl) * g.KGo + 16 * mb + kg) * plane + (long long)p0 * 8;
-            bulk_g2s(sbase + (uint32_t)((hl * kga + kg) * g.KC) * 16, src, bytesA, bar_full + 8 * s);
-          }
-          for (int kg = 0; kg < g.KGn; ++kg) {
-            const __nv_bfloat16* src =
-                p.xs + ((long long)(n * 2 + hl) * g.KGi + nc * g.KGn + kg) * plane + (long long)(p0 + xoff) * 8;
-            bulk_g2s(sbase + g.a_bytes + (uint32_t)((hl * g.KGn + kg) * g.XS) * 16, src, bytesB, bar_full + 8 * s);
-          }
+    // TMA producer: the whole warp walks the units; lane 0 arms the barrier, then the lanes issue the bulk
+    // copies of the stage in parallel (one thread issuing 16-70 copies per stage with their address
+    // arithmetic was a serial bottleneck)
+    int s = 0;
+    uint32_t ph = 0;
+    const int ncopy = 2 * (kga + g.KGn);
+    for (int u = cta; u < nunits; u += p.ctas_per_group) {
+      const int n = u / g.nchunks, ch = u - n * g.nchunks;
+      const int p0 = g.range0 + ch * g.KC;
+      const int kc = min(g.KC, g.range_len - ch * g.KC);      // multiple of 16
+      const uint32_t bytesA = (uint32_t)kc * 16, bytesB = (uint32_t)(kc + 2) * 16;   // X span: kc + 2 tap slots
+      mbar_wait(bar_empty + 8 * s, ph ^ 1);
+      const uint32_t sbase = stage0 + (uint32_t)s * g.stage_bytes;
+      if (lane == 0) mbar_expect_tx(bar_full + 8 * s, 2u * kga * bytesA + 2u * g.KGn * bytesB);
+      __syncwarp();
+      for (int c = lane; c < ncopy; c += 32) {
+        const int hl = c / (kga + g.KGn), r = c - hl * (kga + g.KGn);
+        if (r < kga) {
+          const __nv_bfloat16* src = p.dys + ((long long)(n * 2 + hl) * g.KGo + 16 * mb + r) * plane + (long long)p0 * 8;
+          bulk_g2s(sbase + (uint32_t)((hl * kga + r) * g.KC) * 16, src, bytesA, bar_full + 8 * s);
+        } else {
+          const int kg = r - kga;
+          const __nv_bfloat16* src =
+              p.xs + ((long long)(n * 2 + hl) * g.KGi + nc * g.KGn + kg) * plane + (long long)(p0 + xoff) * 8;
+          bulk_g2s(sbase + g.a_bytes + (uint32_t)((hl * g.KGn + kg) * g.XS) * 16, src, bytesB, bar_full + 8 * s);
         }
-        if (++s == g.stages) { s = 0; ph ^= 1; }
       }
+      __syncwarp();
+      if (++s == g.stages) { s = 0; ph ^= 1; }
     }
   } else if (warp == 1) {
     // whole warp runs the (warp-uniform) loops; one elected lane issues the tcgen05 instructions
@@ -179,22 +205,13 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_tc_kernel(const WgParams 
       const uint32_t a_s = ((stage0 + (uint32_t)s * g.stage_bytes) >> 4) + a_low;
       const uint32_t b_s = ((stage0 + (uint32_t)s * g.stage_bytes + g.a_bytes) >> 4) + b_low;
       if (elect_one_sync()) {
-        uint32_t st = started;
-        for (int k = 0; k < kc; k += 16) {
-          const uint32_t al = a_s + k;                          // 16 slots = 16 units of 16 B
-          const uint64_t A_hi = ((uint64_t)a_hiw << 32) | al, A_lo = ((uint64_t)a_hiw << 32) | (al + a_losplit);
-#pragma unroll
-          for (int dx = 0; dx < 3; ++dx) {
-            if (dx < ndx) {
-              const uint32_t bl = b_s + k + dx;
-              const uint64_t B_hi = ((uint64_t)b_hiw << 32) | bl, B_lo = ((uint64_t)b_hiw << 32) | (bl + b_losplit);
-              const uint32_t d = tmem_base + (uint32_t)(dx * g.Nn);
-              tc_mma_bf16(d, A_hi, B_hi, idesc, st);
-              if (!stacked) tc_mma_bf16(d, A_lo, B_hi, idesc, 1u);
-              tc_mma_bf16(d, A_hi, B_lo, idesc, 1u);
-            }
-          }
-          st = 1;
+        // the issue loop is specialised on (taps per row, stacked) so that it is branch-free
+        if (ndx == 3) {
+          if (stacked) wg_issue<3, true>(a_s, b_s, a_hiw, b_hiw, a_losplit, b_losplit, tmem_base, g.Nn, idesc, kc, started);
+          else wg_issue<3, false>(a_s, b_s, a_hiw, b_hiw, a_losplit, b_losplit, tmem_base, g.Nn, idesc, kc, started);
+        } else {
+          if (stacked) wg_issue<1, true>(a_s, b_s, a_hiw, b_hiw, a_losplit, b_losplit, tmem_base, g.Nn, idesc, kc, started);
+          else wg_issue<1, false>(a_s, b_s, a_hiw, b_hiw, a_losplit, b_losplit, tmem_base, g.Nn, idesc, kc, started);
         }
         tc_commit(bar_empty + 8 * s);
         if (u + p.ctas_per_group >= nunits) tc_commit(bar_done);
