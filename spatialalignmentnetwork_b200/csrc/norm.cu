@@ -245,6 +245,47 @@ __global__ void __launch_bounds__(256) act_bwd_reduce_map_kernel(const GMap m, c
         t2 += gg * (csa * yc);
       }
     }
+  } else if (MODE == 1 && (m.Wy & 3) == 0) {
+    // avg-pool adjoint, vectorised: 4 consecutive y pixels of a row read 2 consecutive dx pixels
+    const float4* y4 = (const float4*)(y + base);
+    const int n4 = P >> 2, w4 = m.Wy >> 2, wd = m.Wy >> 1;
+    for (int i = threadIdx.x; i < n4; i += blockDim.x) {
+      const int h = i / w4, wq = i - h * w4;
+      const float4 yv4 = __ldg(y4 + i);
+      const float2 g2 = __ldg((const float2*)(gp + (h >> 1) * wd + 2 * wq));
+      const float yv[4] = {yv4.x, yv4.y, yv4.z, yv4.w};
+      const float gv[4] = {0.25f * g2.x, 0.25f * g2.x, 0.25f * g2.y, 0.25f * g2.y};
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const float yc = yv[k] - cm;
+        float gg = gv[k];
+        if (fmaf(ca, yc, cb) <= 0.f) gg *= slope;
+        t1 += gg;
+        t2 += gg * (csa * yc);
+      }
+    }
+  } else if (MODE == 2 && (m.Wy & 3) == 0) {
+    // pixel-shuffle adjoint, vectorised: 4 consecutive pixels of sub-plane (a, b) read every other one of 8
+    // consecutive dx pixels of row 2h + a
+    const float4* y4 = (const float4*)(y + base);
+    const int n4 = P >> 2, w4 = m.Wy >> 2, q4 = m.Hy * w4, wd = 2 * m.Wy;
+    for (int i = threadIdx.x; i < n4; i += blockDim.x) {
+      const int sub = i / q4, r = i - sub * q4;
+      const int h = r / w4, wq = r - h * w4;
+      const float4 yv4 = __ldg(y4 + i);
+      const float4* gq = (const float4*)(gp + (2 * h + (sub >> 1)) * wd + 8 * wq);
+      const float4 ga = __ldg(gq), gb = __ldg(gq + 1);
+      const float yv[4] = {yv4.x, yv4.y, yv4.z, yv4.w};
+      const float gv[4] = {(sub & 1) ? ga.y : ga.x, (sub & 1) ? ga.w : ga.z, (sub & 1) ? gb.y : gb.x, (sub & 1) ? gb.w : gb.z};
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const float yc = yv[k] - cm;
+        float gg = gv[k];
+        if (fmaf(ca, yc, cb) <= 0.f) gg *= slope;
+        t1 += gg;
+        t2 += gg * (csa * yc);
+      }
+    }
   } else {
     for (int i = threadIdx.x; i < P; i += 2 * blockDim.x) {
       const int i2 = i + blockDim.x;
@@ -299,6 +340,50 @@ __global__ void __launch_bounds__(256) act_bwd_apply_map_kernel(const GMap m, co
       }
       d4[i] = make_float4(yv[0], yv[1], yv[2], yv[3]);
       if (has2) d4[i2] = make_float4(yv[4], yv[5], yv[6], yv[7]);
+    }
+    return;
+  }
+  if (MODE == 1 && (m.Wy & 3) == 0) {
+    const float4* y4 = (const float4*)(y + base);
+    float4* d4 = (float4*)(dy + base);
+    const int n4 = P >> 2, w4 = m.Wy >> 2, wd = m.Wy >> 1;
+    for (int i = blockIdx.y * blockDim.x + threadIdx.x; i < n4; i += stride) {
+      const int h = i / w4, wq = i - h * w4;
+      const float4 yv4 = __ldg(y4 + i);
+      const float2 g2 = __ldg((const float2*)(gp + (h >> 1) * wd + 2 * wq));
+      float yv[4] = {yv4.x, yv4.y, yv4.z, yv4.w};
+      const float gv[4] = {0.25f * g2.x, 0.25f * g2.x, 0.25f * g2.y, 0.25f * g2.y};
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const float yc = yv[k] - cm;
+        float gg = gv[k];
+        if (fmaf(ca, yc, cb) <= 0.f) gg *= slope;
+        yv[k] = fmaf(cp, gg, fmaf(cq, yc, cr));
+      }
+      d4[i] = make_float4(yv[0], yv[1], yv[2], yv[3]);
+    }
+    return;
+  }
+  if (MODE == 2 && (m.Wy & 3) == 0) {
+    const float4* y4 = (const float4*)(y + base);
+    float4* d4 = (float4*)(dy + base);
+    const int n4 = P >> 2, w4 = m.Wy >> 2, q4 = m.Hy * w4, wd = 2 * m.Wy;
+    for (int i = blockIdx.y * blockDim.x + threadIdx.x; i < n4; i += stride) {
+      const int sub = i / q4, r = i - sub * q4;
+      const int h = r / w4, wq = r - h * w4;
+      const float4 yv4 = __ldg(y4 + i);
+      const float4* gq = (const float4*)(gp + (2 * h + (sub >> 1)) * wd + 8 * wq);
+      const float4 ga = __ldg(gq), gb = __ldg(gq + 1);
+      float yv[4] = {yv4.x, yv4.y, yv4.z, yv4.w};
+      const float gv[4] = {(sub & 1) ? ga.y : ga.x, (sub & 1) ? ga.w : ga.z, (sub & 1) ? gb.y : gb.x, (sub & 1) ? gb.w : gb.z};
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const float yc = yv[k] - cm;
+        float gg = gv[k];
+        if (fmaf(ca, yc, cb) <= 0.f) gg *= slope;
+        yv[k] = fmaf(cp, gg, fmaf(cq, yc, cr));
+      }
+      d4[i] = make_float4(yv[0], yv[1], yv[2], yv[3]);
     }
     return;
   }
