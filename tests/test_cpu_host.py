@@ -124,3 +124,39 @@ def test_grad_allreduce_world_size_2(tmp_path):
                               stderr=subprocess.STDOUT) for r in range(2)]
     outs = [p.communicate(timeout=120)[0].decode() for p in procs]
     assert all(p.returncode == 0 for p in procs), outs
+
+
+def test_tc_geometry_covers_every_layer_shape(built):
+    """Host-side geometry of the tcgen05 kernels (no GPU needed): every conv of the cascade / sensitivity /
+    alignment U-Nets has a strip geometry (shared memory, TMEM columns, output-channel split) at the benchmark
+    size, at the multi-coil 640x368 size and at small test sizes, for forward, data gradient and weight gradient."""
+    from spatialalignmentnetwork_b200 import _lib
+    L = _lib.lib()
+
+    def unet_layers(cin, ch, pools):            # (Cin, Cout, K, level) of varnet.Unet
+        out, c = [(cin, ch, 3, 0), (ch, ch, 3, 0)], ch
+        for lv in range(1, pools):
+            out += [(c, 2 * c, 3, lv), (2 * c, 2 * c, 3, lv)]
+            c *= 2
+        out += [(c, 2 * c, 3, pools), (2 * c, 2 * c, 3, pools)]
+        for lv in range(pools - 1, -1, -1):
+            out += [(2 * c, 4 * c, 1, lv + 1), (2 * c, c, 3, lv), (c, c, 3, lv)]     # convT as 1x1, cat conv, conv
+            c //= 2
+        return out + [(ch, 2, 1, 0)]
+
+    align = [(2, 32, 3, 0), (32, 32, 3, 0), (96, 32, 3, 0), (32, 2, 3, 0)]
+    for lv in range(1, 5):
+        align += [(32 if lv == 1 else 64, 64, 1, lv), (64, 64, 3, lv), (128, 64, 3, lv), (64, 64, 1, lv)]
+    for (H, W) in [(320, 320), (640, 368), (64, 64), (48, 32)]:
+        for layers in (unet_layers(3, 18, 4), unet_layers(2, 8, 4), align):
+            for cin, cout, k, lv in layers:
+                h, w = H >> lv, W >> lv
+                if h < 1 or w < 1:
+                    continue
+                assert L.san_tc_supported(h, w, cin, cout, k) == 1, (h, w, cin, cout, k)
+                assert L.san_tc_supported(h, w, cout, cin, k) == 1, ("dgrad", h, w, cin, cout, k)
+                assert L.san_tc_staged_weight_elems(h, w, cout, cin, k) > 0
+                if w >= 16:
+                    assert L.san_tc_wgrad_supported(h, w, cin, cout, k) == 1, ("wgrad", h, w, cin, cout, k)
+    # staged activation buffer: [lead 8][N][2][Cpad/8][(H+2)(W+2)][8][trail 256]
+    assert L.san_tc_staged_act_elems(2, 4, 6, 18) == 2 * 2 * 4 * 6 * 8 * 8 + 8 + 256
