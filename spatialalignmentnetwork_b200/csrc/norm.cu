@@ -18,38 +18,40 @@ namespace {
 // ---- statistics -------------------------------------------------------------
 __global__ void __launch_bounds__(256) plane_stats_kernel(const float* __restrict__ x, float* __restrict__ mean,
                                                           float* __restrict__ m2, int P) {
+  // ONE pass: shifted-data sums in fp64 (pivot = first element of the plane, so the subtraction
+  // Q - S^2/P cancels at most a few bits): mean = K + S/P, m2 = sum (x - mean)^2 = Q - S^2/P.
   __shared__ double red[32];
   const float* p = x + (long long)blockIdx.x * P;
-  float s = 0.f;
+  const double K = (double)__ldg(p);
+  double s = 0.0, q = 0.0;
   if ((P & 3) == 0) {
     const float4* p4 = (const float4*)p;
-    for (int i = threadIdx.x; i < P / 4; i += blockDim.x) {
-      float4 v = p4[i];
-      s += (v.x + v.y) + (v.z + v.w);
-    }
-  } else {
-    for (int i = threadIdx.x; i < P; i += blockDim.x) s += p[i];
-  }
-  const double tot = block_sum_d((double)s, red);
-  const float mu = (float)(tot / P);
-  float q = 0.f;
-  if ((P & 3) == 0) {
-    const float4* p4 = (const float4*)p;
-    for (int i = threadIdx.x; i < P / 4; i += blockDim.x) {
-      float4 v = p4[i];
-      const float a = v.x - mu, b = v.y - mu, c = v.z - mu, d = v.w - mu;
-      q += (a * a + b * b) + (c * c + d * d);
+    const int n4 = P >> 2;
+    for (int i = threadIdx.x; i < n4; i += 2 * blockDim.x) {
+      const int i2 = i + blockDim.x;
+      const float4 va = __ldg(p4 + i);
+      float4 vb = make_float4((float)K, (float)K, (float)K, (float)K);
+      if (i2 < n4) vb = __ldg(p4 + i2);
+      const double d0 = (double)va.x - K, d1 = (double)va.y - K, d2 = (double)va.z - K, d3 = (double)va.w - K;
+      const double e0 = (double)vb.x - K, e1 = (double)vb.y - K, e2 = (double)vb.z - K, e3 = (double)vb.w - K;
+      s += ((d0 + d1) + (d2 + d3)) + ((e0 + e1) + (e2 + e3));
+      q += ((d0 * d0 + d1 * d1) + (d2 * d2 + d3 * d3)) + ((e0 * e0 + e1 * e1) + (e2 * e2 + e3 * e3));
     }
   } else {
     for (int i = threadIdx.x; i < P; i += blockDim.x) {
-      const float a = p[i] - mu;
-      q += a * a;
+      const double d = (double)__ldg(p + i) - K;
+      s += d;
+      q += d * d;
     }
   }
-  const double tq = block_sum_d((double)q, red);
+  // (the float-K padding of the vector path is exact only when K is a float, which it is: it was loaded as one)
+  const double S = block_sum_d(s, red);
+  const double Q = block_sum_d(q, red);
   if (threadIdx.x == 0) {
-    mean[blockIdx.x] = mu;
-    m2[blockIdx.x] = (float)tq;
+    double v = Q - S * S / (double)P;
+    if (v < 0.0) v = 0.0;
+    mean[blockIdx.x] = (float)(K + S / (double)P);
+    m2[blockIdx.x] = (float)v;
   }
 }
 

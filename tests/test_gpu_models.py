@@ -8,7 +8,7 @@ import random
 import pytest
 import torch
 
-from conftest import assert_close_to_fp64, grad_floor, load_golden, rel_l2, sub
+from conftest import assert_close_to_fp64, assert_grads_kink_tolerant, grad_floor, load_golden, rel_l2, sub
 
 pytestmark = pytest.mark.gpu
 
@@ -52,13 +52,9 @@ def test_varnet_fwd_bwd(tag):
     loss = ((rec - g["tgt"].cuda()) ** 2).mean()
     loss.backward()
     assert abs(loss.item() - g["loss"].item()) < 1e-4 * abs(g["loss"].item())
-    assert rel_l2(ks.grad, g["g_kspace"]) < GTOL_TINY
-    assert rel_l2(ref.grad, g["g_ref"]) < GTOL_TINY
-    grads = sub(g, "g.")
-    fl = grad_floor(grads)
-    params = dict(net.named_parameters())
-    for name, gg in grads.items():
-        assert rel_l2(params[name].grad, gg, fl) < GTOL_TINY, name
+    ours = {"g_kspace": ks.grad, "g_ref": ref.grad, **{k: p.grad for k, p in net.named_parameters()}}
+    gold = {"g_kspace": g["g_kspace"], "g_ref": g["g_ref"], **sub(g, "g.")}
+    assert_grads_kink_tolerant(ours, gold, GTOL_TINY, tag + ": ")
 
 
 def test_varnet_checkpointed_matches():
@@ -113,15 +109,11 @@ def test_align_fwd_bwd():
     loss = ((warped - g["tgt"].cuda()) ** 2).mean() + 1000.0 * ls
     loss.backward()
     assert rel_l2(img.grad, g["g_img"]) < GTOL
-    # bar = max(GTOL_TINY, 4 x the CPU fp32 oracle's own error against the fp64 oracle): the golden case is
-    # 2 x 32 x 48, its deep levels hold ~1.5e3 activations per layer, where one kink flip is 2.5e-2
+    # the golden case is 2 x 32 x 48: its deep levels hold ~1.5e3 activations per layer, where one kink flip is
+    # 2.5e-2 -> kink-tolerant comparison against the fp64 oracle and against the reference's own dump
     ours = {"g_img": img.grad, **{k: p.grad for k, p in st.named_parameters()}}
-    assert_close_to_fp64(ours, _align_oracle(g, torch.float32), _align_oracle(g, torch.float64), GTOL_TINY)
-    # and against the reference's own dump, at the (looser) bar that the chaos allows
-    grads = sub(g, "g.")
-    fl = grad_floor(grads)
-    for name, gg in grads.items():
-        assert rel_l2(ours[name], gg, fl) < GTOL_TINY, name
+    assert_grads_kink_tolerant(ours, _align_oracle(g, torch.float64), GTOL_TINY, "align vs fp64 oracle: ")
+    assert_grads_kink_tolerant(ours, sub(g, "g."), GTOL_TINY, "align vs reference dump: ")
     sd = st.state_dict()
     for name, v in sub(g, "sd_after.").items():           # BatchNorm running-stat side effect
         assert rel_l2(sd[name].double(), v.double()) < 1e-5, name
@@ -158,11 +150,7 @@ def test_rec_step_end_to_end():
         assert abs(getattr(net, k).item() - g[k].item()) < 1e-4 * max(1e-3, abs(g[k].item())), k
     net.loss_all.backward()
     for pre, mod in (("gT.", net.net_T), ("gR.", net.net_R)):
-        grads = sub(g, pre)
-        fl = grad_floor(grads)
-        params = dict(mod.named_parameters())
-        for name, gg in grads.items():
-            assert rel_l2(params[name].grad, gg, fl) < GTOL_TINY, name
+        assert_grads_kink_tolerant({k: p.grad for k, p in mod.named_parameters()}, sub(g, pre), GTOL_TINY, pre)
 
 
 def test_update_and_test_api():
@@ -222,9 +210,7 @@ def test_varnet_multicoil_nonsquare_vs_oracle(shape):
     assert rel_l2(rec, rec_o) < TOL
     ((rec - tgt.cuda()) ** 2).mean().backward()
     grads = {k: v.grad for k, v in sdo.items() if v.grad is not None}
-    fl = grad_floor(grads)
-    for name, p in net.named_parameters():
-        assert rel_l2(p.grad, grads[name], fl) < GTOL_TINY, name
+    assert_grads_kink_tolerant({k: p.grad for k, p in net.named_parameters()}, grads, GTOL_TINY, "multicoil: ")
 
 
 def test_train_and_eval_entry_points(tmp_path):
