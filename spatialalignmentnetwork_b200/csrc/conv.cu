@@ -2,9 +2,10 @@
 // reference varnet.py:139-146 (3x3 no-bias), :75-80 (1x1 + bias), :176-179
 // (ConvTranspose2d 2x2 s2, run as a 1x1 conv + pixel shuffle) and unet.py:119-140
 // (3x3 / 1x1 + bias).  This is the exact-fp32 path: shared-memory tiled FFMA with
-// register blocking (4 pixels x CPT output channels per thread).  The tcgen05
-// BF16x3 implicit-GEMM path (conv_tc.cu) replaces it for the layers it supports;
-// both are validated against the same oracle.
+// register blocking (4 pixels x CPT output channels per thread).  The default path
+// of the U-Nets is the tcgen05 BF16x3 implicit GEMM of conv_tc.cu / wgrad_tc.cu; these
+// kernels remain as the SAN_TC=0 A/B path, as the on-device checker in the tests and
+// for weight gradients of images narrower than 16 pixels.
 //
 //   forward : y[n,co,h,w] = bias[co] + sum_{ci,r,s} x[n,ci,h+r-p,w+s-p] * w[co,ci,r,s]
 //   dgrad   : the same kernel on dY with weights packed flipped/transposed
