@@ -1,6 +1,6 @@
 """Diagnostic (GPU box): where does backward error of the san_b200 modules come from?
 Compares ours (CUDA fp32) and the CPU fp32 oracle against the CPU fp64 oracle, per tensor.
-Not a test; run as ``python tools/diag_backward.py``."""
+Not a test; run as ``python tools/diag_backward.py`` (``SAN_TC=0`` selects the layer-by-layer fp32 kernels)."""
 import os
 import sys
 

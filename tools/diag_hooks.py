@@ -3,7 +3,9 @@
 Runs the golden ``align_s`` case twice through the SAME module code: once on the san_b200 kernels
 (fp32) and once with every ``ops.X.apply`` swapped for a torch fp64 emulation; a tensor hook on every
 op output records the gradient that reaches it.  Printing the per-op error in backward order shows the
-first op whose *input* gradient is wrong."""
+first op whose *input* gradient is wrong.
+
+Hooks the layer-by-layer ops: run with ``SAN_TC=0`` (the default fused tcgen05 path bypasses them)."""
 import os
 import sys
 
