@@ -94,6 +94,9 @@ int san_space_to_depth2(const float* y, float* x, int N, int Co, int H, int W, v
 long long san_tc_staged_act_elems(int N, int H, int W, int C);
 long long san_tc_staged_weight_elems(int H, int W, int Cout, int Cin, int K);   /* Cout/Cin of the LAUNCH */
 int san_tc_supported(int H, int W, int Cin, int Cout, int K);
+/* host-only: strip geometry of san_tc_conv for this shape; out[16] = Cin_pad, KG, KS, nsplit, Npad, Wp, Hp, R, T,
+ * S_alloc, strips, stages, acc_stages, a_bytes, b_bytes, smem_bytes (host pointer) */
+int san_tc_describe(int H, int W, int Cin, int Cout, int K, int* out);
 /* Fused operand producer: up to 3 channel-concatenated sources (varnet.py:116 concat order),
  * each out = leaky_relu(a[plane]*(y - mu[plane]) + b[plane], slope) (a NULL = identity), i.e. the
  * InstanceNorm / BatchNorm + LeakyReLU of varnet.py:141-145 / unet.py:124-126 applied on the fly;
@@ -132,6 +135,9 @@ int san_tc_conv(const void* xs, const void* ws, const float* bias, float* y, int
 /* dW[Cout,Cin,K,K] (and dbias[Cout] from the fp32 dy, both optional-bias) from the staged dY and the staged
  * input of the forward conv: tcgen05 GEMM over the pixel dimension, MN-major operands, BF16x3 */
 int san_tc_wgrad_supported(int H, int W, int Cin, int Cout, int K);
+/* host-only: decomposition of san_tc_wgrad; out[16] = KGo, KGi, nmb, nnc, ndy, Nn, KGn, KC, XS, stages, smem_bytes,
+ * nchunks, Wp, PS, range0, range_len (host pointer) */
+int san_tc_wgrad_describe(int H, int W, int Cin, int Cout, int K, int* out);
 int san_tc_wgrad(const void* dys, const void* xs, float* dw, float* dbias, const float* dy, int N, int H, int W, int Cin,
                  int Cout, int K, void* stream);
 

@@ -517,6 +517,17 @@ long long san_tc_staged_weight_elems(int H, int W, int Cout, int Cin, int K) {
   return (long long)g.nsplit * g.KS * K * K * 4 * g.Npad * 8;
 }
 
+// Host-only: the strip geometry the kernel would use, for tests / tooling.  out[0..15] = Cin_pad, KG, KS, nsplit,
+// Npad, Wp, Hp, R, T, S_alloc, strips, stages, acc_stages, a_bytes, b_bytes, smem_bytes.
+int san_tc_describe(int H, int W, int Cin, int Cout, int K, int* out) {
+  TcGeom g;
+  if (!out || !tc_geometry(H, W, Cin, Cout, K, &g)) return SAN_ERR_UNSUPPORTED;
+  const int v[16] = {g.Cin_pad, g.KG, g.KS, g.nsplit, g.Npad, g.Wp, g.Hp, g.R, g.T, g.S_alloc, g.strips, g.stages,
+                     g.acc_stages, g.a_bytes, g.b_bytes, g.smem_bytes};
+  for (int i = 0; i < 16; ++i) out[i] = v[i];
+  return SAN_OK;
+}
+
 int san_tc_supported(int H, int W, int Cin, int Cout, int K) {
   TcGeom g;
   return tc_geometry(H, W, Cin, Cout, K, &g) ? 1 : 0;

@@ -273,6 +273,17 @@ __global__ void __launch_bounds__(256) bias_grad_kernel(const float* __restrict_
 
 extern "C" {
 
+// Host-only: the decomposition san_tc_wgrad would use.  out[0..15] = KGo, KGi, nmb, nnc, ndy, Nn, KGn, KC, XS, stages,
+// smem_bytes, nchunks, Wp, PS, range0, range_len.
+int san_tc_wgrad_describe(int H, int W, int Cin, int Cout, int K, int* out) {
+  WgGeom g;
+  if (!out || !wg_geometry(H, W, Cin, Cout, K, &g)) return SAN_ERR_UNSUPPORTED;
+  const int v[16] = {g.KGo, g.KGi, g.nmb, g.nnc, g.ndy, g.Nn, g.KGn, g.KC, g.XS, g.stages, g.smem_bytes, g.nchunks,
+                     g.Wp, g.PS, g.range0, g.range_len};
+  for (int i = 0; i < 16; ++i) out[i] = v[i];
+  return SAN_OK;
+}
+
 int san_tc_wgrad_supported(int H, int W, int Cin, int Cout, int K) {
   WgGeom g;
   return wg_geometry(H, W, Cin, Cout, K, &g) ? 1 : 0;

@@ -10,7 +10,7 @@ import sys
 import pytest
 import torch
 
-from conftest import ROOT, load_golden
+from conftest import ROOT, load_golden, rel_l2
 
 LIB = os.path.join(ROOT, "spatialalignmentnetwork_b200", "libsan_b200.so")
 
@@ -160,3 +160,146 @@ def test_tc_geometry_covers_every_layer_shape(built):
                     assert L.san_tc_wgrad_supported(h, w, cin, cout, k) == 1, ("wgrad", h, w, cin, cout, k)
     # staged activation buffer: [lead 8][N][2][Cpad/8][(H+2)(W+2)][8][trail 256]
     assert L.san_tc_staged_act_elems(2, 4, 6, 18) == 2 * 2 * 4 * 6 * 8 * 8 + 8 + 256
+
+
+def _describe(L, H, W, Cin, Cout, K):
+    import ctypes
+    out = (ctypes.c_int * 16)()
+    assert L.san_tc_describe(H, W, Cin, Cout, K, ctypes.addressof(out)) == 0
+    keys = ("Cin_pad KG KS nsplit Npad Wp Hp R T S_alloc strips stages acc_stages a_bytes b_bytes smem_bytes").split()
+    return dict(zip(keys, list(out)))
+
+
+@pytest.mark.parametrize("shape", [(1, 3, 12, 20, 5, 3), (2, 18, 16, 24, 18, 3), (1, 20, 9, 33, 40, 1), (1, 7, 10, 18, 170, 3)])
+def test_tc_flattened_pixel_formulation_on_cpu(built, shape):
+    """CPU model of csrc/conv_tc.cu driven by the library's own geometry (san_tc_describe): the staged layout
+    Xs[n][hl][kg][slot][8] with a one-pixel zero border, strips of R rows, 128-row M tiles over the flattened padded
+    pixels q = r*Wp + x, filter taps as row offsets dy*Wp + dx of the same tile, BF16x3 partial products, output
+    channel split -- reproduces conv2d.  Checks the index arithmetic and the resource bounds the kernel relies on,
+    without a GPU."""
+    import torch.nn.functional as F
+    from spatialalignmentnetwork_b200 import _lib
+    L = _lib.lib()
+    N, Cin, H, W, Cout, K = shape
+    g = _describe(L, H, W, Cin, Cout, K)
+    Wp, Hp, R, T, Npad, KG = g["Wp"], g["Hp"], g["R"], g["T"], g["Npad"], g["KG"]
+    ntaps = K * K
+    # resource bounds
+    assert g["Cin_pad"] % 16 == 0 and g["Cin_pad"] >= Cin and KG * 8 == g["Cin_pad"] and g["KS"] * 16 == g["Cin_pad"]
+    assert Npad % 16 == 0 and g["nsplit"] * Npad >= Cout and Npad <= 256
+    assert T * Npad * g["acc_stages"] <= 512                                   # TMEM columns
+    assert g["S_alloc"] >= 128 * T + 2 * Wp + 2 and g["S_alloc"] >= (R + 2) * Wp  # every tap row of every tile is in the tile
+    assert g["a_bytes"] == 4 * g["S_alloc"] * 16 and g["b_bytes"] == ntaps * 4 * Npad * 16
+    assert g["stages"] >= 2 and 256 + g["stages"] * (g["a_bytes"] + g["b_bytes"]) <= 225 * 1024
+    assert g["strips"] == -(-H // R) and 128 * T >= R * Wp
+    torch.manual_seed(7)
+    x = torch.randn(N, Cin, H, W)
+    w = torch.randn(Cout, Cin, K, K) / (Cin * ntaps) ** 0.5
+    ref = F.conv2d(x.double(), w.double(), padding=K // 2)
+
+    def split(t):           # BF16 hi / lo halves
+        hi = t.to(torch.bfloat16).float()
+        return hi, (t - hi).to(torch.bfloat16).float()
+
+    # staged activations [N][hl][KG][Hp*Wp][8] (zero border, zero pad channels)
+    xp = torch.zeros(N, g["Cin_pad"], Hp, Wp)
+    xp[:, :Cin, 1:H + 1, 1:W + 1] = x
+    xs = torch.stack(split(xp), 1).reshape(N, 2, KG, 8, Hp * Wp).permute(0, 1, 2, 4, 3)     # [N,hl,KG,slot,8]
+    wp_ = torch.zeros(g["nsplit"] * Npad, g["Cin_pad"], ntaps)
+    wp_[:Cout, :Cin] = w.reshape(Cout, Cin, ntaps)
+    whi, wlo = split(wp_)
+    out = torch.zeros(N, Cout, H, W, dtype=torch.float64)
+    for n in range(N):
+        for st in range(g["strips"]):
+            y0 = st * R
+            rows_in = min(R + 2, Hp - y0)
+            tile = torch.zeros(2, KG, g["S_alloc"], 8)                         # what the TMA bulk copies deliver
+            tile[:, :, :rows_in * Wp] = xs[n][:, :, y0 * Wp:(y0 + rows_in) * Wp]
+            for ns in range(g["nsplit"]):
+                acc = torch.zeros(128 * T, Npad, dtype=torch.float64)
+                for tap in range(ntaps):
+                    off = (tap // 3) * Wp + (tap % 3) if ntaps == 9 else Wp + 1
+                    a_hi = tile[0, :, off:off + 128 * T].permute(1, 0, 2).reshape(128 * T, -1).double()   # [rows, Cin_pad]
+                    a_lo = tile[1, :, off:off + 128 * T].permute(1, 0, 2).reshape(128 * T, -1).double()
+                    b_hi = whi[ns * Npad:(ns + 1) * Npad, :, tap].double()
+                    b_lo = wlo[ns * Npad:(ns + 1) * Npad, :, tap].double()
+                    acc += a_hi @ b_hi.T + a_lo @ b_hi.T + a_hi @ b_lo.T
+                for q in range(R * Wp):
+                    r, xx = divmod(q, Wp)
+                    if xx < W and y0 + r < H:
+                        c_cnt = min(Npad, Cout - ns * Npad)
+                        if c_cnt > 0:
+                            out[n, ns * Npad:ns * Npad + c_cnt, y0 + r, xx] = acc[q, :c_cnt]
+    assert rel_l2(out, ref) < 2e-5
+
+
+@pytest.mark.parametrize("shape", [(2, 3, 12, 20, 5, 3), (1, 18, 16, 24, 18, 3), (1, 20, 9, 33, 40, 1), (1, 7, 10, 18, 170, 3),
+                                   (1, 192, 6, 16, 24, 3)])
+def test_tc_wgrad_formulation_on_cpu(built, shape):
+    """CPU model of csrc/wgrad_tc.cu driven by san_tc_wgrad_describe: groups (128-channel block of dY, chunk of
+    input channels, filter row), pixel chunks of KC slots over the range [Wp, Wp + ceil16(H*Wp)) of every image,
+    K = 16-slot GEMM steps, the X span starting (dy-1)*Wp - 1 slots before the dY chunk with dx as a +1-slot
+    shift, zero border pixels of dY instead of masks, lead-in / trailing slack of the staged buffer -- reproduces
+    the conv2d weight gradient."""
+    import ctypes
+    import torch.nn.functional as F
+    from spatialalignmentnetwork_b200 import _lib
+    L = _lib.lib()
+    N, Cin, H, W, Cout, K = shape
+    out = (ctypes.c_int * 16)()
+    assert L.san_tc_wgrad_describe(H, W, Cin, Cout, K, ctypes.addressof(out)) == 0
+    g = dict(zip("KGo KGi nmb nnc ndy Nn KGn KC XS stages smem_bytes nchunks Wp PS range0 range_len".split(), list(out)))
+    Wp, PS, KC = g["Wp"], g["PS"], g["KC"]
+    assert g["nnc"] * g["Nn"] == g["KGi"] * 8 and g["Nn"] % 16 == 0 and g["Nn"] <= 160 and 3 * g["Nn"] <= 512
+    assert g["nmb"] == -(-g["KGo"] // 16) and KC % 16 == 0 and g["range_len"] % 16 == 0 and g["stages"] >= 2
+    assert g["range0"] == Wp and g["range0"] + g["range_len"] <= PS and g["smem_bytes"] <= 225 * 1024
+    assert g["nchunks"] == -(-g["range_len"] // KC)
+    torch.manual_seed(9)
+    x = torch.randn(N, Cin, H, W)
+    gy = torch.randn(N, Cout, H, W)
+    wr = torch.zeros(Cout, Cin, K, K, dtype=torch.float64, requires_grad=True)
+    (F.conv2d(x.double(), wr, padding=K // 2) * gy.double()).sum().backward()
+    LEAD, TRAIL = 8, 256
+
+    def staged(t, C):       # flat buffer [lead][N][hl][KG][PS][8][trail] of BF16 hi/lo values (as float)
+        Cp = (C + 15) // 16 * 16
+        tp = torch.zeros(N, Cp, H + 2, W + 2)
+        tp[:, :C, 1:H + 1, 1:W + 1] = t
+        hi = tp.to(torch.bfloat16).float()
+        lo = (tp - hi).to(torch.bfloat16).float()
+        body = torch.stack([hi, lo], 1).reshape(N, 2, Cp // 8, 8, PS).permute(0, 1, 2, 4, 3).reshape(-1)
+        return torch.cat([torch.zeros(LEAD), body, torch.zeros(TRAIL)]), Cp // 8
+
+    dys, KGo = staged(gy, Cout)
+    xs, KGi = staged(x, Cin)
+    assert (KGo, KGi) == (g["KGo"], g["KGi"])
+
+    def span(buf, KGtot, n, hl, kg, slot0, nslots):      # what one bulk copy delivers: [nslots, 8]
+        o = LEAD + (((n * 2 + hl) * KGtot + kg) * PS + slot0) * 8
+        assert o >= 0 and o + nslots * 8 <= buf.numel()
+        return buf[o:o + nslots * 8].reshape(nslots, 8).double()
+
+    dw = torch.zeros(Cout, Cin, K, K, dtype=torch.float64)
+    for mb in range(g["nmb"]):
+        kga = min(16, KGo - 16 * mb)
+        for nc in range(g["nnc"]):
+            for dyi in range(g["ndy"]):
+                xoff = (dyi - 1) * Wp - 1 if K == 3 else 0
+                D = [torch.zeros(kga * 8, g["Nn"], dtype=torch.float64) for _ in range(g["ndy"])]
+                for n in range(N):
+                    for ch in range(g["nchunks"]):
+                        p0 = g["range0"] + ch * KC
+                        kc = min(KC, g["range_len"] - ch * KC)
+                        A = [torch.cat([span(dys, KGo, n, hl, 16 * mb + k, p0, kc) for k in range(kga)], 1) for hl in (0, 1)]
+                        B = [torch.cat([span(xs, KGi, n, hl, nc * g["KGn"] + k, p0 + xoff, kc + 2) for k in range(g["KGn"])], 1)
+                             for hl in (0, 1)]
+                        for dx in range(g["ndy"]):
+                            Bh, Bl = B[0][dx:dx + kc], B[1][dx:dx + kc]
+                            D[dx] += A[0].T @ Bh + A[1].T @ Bh + A[0].T @ Bl
+                for dx in range(g["ndy"]):
+                    tap = (dyi, dx) if K == 3 else (0, 0)
+                    co0, ci0 = mb * 128, nc * g["Nn"]
+                    nco, nci = min(kga * 8, Cout - co0), min(g["Nn"], Cin - ci0)
+                    if nco > 0 and nci > 0:
+                        dw[co0:co0 + nco, ci0:ci0 + nci, tap[0], tap[1]] += D[dx][:nco, :nci]
+    assert rel_l2(dw, wr.grad) < 2e-5
