@@ -210,6 +210,38 @@ int san_mi_hist_bwd(const float* I, const float* J, const float* gjoint, const f
 /* single-channel KxK correlation, zero padding K/2 (gaussian_smooth, miloss.py:13-24) */
 int san_filter2d(const float* x, const float* w, float* y, long long planes, int H, int W, int K, void* stream);
 
+/* ---- GAN branch: spectral norm + point-wise losses (gan.py:24,131-137; model.py:138-139) ---- */
+/* torch.nn.utils.spectral_norm (gan.py:24; one power iteration, dim 0) on W [rows, cols]:
+ * power_iteration != 0 (training): v = normalize(W^T u, eps), u = normalize(W v, eps) IN PLACE;
+ * then sigma[0] = u . (W v).  tmp: max(rows, cols) floats. */
+int san_sn_sigma(const float* w, float* u, float* v, float* tmp, float* sigma, int rows, int cols, float eps,
+                 int power_iteration, void* stream);
+/* out = w / sigma[0] */
+int san_sn_scale(const float* w, const float* sigma, float* out, long long n, void* stream);
+/* dW = (G - <G, W_sn> u v^T) / sigma   (u, v constants, as in torch).  scratch: 1 double. */
+int san_sn_bwd(const float* g, const float* w_sn, const float* u, const float* v, const float* sigma, double* scratch,
+               float* dw, int rows, int cols, void* stream);
+/* out[0] = mean_i f(x_i, y_i): mode 0 |x - y| (F.l1_loss, model.py:138), 1 max(sign*x, -1) (hinge,
+ * gan.py:133), 2 sign*x (gan.py:135).  y only for mode 0.  scratch: 1 double. */
+int san_pair_loss_fwd(const float* x, const float* y, long long n, int mode, float sign, float* out, double* scratch,
+                      void* stream);
+int san_pair_loss_bwd(const float* x, const float* y, const float* gout, long long n, int mode, float sign, float* dx,
+                      float* dy, void* stream);
+
+/* ---- evaluation metrics (metrics.py:23-68, model.py:265-286) ---- */
+/* out3 = { sum (a-b)^2, sum |a-b|, sum a^2 } in fp64 over n floats */
+int san_error_sums(const float* a, const float* b, long long n, double* out3, void* stream);
+/* per image n: np.histogram2d(x[n], y[n], bins, range [minv, maxv]) -> plug-in mutual information; out [N] doubles */
+int san_mi_metric(const float* x, const float* y, int N, int P, int bins, float minv, float maxv, double* out,
+                  void* stream);
+
+/* ---- optimiser (model.py:72-81: torch.optim.AdamW, one instance per network) ---- */
+/* One AdamW step (no amsgrad) on `ntensors` fp32 tensors.  params / grads / exp_avg / exp_avg_sq / numel are HOST
+ * arrays of device pointers (and element counts); `step` is the 1-based step count of the bias corrections. */
+int san_adamw_step(void* const* params, const void* const* grads, void* const* exp_avg, void* const* exp_avg_sq,
+                   const long long* numel, int ntensors, float lr, float beta1, float beta2, float eps,
+                   float weight_decay, int step, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

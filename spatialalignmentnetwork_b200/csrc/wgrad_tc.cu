@@ -9,7 +9,7 @@
 // is again only a shifted start address of the X tile.  Border pixels of dY are zero, so the padding
 // columns and the zero rows between images contribute nothing and need no masking.
 //
-// Decomposition: group = (block of <= 128 output channels, chunk of <= 160 input channels, filter
+// Decomposition: group = (block of <= 128 output channels, one of <= 16 chunks of <= 160 input channels, filter
 // row dy); the CTAs of a group split the pixel range of all images into chunks of KC slots and keep
 // three [128 x Nn] fp32 accumulators (dx = 0, 1, 2) in TMEM for the whole kernel; one atomicAdd pass
 // per CTA at the end.  BF16x3 as in the forward: hi*hi + lo*hi + hi*lo.
@@ -50,7 +50,7 @@ bool wg_geometry(int H, int W, int Cin, int Cout, int K, WgGeom* g) {
   g->nmb = (g->KGo + 15) / 16;
   const int cip = pad16(Cin);
   g->nnc = 0;
-  for (int k = 1; k <= 8; ++k)
+  for (int k = 1; k <= 16; ++k)
     if (cip % k == 0 && (cip / k) % 16 == 0 && cip / k <= 160) { g->nnc = k; break; }
   if (!g->nnc) return false;
   g->Nn = cip / g->nnc; g->KGn = g->Nn / 8;

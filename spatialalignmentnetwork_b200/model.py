@@ -1,20 +1,25 @@
-"""``CSModel`` for the reconstruction + rec-guided registration path of the reference
-(``reg`` in {'None', 'Rec'}; reference model.py:39-121, 142-169, 193-216, 265-321) on the
-san_b200 kernels.  Same attribute protocol (``img_*`` / ``loss_*`` tensors harvested by
-``get_vis``), same ``set_input`` / ``update`` / ``test`` / ``save`` / ``load`` calls, same
-``net_T`` / ``net_R`` / ``net_mask`` checkpoint keys.  The GAN branches (``net_G`` / ``net_D``,
-reg 'Mixed' / 'GAN-Only') are outside this hot path and raise.
+"""``CSModel`` of the reference (model.py:39-321) on the san_b200 kernels: all four training modes
+(``reg`` in {'None', 'Rec', 'Mixed', 'GAN-Only'}), ``test()`` with device-side metrics, same attribute
+protocol (``img_*`` / ``loss_*`` / ``metric_*`` harvested by ``get_vis``), same ``set_input`` / ``update`` /
+``test`` / ``save`` / ``load`` calls, same ``net_mask`` / ``net_G`` / ``net_D`` / ``net_T`` / ``net_R``
+checkpoint keys and construction order (so a seeded build draws the same initial weights).
 
 Additions over the reference (none changes results): ``num_cascades`` config knob (reference
-hard-codes 8, model.py:64), optional gradient all-reduce hook for one-process-per-GPU data
-parallel training, optional per-cascade recomputation.
+hard-codes 8, model.py:64) and ``gan_layers_G`` / ``gan_layers_D`` (reference hard-codes the widths,
+model.py:58-61), optional gradient all-reduce hook for one-process-per-GPU data parallel training,
+optional per-cascade recomputation, ``fused_adamw`` (one multi-tensor AdamW launch per network instead of
+torch's foreach kernels; same arithmetic).
 """
+import math
+
 import torch
 
 from . import ops
 from .basemodel import BaseModel, Config  # noqa: F401
 from .cross import SpatialTransformer
+from .gan import NetD, NetG, loss_gan
 from .masks import masks
+from .optim import AdamW
 from .signal_utils import fft2, fftshift2, ifft2, rss
 from .ssimloss import ssimloss
 from .varnet import VarNet
@@ -43,15 +48,28 @@ class CSModel(BaseModel):
     def build(self, cfg):
         super().build(cfg)
         assert cfg.lr == 1e-4
-        self.net_mask = masks[cfg.mask](cfg.sparsity, cfg.shape)
+        if cfg.mask in ("mask", "taylor"):
+            self.net_mask = masks[cfg.mask](cfg.shape)
+        else:
+            self.net_mask = masks[cfg.mask](cfg.sparsity, cfg.shape)
+        # same construction order as the reference (model.py:58-71): identical RNG consumption under a seed
+        layers_G = tuple(cfg.gan_layers_G) if "gan_layers_G" in cfg else (64, 128, 256, 512, 512)
+        layers_D = ([list(b) for b in cfg.gan_layers_D] if "gan_layers_D" in cfg else
+                    ([64] * 2, [128] * 2, [256] * 2, [256] * 2, [256] * 2))
+        self.net_G = NetG(in_channels=1, out_channels=1, layers=layers_G)
+        self.net_D = NetD(in_channels=2, layers=layers_D)
         self.net_T = SpatialTransformer(channels=cfg.coils)
         self.net_R = VarNet(num_cascades=cfg.num_cascades if "num_cascades" in cfg else 8,
                             sens_chans=8, sens_pools=4, chans=18, pools=4, use_ref=True)
         if "checkpoint_cascades" in cfg:
             self.net_R.checkpoint_cascades = bool(cfg.checkpoint_cascades)
-        self.optim_T = torch.optim.AdamW(self.net_T.parameters(), lr=cfg.lr, weight_decay=0)
-        self.optim_R = torch.optim.AdamW(self.net_R.parameters(), lr=cfg.lr, weight_decay=0)
-        self.use_amp = False  # fp32 parity path only
+        opt = AdamW if ("fused_adamw" not in cfg or cfg.fused_adamw) else torch.optim.AdamW
+        self.optim_G = opt(self.net_G.parameters(), lr=cfg.lr, weight_decay=0)
+        self.optim_D = opt(self.net_D.parameters(), lr=cfg.lr, weight_decay=0)
+        self.optim_T = opt(self.net_T.parameters(), lr=cfg.lr, weight_decay=0)
+        self.optim_R = opt(self.net_R.parameters(), lr=cfg.lr, weight_decay=0)
+        self.optim_M = opt(self.net_mask.parameters(), lr=cfg.lr, weight_decay=0)
+        self.use_amp = False  # fp32 parity path only (the reference's GradScaler is a no-op without amp)
 
     def set_input(self, img_full, img_aux=None):
         for name in [k for k in self.__dict__ if k.startswith(("loss_", "img_", "metric_"))]:
@@ -69,6 +87,32 @@ class CSModel(BaseModel):
         self.img_aux_rss = rss(self.img_aux)
         with torch.no_grad():
             self.img_mask = fftshift2(torch.ones_like(self.img_full_rss) - self.net_mask.pruned.float())
+
+    def forwardG(self):
+        """Modality translation (reference model.py:123-140): the first half of the batch is warped then
+        translated (R -> TR), the second half translated then warped (T -> RT)."""
+        aux_TR, aux_RT = torch.chunk(self.img_aux_rss, 2, dim=0)
+        T = self.net_G(aux_RT)
+        R, RT = torch.chunk(self.net_T.warp(img=torch.cat((aux_TR, T)), grid=self.img_grid), 2)
+        TR = self.net_G(R)
+        self.img_synth = torch.cat((R, T), dim=0)
+        self.img_aligned = torch.cat((TR, RT), dim=0)
+        self.loss_gan_sim = ops.l1_loss(self.img_aligned, self.img_full_rss)
+        self.loss_all = self.loss_all + self.loss_gan_sim * self.cfg.weight_gan_sim
+
+    def forwardD(self, D_loss):
+        """Hinge GAN terms on [image, 0] pairs (reference model.py:171-190); the zero second channel is read as
+        a second conv source instead of being concatenated."""
+        zeros = torch.zeros_like(self.img_full_rss)
+        if D_loss:
+            self.loss_gan_Dfake = loss_gan(self.net_D.forward_sources([self.img_aligned.detach(), zeros]),
+                                           real=False, D_loss=True)
+            self.loss_gan_Dreal = loss_gan(self.net_D.forward_sources([self.img_full_rss.detach(), zeros]),
+                                           real=True, D_loss=True)
+            self.loss_all = self.loss_all + (self.loss_gan_Dfake + self.loss_gan_Dreal) * self.cfg.weight_gan
+        else:
+            self.loss_gan_G = loss_gan(self.net_D.forward_sources([self.img_aligned, zeros]), real=False, D_loss=False)
+            self.loss_all = self.loss_all + self.loss_gan_G * self.cfg.weight_gan
 
     def forwardT(self):
         moving = _cabs(self.img_aux)
@@ -111,9 +155,31 @@ class CSModel(BaseModel):
             self._sync([self.net_T, self.net_R])
             self.optim_T.step()
             self.optim_R.step()
+        elif self.cfg.reg in ("Mixed", "GAN-Only"):
+            # (reconstruction and) GAN-guided registration: update T, G (and R), then D (model.py:217-260)
+            with_R = self.cfg.reg == "Mixed"
+            self.loss_all = 0
+            self.forwardT()
+            self.forwardG()
+            if with_R:
+                self.forwardR()
+            self.forwardD(D_loss=False)
+            nets = [self.net_T, self.net_G] + ([self.net_R] if with_R else [])
+            opts = [self.optim_T, self.optim_G] + ([self.optim_R] if with_R else [])
+            for o in opts:
+                o.zero_grad()
+            self.loss_all.backward()
+            self._sync(nets)
+            for o in opts:
+                o.step()
+            self.loss_all = 0
+            self.forwardD(D_loss=True)
+            self.optim_D.zero_grad()
+            self.loss_all.backward()
+            self._sync([self.net_D])
+            self.optim_D.step()
         else:
-            raise NotImplementedError(
-                f"reg={self.cfg.reg!r}: the GAN branches (net_G / net_D) are outside the san_b200 hot path")
+            assert False, f"unknown reg {self.cfg.reg!r}"
 
     def test(self):
         assert not self.training
@@ -121,13 +187,18 @@ class CSModel(BaseModel):
             self.loss_all = 0
             self.forwardT()
             self.loss_all = 0
+            self.forwardG()
+            self.loss_all = 0
             self.forwardR()
-            mse = torch.mean((self.img_full_rss - self.img_rec) ** 2)
-            self.metric_MSE = mse.item()
-            self.metric_MAE = torch.mean((self.img_full_rss - self.img_rec).abs()).item()
-            self.metric_PSNR = (10 * torch.log10(1.0 / mse)).item()       # metrics.py:35-38, range 1
-            self.metric_SSIM = 1.0 - self.loss_sim.item()
-        return -self.metric_PSNR
+            # metrics.py on the device: fp64 reductions, a few scalars cross to the host
+            n = self.img_full_rss.numel()
+            se, ae, _ = ops.error_sums(self.img_full_rss, self.img_rec)
+            self.metric_MI = ops.mi_metric(self.img_full_rss, self.img_warped_rss)
+            self.metric_MSE = se / n
+            self.metric_MAE = ae / n
+            self.metric_PSNR = 10.0 * math.log10(1.0 / self.metric_MSE)     # metrics.py:35-38, data_range 1
+            self.metric_SSIM = 1.0 - self.loss_sim.item()                   # skimage SSIM == 1 - ssimloss
+        return -self.metric_MI if self.cfg.reg == "GAN-Only" else -self.metric_PSNR
 
     def get_vis(self, content=None):
         assert content in [None, "scalars", "histograms", "images"]

@@ -685,3 +685,118 @@ class _Add(Function):
     @staticmethod
     def backward(ctx, g):
         return g, g
+
+
+class SpaceToDepth2(Function):
+    """[N, C, 2H, 2W] -> [N, C*4, H, W] (channel = c*4 + a*2 + b): turns the kernel-2 stride-2 convolution of
+    gan.py:43-46 into a 1x1 convolution over 4C channels."""
+
+    @staticmethod
+    def forward(ctx, y):
+        y = _f32(y, "space_to_depth")
+        N, C, H2, W2 = y.shape
+        assert H2 % 2 == 0 and W2 % 2 == 0, "space_to_depth needs even sizes"
+        x = torch.empty(N, C * 4, H2 // 2, W2 // 2, dtype=torch.float32, device=y.device)
+        call("space_to_depth2", y, x, N, C, H2 // 2, W2 // 2)
+        return x
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, g):
+        g = _f32(g, "space_to_depth.backward")
+        N, C4, H, W = g.shape
+        dy = torch.empty(N, C4 // 4, 2 * H, 2 * W, dtype=torch.float32, device=g.device)
+        call("depth_to_space2", g, dy, N, C4 // 4, H, W)
+        return dy
+
+
+# --------------------------------------------------------------------------- GAN branch
+class SpectralNormWeight(Function):
+    """``torch.nn.utils.spectral_norm`` (reference gan.py:24): W / sigma with sigma = u . (W v); in training
+    mode one power iteration first updates the ``u`` / ``v`` buffers in place.  u, v are constants of the
+    backward (torch detaches / clones them)."""
+
+    @staticmethod
+    def forward(ctx, w, u, v, power_iteration, eps):
+        w = _f32(w, "spectral_norm")
+        rows = w.shape[0]
+        cols = w.numel() // rows
+        assert u.numel() == rows and v.numel() == cols and u.is_contiguous() and v.is_contiguous()
+        tmp = torch.empty(max(rows, cols), dtype=torch.float32, device=w.device)
+        sigma = torch.empty(1, dtype=torch.float32, device=w.device)
+        call("sn_sigma", w, u, v, tmp, sigma, rows, cols, eps, int(power_iteration))
+        out = torch.empty_like(w)
+        call("sn_scale", w, sigma, out, w.numel())
+        ctx.save_for_backward(out, u.clone(), v.clone(), sigma)
+        ctx.mark_non_differentiable(u, v)
+        return out
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, g):
+        w_sn, u, v, sigma = ctx.saved_tensors
+        g = _f32(g, "spectral_norm.backward")
+        rows = w_sn.shape[0]
+        cols = w_sn.numel() // rows
+        dw = torch.empty_like(w_sn)
+        scratch = torch.empty(1, dtype=torch.float64, device=g.device)
+        call("sn_bwd", g, w_sn, u, v, sigma, scratch, dw, rows, cols)
+        return dw, None, None, None, None
+
+
+class PairLoss(Function):
+    """mean_i f(x_i, y_i): mode 0 ``F.l1_loss`` (model.py:138-139), mode 1 ``clamp(sign*x, min=-1).mean()``
+    and mode 2 ``(sign*x).mean()`` (the hinge / generator terms of ``loss_gan``, gan.py:131-137)."""
+
+    @staticmethod
+    def forward(ctx, x, y, mode, sign):
+        x = _f32(x, "pair_loss")
+        y = _f32(y, "pair_loss") if y is not None else None
+        assert mode in (0, 1, 2) and (mode != 0 or (y is not None and y.shape == x.shape))
+        out = torch.empty((), dtype=torch.float32, device=x.device)
+        scratch = torch.empty(1, dtype=torch.float64, device=x.device)
+        call("pair_loss_fwd", x, y, x.numel(), mode, float(sign), out, scratch)
+        ctx.save_for_backward(x, y)
+        ctx.cfg = (mode, float(sign))
+        return out
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, g):
+        x, y = ctx.saved_tensors
+        mode, sign = ctx.cfg
+        dx = torch.empty_like(x) if ctx.needs_input_grad[0] else None
+        dy = torch.empty_like(y) if (y is not None and ctx.needs_input_grad[1]) else None
+        if dx is None and dy is None:
+            return None, None, None, None
+        if dx is None and mode != 0:
+            return None, None, None, None
+        call("pair_loss_bwd", x, y, _c(g), x.numel(), mode, sign, dx, dy)
+        return dx, dy, None, None
+
+
+def l1_loss(x, y):
+    """``torch.nn.functional.l1_loss`` (mean reduction)."""
+    return PairLoss.apply(x, y, 0, 1.0)
+
+
+# --------------------------------------------------------------------------- metrics
+def error_sums(a, b):
+    """-> (sum (a-b)^2, sum |a-b|, sum a^2) as python floats (fp64 device reduction, one D2H of 24 bytes)."""
+    a, b = _f32(a, "error_sums"), _f32(b, "error_sums")
+    assert a.shape == b.shape
+    out = torch.empty(3, dtype=torch.float64, device=a.device)
+    call("error_sums", a, b, a.numel(), out)
+    return tuple(out.tolist())
+
+
+def mi_metric(gt, pred, bins=64, minVal=0.0, maxVal=1.0):
+    """metrics.mi (reference metrics.py:54-68): mean over the batch of the plug-in mutual information of the
+    hard ``bins x bins`` joint histogram."""
+    gt, pred = _f32(gt, "mi_metric"), _f32(pred, "mi_metric")
+    assert gt.shape == pred.shape and gt.dim() == 4, "wrong shape [batch, channel=1, rows, cols"
+    N = gt.shape[0]
+    out = torch.empty(N, dtype=torch.float64, device=gt.device)
+    call("mi_metric", gt, pred, N, gt.numel() // N, bins, float(minVal), float(maxVal), out)
+    vals = out.tolist()
+    return sum(vals) / len(vals)

@@ -8,7 +8,8 @@ reference train.py:198-253), same checkpoint directory format (basemodel.ckpt_sa
   * ``--train synthetic[:N]`` / ``--val synthetic[:N]`` generate seeded phantom slice pairs on the device instead
     of reading the fastMRI h5 volumes (h5py and the data are not available offline); csv paths are accepted only
     when ``h5py`` is importable;
-  * ``--reg`` is limited to None / Rec (the GAN branches are outside this hot path), ``--aux_aug`` to None.
+  * ``--aux_aug`` is limited to None; ``--gan_layers_G`` / ``--gan_layers_D`` (not in the reference) shrink the GAN
+    networks for smoke runs.
 """
 import argparse
 import json
@@ -55,6 +56,10 @@ def main(args):
     cfg = Config(sparsity=args.sparsity, lr=args.lr, shape=args.crop, coils=args.coils, reg=args.reg, mask=args.mask,
                  weight_smooth=args.smooth_weight, weight_gan=args.gan_weight, weight_gan_sim=args.gan_sim_weight,
                  weight_sim=args.sim_weight, use_amp=False, num_cascades=args.num_cascades)
+    if args.gan_layers_G:
+        cfg.gan_layers_G = [int(c) for c in args.gan_layers_G.split(",")]
+    if args.gan_layers_D:
+        cfg.gan_layers_D = [[int(c) for c in blk.split(",")] for blk in args.gan_layers_D.split(";")]
     net = CSModel(ckpt=args.resume, objects=args.load_nets) if args.resume else CSModel(cfg)
     net.to(device)
     if world > 1:
@@ -106,7 +111,7 @@ if __name__ == "__main__":
     p.add_argument("--batch_size", type=int, default=10, help="GLOBAL batch size (sharded over ranks)")
     p.add_argument("--num_workers", type=int, default=0)
     p.add_argument("--lr", type=float, default=1e-4)
-    p.add_argument("--reg", type=str, required=True, choices=["None", "Rec"])
+    p.add_argument("--reg", type=str, required=True, choices=["None", "Rec", "Mixed", "GAN-Only"])
     p.add_argument("--smooth_weight", type=float, required=True)
     p.add_argument("--gan_weight", type=float, default=0.0)
     p.add_argument("--gan_sim_weight", type=float, default=0.0)
@@ -120,6 +125,8 @@ if __name__ == "__main__":
     p.add_argument("--aux_aug", type=str, default="None", choices=["None"])
     p.add_argument("--force_gpu", action="store_true")
     p.add_argument("--num_cascades", type=int, default=8)
+    p.add_argument("--gan_layers_G", type=str, default="", help="e.g. 8,16,16 (default: the reference's 64,128,256,512,512)")
+    p.add_argument("--gan_layers_D", type=str, default="", help="e.g. '8,8;16,16' (default: the reference's widths)")
     p.add_argument("--log_every", type=int, default=50)
     p.add_argument("--ckpt_every", type=int, default=1000)
     main(p.parse_args())
