@@ -196,7 +196,10 @@ CLASSES = {
     "resample": ("pool2", "up2", "depth_to_space2", "space_to_depth2", "axpby"),
     "align_warp": ("grid_from_offset", "grid_to_nchw", "warp_fwd", "warp_bwd", "grad_loss_fwd", "grad_loss_bwd"),
     "losses": ("ssim_loss_fwd", "ssim_loss_bwd", "lncc_loss_fwd", "lncc_loss_bwd", "mi_hist_fwd", "mi_hist_bwd",
-               "filter2d"),
+               "filter2d", "pair_loss_fwd", "pair_loss_bwd"),
+    "gan_weights": ("sn_sigma", "sn_scale", "sn_bwd"),
+    "optimizer": ("adamw_step",),
+    "metrics": ("error_sums", "mi_metric"),
 }
 
 

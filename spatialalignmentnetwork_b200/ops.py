@@ -728,7 +728,6 @@ class SpectralNormWeight(Function):
         out = torch.empty_like(w)
         call("sn_scale", w, sigma, out, w.numel())
         ctx.save_for_backward(out, u.clone(), v.clone(), sigma)
-        ctx.mark_non_differentiable(u, v)
         return out
 
     @staticmethod

@@ -1,4 +1,4 @@
-"""One-process-per-GPU data parallelism for the Rec step: slices are independent, so the batch
+"""One-process-per-GPU data parallelism for the training step (all ``reg`` modes): slices are independent, so the batch
 is sharded across ranks and the only exchange is a gradient all-reduce (mean) per optimiser
 step over NCCL / NVLink (gloo on CPU for tests).  The reference has no distributed code
 (SURVEY.md §2.2); BatchNorm in ``net_T`` uses per-rank batch statistics (standard DDP
@@ -46,7 +46,8 @@ def broadcast_state(modules, src=0, group=None):
 
 def attach(model, group=None):
     """Install the gradient all-reduce into a ``CSModel`` and synchronise its initial state."""
-    broadcast_state([model.net_mask, model.net_T, model.net_R], group=group)
+    nets = [getattr(model, k) for k in ("net_mask", "net_G", "net_D", "net_T", "net_R") if hasattr(model, k)]
+    broadcast_state(nets, group=group)
     model.grad_sync = lambda params: allreduce_mean_grads(params, group=group)
     return model
 

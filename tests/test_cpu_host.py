@@ -147,8 +147,18 @@ def test_tc_geometry_covers_every_layer_shape(built):
     align = [(2, 32, 3, 0), (32, 32, 3, 0), (96, 32, 3, 0), (32, 2, 3, 0)]
     for lv in range(1, 5):
         align += [(32 if lv == 1 else 64, 64, 1, lv), (64, 64, 3, lv), (128, 64, 3, lv), (64, 64, 1, lv)]
+    # NetG(1, 1, (64, 128, 256, 512, 512)) / NetD(2, 5 blocks) of model.py:58-61 (gan.py:72-129): ConvDown as a
+    # 1x1 conv over 4*Cin space-to-depth channels, concat convs, the 1-channel heads
+    ch = [64, 128, 256, 512, 512]
+    netg = [(1, 64, 3, 0), (64, 64, 3, 0), (192, 64, 3, 0), (64, 1, 3, 0)]
+    for lv in range(1, 5):
+        netg += [(ch[lv - 1] * 4, ch[lv], 1, lv), (ch[lv], ch[lv], 3, lv)]
+        if lv < 4:
+            netg += [(ch[lv] + ch[lv + 1], ch[lv], 3, lv)]
+    netd = [(2, 64, 3, 0), (64, 64, 3, 0), (64, 128, 3, 1), (128, 128, 3, 1), (128, 256, 3, 2), (256, 256, 3, 2),
+            (256, 256, 3, 3), (256, 256, 3, 4), (256, 1, 3, 4)]
     for (H, W) in [(320, 320), (640, 368), (64, 64), (48, 32)]:
-        for layers in (unet_layers(3, 18, 4), unet_layers(2, 8, 4), align):
+        for layers in (unet_layers(3, 18, 4), unet_layers(2, 8, 4), align, netg, netd):
             for cin, cout, k, lv in layers:
                 h, w = H >> lv, W >> lv
                 if h < 1 or w < 1:
@@ -234,7 +244,7 @@ def test_tc_flattened_pixel_formulation_on_cpu(built, shape):
 
 
 @pytest.mark.parametrize("shape", [(2, 3, 12, 20, 5, 3), (1, 18, 16, 24, 18, 3), (1, 20, 9, 33, 40, 1), (1, 7, 10, 18, 170, 3),
-                                   (1, 192, 6, 16, 24, 3)])
+                                   (1, 192, 6, 16, 24, 3), (1, 2048, 3, 16, 16, 1)])
 def test_tc_wgrad_formulation_on_cpu(built, shape):
     """CPU model of csrc/wgrad_tc.cu driven by san_tc_wgrad_describe: groups (128-channel block of dY, chunk of
     input channels, filter row), pixel chunks of KC slots over the range [Wp, Wp + ceil16(H*Wp)) of every image,
