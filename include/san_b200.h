@@ -210,6 +210,16 @@ int san_mi_hist_bwd(const float* I, const float* J, const float* gjoint, const f
 /* single-channel KxK correlation, zero padding K/2 (gaussian_smooth, miloss.py:13-24) */
 int san_filter2d(const float* x, const float* w, float* y, long long planes, int H, int W, int K, void* stream);
 
+/* ---- misalignment augmentation of the auxiliary modality (augment.py:7-66, train.py:207-212) ---- */
+/* grid[n,h,w,:] = affine_grid(theta[n] (2x3), align_corners=False) + bicubic up-sampling (align_corners=False)
+ * of the control displacements ctrl[n] ([2,G,G], channel 0 = x; NULL: rigid only); grid [N,H,W,2] */
+int san_augment_grid(const float* theta, const float* ctrl, int G, float* grid, int N, int H, int W, void* stream);
+/* grid_sample(img, grid, bilinear, padding_mode='reflection', align_corners=False) on every plane of
+ * img [N,C,H,W] with `interleave` float components per pixel (1 = float, 2 = complex64: real and imaginary
+ * parts are sampled separately, augment.py:57-60); out [N,C,Ho,Wo] in the same format */
+int san_warp_reflect(const float* img, const float* grid, float* out, int N, int C, int H, int W, int Ho, int Wo,
+                     int interleave, void* stream);
+
 /* ---- GAN branch: spectral norm + point-wise losses (gan.py:24,131-137; model.py:138-139) ---- */
 /* torch.nn.utils.spectral_norm (gan.py:24; one power iteration, dim 0) on W [rows, cols]:
  * power_iteration != 0 (training): v = normalize(W^T u, eps), u = normalize(W v, eps) IN PLACE;
@@ -239,8 +249,8 @@ int san_mi_metric(const float* x, const float* y, int N, int P, int bins, float 
 /* One AdamW step (no amsgrad) on `ntensors` fp32 tensors.  params / grads / exp_avg / exp_avg_sq / numel are HOST
  * arrays of device pointers (and element counts); `step` is the 1-based step count of the bias corrections. */
 int san_adamw_step(void* const* params, const void* const* grads, void* const* exp_avg, void* const* exp_avg_sq,
-                   const long long* numel, int ntensors, float lr, float beta1, float beta2, float eps,
-                   float weight_decay, int step, void* stream);
+                   const long long* numel, int ntensors, double lr, double beta1, double beta2, double eps,
+                   double weight_decay, int step, void* stream);
 
 #ifdef __cplusplus
 }

@@ -19,4 +19,4 @@ build container by ``tests/golden/make_golden.py`` (which imports
 ``/root/reference``) and committed as ``tests/golden/*.npz``.
 ``tests/test_oracle_golden.py`` checks every oracle function against them.
 """
-from . import signal, varnet, align, losses, step, gan  # noqa: F401
+from . import signal, varnet, align, losses, step, gan, augment  # noqa: F401

@@ -25,8 +25,10 @@ struct AdamTable {
   int nt;
 };
 
-__global__ void __launch_bounds__(256) adamw_kernel(const AdamTable t, float lr, float b1, float b2, float eps, float wd,
-                                                    float bc1, float bc2_sqrt) {
+// decay = 1 - lr*wd, omb1 = 1 - beta1, omb2 = 1 - beta2, step = lr / (1 - beta1^t): formed in fp64 on the host and
+// rounded once, as torch does with its python-float hyper-parameters (1.f - 0.999f would be off by 1.3e-5)
+__global__ void __launch_bounds__(256) adamw_kernel(const AdamTable t, float decay, float omb1, float b2, float omb2,
+                                                    float eps, float step, float bc2_sqrt) {
   int ti = 0;
   while (ti + 1 < t.nt && (int)blockIdx.x >= t.chunk0[ti + 1]) ++ti;
   const long long base = (long long)((int)blockIdx.x - t.chunk0[ti]) * AD_CHUNK;
@@ -36,12 +38,11 @@ __global__ void __launch_bounds__(256) adamw_kernel(const AdamTable t, float lr,
   const float* __restrict__ g = t.g[ti];
   float* __restrict__ m = t.m[ti];
   float* __restrict__ v = t.v[ti];
-  const float step = lr / bc1;
   for (long long i = base + threadIdx.x; i < end; i += blockDim.x) {
     const float gi = g[i];
-    float pi = p[i] * (1.f - lr * wd);
-    const float mi = m[i] + (gi - m[i]) * (1.f - b1);          // lerp, as torch
-    const float vi = v[i] * b2 + (1.f - b2) * gi * gi;
+    float pi = p[i] * decay;
+    const float mi = m[i] + (gi - m[i]) * omb1;                // lerp, as torch
+    const float vi = v[i] * b2 + omb2 * gi * gi;
     const float denom = sqrtf(vi) / bc2_sqrt + eps;
     pi -= step * (mi / denom);
     p[i] = pi; m[i] = mi; v[i] = vi;
@@ -53,11 +54,11 @@ __global__ void __launch_bounds__(256) adamw_kernel(const AdamTable t, float lr,
 extern "C" {
 
 int san_adamw_step(void* const* params, const void* const* grads, void* const* exp_avg, void* const* exp_avg_sq,
-                   const long long* numel, int ntensors, float lr, float beta1, float beta2, float eps,
-                   float weight_decay, int step, void* stream) {
+                   const long long* numel, int ntensors, double lr, double beta1, double beta2, double eps,
+                   double weight_decay, int step, void* stream) {
   SAN_CHECK_ARG(params && grads && exp_avg && exp_avg_sq && numel && ntensors >= 0 && step >= 1, "san_adamw_step: bad args");
-  const float bc1 = 1.f - (float)pow((double)beta1, (double)step);
-  const float bc2_sqrt = (float)sqrt(1.0 - pow((double)beta2, (double)step));
+  const double bc1 = 1.0 - pow(beta1, (double)step);
+  const float bc2_sqrt = (float)sqrt(1.0 - pow(beta2, (double)step));
   for (int t0 = 0; t0 < ntensors; t0 += AD_MAXT) {
     AdamTable tab;
     tab.nt = ntensors - t0 < AD_MAXT ? ntensors - t0 : AD_MAXT;
@@ -74,7 +75,9 @@ int san_adamw_step(void* const* params, const void* const* grads, void* const* e
       blocks += (int)((numel[t0 + i] + AD_CHUNK - 1) / AD_CHUNK);
     }
     tab.chunk0[tab.nt] = blocks;
-    adamw_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(tab, lr, beta1, beta2, eps, weight_decay, bc1, bc2_sqrt);
+    adamw_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(tab, (float)(1.0 - lr * weight_decay), (float)(1.0 - beta1),
+                                                           (float)beta2, (float)(1.0 - beta2), (float)eps,
+                                                           (float)(lr / bc1), bc2_sqrt);
     SAN_LAUNCH_CHECK();
   }
   return SAN_OK;

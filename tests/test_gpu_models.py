@@ -159,7 +159,8 @@ def test_update_and_test_api():
     torch.manual_seed(0)
     random.seed(0)
     cfg = M.Config(sparsity=0.25, lr=1e-4, shape=64, coils=1, reg="Rec", mask="equispaced",
-                   weight_smooth=1000.0, weight_sim=1.0, num_cascades=1)
+                   weight_smooth=1000.0, weight_sim=1.0, weight_gan=0.1, weight_gan_sim=1.0, num_cascades=1,
+                   gan_layers_G=[8, 16, 16], gan_layers_D=[[8, 8], [16, 16]])
     net = M.CSModel(cfg).to("cuda")
     full = torch.complex(torch.rand(2, 1, 64, 64), torch.rand(2, 1, 64, 64)).cuda()
     aux = torch.complex(torch.rand(2, 1, 64, 64), torch.rand(2, 1, 64, 64)).cuda()

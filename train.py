@@ -8,7 +8,7 @@ reference train.py:198-253), same checkpoint directory format (basemodel.ckpt_sa
   * ``--train synthetic[:N]`` / ``--val synthetic[:N]`` generate seeded phantom slice pairs on the device instead
     of reading the fastMRI h5 volumes (h5py and the data are not available offline); csv paths are accepted only
     when ``h5py`` is importable;
-  * ``--aux_aug`` is limited to None; ``--gan_layers_G`` / ``--gan_layers_D`` (not in the reference) shrink the GAN
+  * ``--gan_layers_G`` / ``--gan_layers_D`` (not in the reference) shrink the GAN
     networks for smoke runs.
 """
 import argparse
@@ -41,6 +41,7 @@ def synthetic_pairs(n, shape, coils, device, seed):
 def main(args):
     import torch.distributed as dist
     from spatialalignmentnetwork_b200 import parallel
+    from spatialalignmentnetwork_b200.augment import augment_funcs, center_crop
     from spatialalignmentnetwork_b200.model import CSModel, Config
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -78,7 +79,10 @@ def main(args):
         perm = torch.randperm(n_train, generator=torch.Generator().manual_seed(epoch)).to(device)
         for b0 in range(0, n_train - args.batch_size + 1, args.batch_size):
             idx = parallel.shard(perm[b0:b0 + args.batch_size], rank, world)
-            net.set_input(full_t[idx], aux_t[idx])
+            with torch.no_grad():                           # reference train.py:208-210
+                batch = augment_funcs[args.aux_aug]([full_t[idx], aux_t[idx]])
+                batch = [center_crop(x, (net.cfg.shape, net.cfg.shape)).contiguous() for x in batch]
+            net.set_input(*batch)
             net.update()
             it += 1
             if rank == 0 and it % args.log_every == 0:
@@ -122,7 +126,7 @@ if __name__ == "__main__":
     p.add_argument("--val", type=str, required=True)
     p.add_argument("--crop", type=int, default=320)
     p.add_argument("--coils", type=int, default=1)
-    p.add_argument("--aux_aug", type=str, default="None", choices=["None"])
+    p.add_argument("--aux_aug", type=str, default="None", choices=["None", "Rigid", "BSpline", "PBSpline"])
     p.add_argument("--force_gpu", action="store_true")
     p.add_argument("--num_cascades", type=int, default=8)
     p.add_argument("--gan_layers_G", type=str, default="", help="e.g. 8,16,16 (default: the reference's 64,128,256,512,512)")
