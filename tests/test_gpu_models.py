@@ -240,3 +240,28 @@ def test_train_and_eval_entry_points(tmp_path):
     assert ev.returncode == 0, ev.stderr[-2000:]
     m = json.loads(ev.stdout.strip().splitlines()[-1])
     assert m["metric_PSNR"] > 5 and 0 <= m["metric_SSIM"] <= 1
+
+
+def test_train_entry_point_mixed_mode_with_augmentation(tmp_path):
+    """train.py --reg Mixed --aux_aug PBSpline (reference train.py:35-59,207-212; model.py:217-239): generator and
+    discriminator steps through the CLI with shrunk GAN networks; checkpoint holds all five networks."""
+    import json
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    logdir = str(tmp_path / "run")
+    cmd = [sys.executable, os.path.join(root, "train.py"), "--logdir", logdir, "--reg", "Mixed", "--smooth_weight", "1000",
+           "--sim_weight", "1", "--gan_weight", "0.1", "--gan_sim_weight", "1", "--mask", "equispaced", "--sparsity", "0.25",
+           "--train", "synthetic:8", "--val", "synthetic:4", "--crop", "64", "--batch_size", "4", "--epoch", "2",
+           "--num_cascades", "1", "--log_every", "1", "--aux_aug", "PBSpline", "--gan_layers_G", "8,16,16",
+           "--gan_layers_D", "8,8;16,16", "--force_gpu"]
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=root)
+    assert out.returncode == 0, out.stderr[-2000:]
+    its = [json.loads(l) for l in out.stdout.splitlines() if l.startswith("{") and "iter" in l]
+    assert len(its) == 4
+    for l in its:
+        for k in ("loss_smooth", "loss_sim", "loss_gan_sim", "loss_gan_G", "loss_gan_Dfake", "loss_gan_Dreal"):
+            assert l[k] == l[k], (k, l)                                                # present and finite
+    ck = [d for d in os.listdir(logdir) if d.endswith("_final.pt")]
+    assert len(ck) == 1 and {"config", "net_T", "net_R", "net_G", "net_D", "net_mask"} <= set(os.listdir(os.path.join(logdir, ck[0])))
