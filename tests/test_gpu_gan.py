@@ -229,9 +229,13 @@ def test_mixed_step_vs_reference_golden():
         assert abs(getattr(net, k).item() - g[k].item()) < 3e-4 * max(1e-3, abs(g[k].item())), k
     assert abs(net.loss_all.item() - g["loss_G"].item()) < 3e-4 * abs(g["loss_G"].item())
     net.loss_all.backward()
-    for t, bar in (("T", 1.2e-1), ("R", GTOL_TINY), ("G", 1e-1)):
+    # Small tensors (e.g. the 1-element BatchNorm affine of NetG's first block, 0.3 % of the largest gradient norm)
+    # are sums of cancelling terms: rounding realisations of the CPU model move them by up to 8e-3 of the largest
+    # norm, sign included (3 of 5 realisations fail a 1e-3 floor, none a 3e-2 floor:
+    # tests/test_oracle_gan.py::test_bf16x3_error_model_sets_the_gpu_bars) -> floor 5e-2 for T and G here.
+    for t, bar, fl in (("T", 1.2e-1, 5e-2), ("R", GTOL_TINY, 1e-3), ("G", 1e-1, 5e-2)):
         assert_grads_kink_tolerant({k: p.grad for k, p in getattr(net, "net_" + t).named_parameters()},
-                                   sub(g, f"g{t}."), bar, f"g{t}.")
+                                   sub(g, f"g{t}."), bar, f"g{t}.", floor_frac=fl)
     net.loss_all = 0
     net.forwardD(D_loss=True)
     net.optim_D.zero_grad()

@@ -94,30 +94,50 @@ def test_metrics():
         assert abs(ogan.metric_mi(g["gt"][i:i + 1], g["pred"][i:i + 1]) - g["mi_each"][i].item()) < 1e-12
 
 
-def test_bf16x3_error_model_sets_the_gpu_bars():
-    """What a CORRECT BF16x3 implementation yields on the Mixed-step fixture (tests/bf16x3_model.py): the tiny
-    golden NetG amplifies the 5e-5 operand-rounding error of its input (the warped image) ~20x, so
-    ``img_aligned`` lands ~1e-3 from the fp32 reference (measured on the B200: 1.15e-3) while every loss stays
-    within 2e-5 and the concatenated gradients within 4e-2.  The bars of
-    tests/test_gpu_gan.py::test_mixed_step_vs_reference_golden are 3x these predictions."""
+def _mixed_under_model(g, perturb_seed=None):
+    """The oracle's Mixed step with BF16x3 convolutions; ``perturb_seed``: another rounding realisation (net_T's
+    filters scaled by 1 + 1e-5 * N(0,1))."""
     import bf16x3_model
-    from conftest import cosine
-    g = load_golden("mixed_step")
     req = lambda k, v: v.is_floating_point() and "running" not in k and "weight_u" not in k and "weight_v" not in k
     sds = {t: {k: v.clone().requires_grad_(req(k, v)) for k, v in sub(g, f"sd{t}.").items()} for t in "TRGD"}
+    if perturb_seed is not None:
+        torch.manual_seed(perturb_seed)
+        for v in sds["T"].values():
+            if v.requires_grad and v.dim() == 4:
+                v.data.mul_(1 + 1e-5 * torch.randn_like(v))
     inp = step.set_input(g["full"], g["aux"], g["pruned"])
     with bf16x3_model.patched():
         out = ogan.mixed_step(sds["T"], sds["R"], sds["G"], sds["D"], inp, g["pruned"], 32, 0.25, num_cascades=2,
                               g_levels=G_LEVELS, d_blocks=D_BLOCKS, sens_pools=2, pools=2)
         out["loss_G"].backward()
+    return out, sds
+
+
+def test_bf16x3_error_model_sets_the_gpu_bars():
+    """What a CORRECT BF16x3 implementation yields on the Mixed-step fixture (tests/bf16x3_model.py): the tiny
+    golden NetG amplifies the 5e-5 operand-rounding error of its input (the warped image) ~20x, so
+    ``img_aligned`` lands ~1e-3 from the fp32 reference (measured on the B200: 1.15e-3) while every loss stays
+    within 2e-5 and the concatenated gradients within 4e-2 (6e-2 over other rounding realisations).  Tiny gradient
+    tensors (sums of cancelling terms, < 1 % of the largest gradient norm) move by more than their own size - on
+    the B200 ``gG.unet.0.norm_layer.weight`` came out with the opposite sign - which is why the GPU test floors
+    per-tensor errors at 5e-2 of the largest norm.  The bars of
+    tests/test_gpu_gan.py::test_mixed_step_vs_reference_golden are ~3x these predictions."""
+    from conftest import kink_tolerant_failures
+    g = load_golden("mixed_step")
+    out, sds = _mixed_under_model(g)
     e = {k: rel_l2(out[k], g[k]) for k in ("img_warped", "img_synth", "img_aligned", "img_rec")}
     assert e["img_warped"] < 1e-4 and e["img_synth"] < 1e-4 and e["img_rec"] < 1e-4, e
     assert 3e-4 < e["img_aligned"] < 1.4e-3, e            # the amplified one: above the generic 3e-4 bar, below 4e-3 / 3
     for k in ("loss_smooth", "loss_sim", "loss_gan_sim", "loss_gan_G", "loss_G"):
         assert abs(out[k].item() - g[k].item()) < 1e-4 * max(1e-3, abs(g[k].item())), k
-    cat = lambda d, names: torch.cat([d[k].double().flatten() for k in names])
-    for t, bar in (("T", 5e-2), ("R", 2e-2), ("G", 5e-2)):
-        ref = sub(g, f"g{t}.")
-        ours = {k: v.grad for k, v in sds[t].items() if v.requires_grad}
-        assert rel_l2(cat(ours, list(ref)), cat(ref, list(ref))) < bar, t
-        assert cosine(cat(ours, list(ref)), cat(ref, list(ref))) > 0.995, t
+    for seed in (None, 3):
+        if seed is not None:
+            out, sds = _mixed_under_model(g, seed)
+        for t, bar, gpu_bar in (("T", 6e-2, 1.2e-1), ("R", 3e-2, 6e-2), ("G", 5e-2, 1e-1)):
+            ours = {k: v.grad for k, v in sds[t].items() if v.requires_grad}
+            glob, bad = kink_tolerant_failures(ours, sub(g, f"g{t}."), gpu_bar, floor_frac=5e-2 if t != "R" else 1e-3)
+            assert glob < bar and not bad, (seed, t, glob, bad)
+    # ... and with the generic 1e-3 floor this realisation fails on one tiny tensor of G, like the B200 run did
+    ours = {k: v.grad for k, v in sds["G"].items() if v.requires_grad}
+    _, bad = kink_tolerant_failures(ours, sub(g, "gG."), 1e-1, floor_frac=1e-3)
+    assert len(bad) == 1 and bad[0][0].startswith("unet.0.norm_layer"), bad
