@@ -43,6 +43,9 @@ def parse():
     ap.add_argument("--batch", type=int, default=64, help="slices per GPU per step (weak scaling)")
     ap.add_argument("--shape", type=int, default=320)
     ap.add_argument("--cascades", type=int, default=12)
+    ap.add_argument("--reg", default="Rec", choices=["Rec", "Mixed"],
+                    help="training mode of the step: Rec = the headline cfg2 step; Mixed = BASELINE cfg5 (adds NetG twice, "
+                         "NetD, the GAN losses and the discriminator step, reference model.py:217-239)")
     ap.add_argument("--checkpoint", default="auto", choices=["auto", "0", "1"],
                     help="recompute each cascade in backward (memory knob)")
     ap.add_argument("--cpu-sample", type=int, default=2, help="slices in the CPU baseline sample")
@@ -134,7 +137,7 @@ def build_model(args):
     from spatialalignmentnetwork_b200 import model as M
     torch.manual_seed(SEED)
     random.seed(SEED)
-    cfg = M.Config(sparsity=0.25, lr=1e-4, shape=args.shape, coils=1, reg="Rec", mask="equispaced",
+    cfg = M.Config(sparsity=0.25, lr=1e-4, shape=args.shape, coils=1, reg=args.reg, mask="equispaced",
                    weight_smooth=1000.0, weight_gan=0.1, weight_gan_sim=1.0, weight_sim=1.0, use_amp=False,
                    num_cascades=args.cascades)
     net = M.CSModel(cfg)
@@ -256,30 +259,45 @@ def cpu_step_factory(args, nslices):
     """The reference's path restated on CPU (oracle/): set_input + forwardT + forwardR + backward +
     AdamW step, on ``nslices`` slices, all host threads."""
     import torch
-    from oracle import step as ostep
+    from oracle import gan as ogan, step as ostep
     torch.set_num_threads(os.cpu_count() or 1)
     net = build_model(args)
     pruned = net.net_mask.pruned.clone()
-    sdT = {k: v.detach().clone() for k, v in net.net_T.state_dict().items()}
-    sdR = {k: v.detach().clone() for k, v in net.net_R.state_dict().items()}
-    params = []
-    for d in (sdT, sdR):
-        for k, v in d.items():
-            if v.is_floating_point() and "running" not in k:
+    sds, opts = {}, {}
+    for t in "TRGD":
+        sd = {k: v.detach().clone() for k, v in getattr(net, "net_" + t).state_dict().items()}
+        params = []
+        for k, v in sd.items():
+            if v.is_floating_point() and "running" not in k and "weight_u" not in k and "weight_v" not in k:
                 v.requires_grad_(True)
                 params.append(v)
-    opt = torch.optim.AdamW(params, lr=1e-4, weight_decay=0)
+        sds[t], opts[t] = sd, torch.optim.AdamW(params, lr=1e-4, weight_decay=0)
     full, aux = make_inputs(nslices, args.shape)
 
-    def step():
+    def step_rec():
         inp = ostep.set_input(full, aux, pruned)
-        out = ostep.rec_step(sdT, sdR, inp, pruned, args.shape, 0.25, args.cascades)
-        opt.zero_grad()
+        out = ostep.rec_step(sds["T"], sds["R"], inp, pruned, args.shape, 0.25, args.cascades)
+        opts["T"].zero_grad(); opts["R"].zero_grad()
         out["loss_all"].backward()
-        opt.step()
+        opts["T"].step(); opts["R"].step()
         return out["loss_all"].item()
 
-    return step
+    def step_mixed():           # reference model.py:217-239: T, G, R step, then the discriminator step
+        inp = ostep.set_input(full, aux, pruned)
+        out = ogan.mixed_step(sds["T"], sds["R"], sds["G"], sds["D"], inp, pruned, args.shape, 0.25, args.cascades,
+                              g_levels=4, d_blocks=(2, 2, 2, 2, 2))
+        for t in "TGRD":
+            opts[t].zero_grad()
+        out["loss_G"].backward()
+        for t in "TGR":
+            opts[t].step()
+        d = out["d_side"]()
+        opts["D"].zero_grad()
+        d["loss_D"].backward()
+        opts["D"].step()
+        return d["loss_D"].item()
+
+    return step_mixed if args.reg == "Mixed" else step_rec
 
 
 def run_reference(args):
@@ -311,9 +329,15 @@ def run_reference(args):
 
 
 def workload_config(args, world, checkpoint, sample=None):
-    return {"workload": f"cfg2: bs={args.batch}/GPU {args.shape}x{args.shape} synthetic T1/T2 pairs, "
-                        f"{args.cascades}-cascade VarNet + alignment U-Net, reg='Rec' (smooth*1000 + SSIM), "
-                        "4x equispaced mask, fwd+bwd+AdamW",
+    if args.reg == "Mixed":
+        what = (f"cfg5 step: bs={args.batch}/GPU {args.shape}x{args.shape} synthetic T1/T2 pairs, {args.cascades}-cascade "
+                "VarNet + alignment U-Net + NetG (x2) + NetD, reg='Mixed' (smooth*1000 + L1 gan_sim + SSIM + hinge*0.1, "
+                "then the discriminator step), 4x equispaced mask, fwd+bwd+AdamW x4")
+    else:
+        what = (f"cfg2: bs={args.batch}/GPU {args.shape}x{args.shape} synthetic T1/T2 pairs, "
+                f"{args.cascades}-cascade VarNet + alignment U-Net, reg='Rec' (smooth*1000 + SSIM), "
+                "4x equispaced mask, fwd+bwd+AdamW")
+    return {"workload": what, "reg": args.reg,
             "batch_per_gpu": args.batch, "global_batch": args.batch * world,
             "shape": args.shape, "cascades": args.cascades, "coils": 1, "parallelism": f"dp{world}",
             "checkpoint_cascades": bool(checkpoint),

@@ -313,3 +313,18 @@ def test_tc_wgrad_formulation_on_cpu(built, shape):
                     if nco > 0 and nci > 0:
                         dw[co0:co0 + nco, ci0:ci0 + nci, tap[0], tap[1]] += D[dx][:nco, :nci]
     assert rel_l2(dw, wr.grad) < 2e-5
+
+
+def test_fft_small_host(tmp_path):
+    """csrc/fft_small.cuh (the per-thread register DFTs and the two-phase 16 x 20 decomposition of the opt-in v2 FFT
+    kernels, SAN_FFT_V2=1) compiled for the HOST and checked against a direct fp64 DFT."""
+    import shutil
+    import subprocess
+    nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    exe = str(tmp_path / "fft_small_test")
+    src = os.path.join(ROOT, "tests", "host", "fft_small_test.cu")
+    b = subprocess.run([nvcc, "-std=c++17", "--expt-relaxed-constexpr", "-Wno-deprecated-gpu-targets", "-o", exe, src],
+                       capture_output=True, text=True, timeout=300)
+    assert b.returncode == 0, b.stderr[-2000:]
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=60)
+    assert r.returncode == 0, r.stdout + r.stderr
