@@ -46,6 +46,10 @@ def parse():
     ap.add_argument("--reg", default="Rec", choices=["Rec", "Mixed"],
                     help="training mode of the step: Rec = the headline cfg2 step; Mixed = BASELINE cfg5 (adds NetG twice, "
                          "NetD, the GAN losses and the discriminator step, reference model.py:217-239)")
+    ap.add_argument("--lncc-weight", type=float, default=0.0, help="cfg3: add lncc_loss(full, warped) * weight to the step")
+    ap.add_argument("--mi-weight", type=float, default=0.0, help="cfg5: add ms_mi_loss(full, warped) * weight to the step")
+    ap.add_argument("--mask", default="equispaced", choices=["equispaced", "standard"])
+    ap.add_argument("--sparsity", type=float, default=0.25)
     ap.add_argument("--checkpoint", default="auto", choices=["auto", "0", "1"],
                     help="recompute each cascade in backward (memory knob)")
     ap.add_argument("--cpu-sample", type=int, default=2, help="slices in the CPU baseline sample")
@@ -137,9 +141,13 @@ def build_model(args):
     from spatialalignmentnetwork_b200 import model as M
     torch.manual_seed(SEED)
     random.seed(SEED)
-    cfg = M.Config(sparsity=0.25, lr=1e-4, shape=args.shape, coils=1, reg=args.reg, mask="equispaced",
+    cfg = M.Config(sparsity=args.sparsity, lr=1e-4, shape=args.shape, coils=1, reg=args.reg, mask=args.mask,
                    weight_smooth=1000.0, weight_gan=0.1, weight_gan_sim=1.0, weight_sim=1.0, use_amp=False,
                    num_cascades=args.cascades)
+    if args.lncc_weight:
+        cfg.weight_lncc = args.lncc_weight
+    if args.mi_weight:
+        cfg.weight_mi = args.mi_weight
     net = M.CSModel(cfg)
     with torch.no_grad():  # non-trivial displacement field (zero-init makes offset == 0), SURVEY 8(d)
         torch.nn.init.normal_(net.net_T.net[-1].weight, 0, 1e-2)
@@ -276,7 +284,8 @@ def cpu_step_factory(args, nslices):
 
     def step_rec():
         inp = ostep.set_input(full, aux, pruned)
-        out = ostep.rec_step(sds["T"], sds["R"], inp, pruned, args.shape, 0.25, args.cascades)
+        out = ostep.rec_step(sds["T"], sds["R"], inp, pruned, args.shape, args.sparsity, args.cascades,
+                             weight_lncc=args.lncc_weight, weight_mi=args.mi_weight)
         opts["T"].zero_grad(); opts["R"].zero_grad()
         out["loss_all"].backward()
         opts["T"].step(); opts["R"].step()
@@ -284,8 +293,8 @@ def cpu_step_factory(args, nslices):
 
     def step_mixed():           # reference model.py:217-239: T, G, R step, then the discriminator step
         inp = ostep.set_input(full, aux, pruned)
-        out = ogan.mixed_step(sds["T"], sds["R"], sds["G"], sds["D"], inp, pruned, args.shape, 0.25, args.cascades,
-                              g_levels=4, d_blocks=(2, 2, 2, 2, 2))
+        out = ogan.mixed_step(sds["T"], sds["R"], sds["G"], sds["D"], inp, pruned, args.shape, args.sparsity, args.cascades,
+                              g_levels=4, d_blocks=(2, 2, 2, 2, 2), weight_lncc=args.lncc_weight, weight_mi=args.mi_weight)
         for t in "TGRD":
             opts[t].zero_grad()
         out["loss_G"].backward()
@@ -337,6 +346,12 @@ def workload_config(args, world, checkpoint, sample=None):
         what = (f"cfg2: bs={args.batch}/GPU {args.shape}x{args.shape} synthetic T1/T2 pairs, "
                 f"{args.cascades}-cascade VarNet + alignment U-Net, reg='Rec' (smooth*1000 + SSIM), "
                 "4x equispaced mask, fwd+bwd+AdamW")
+    if args.lncc_weight:
+        what += f" + lncc_loss(full, warped)*{args.lncc_weight:g}"
+    if args.mi_weight:
+        what += f" + ms_mi_loss(full, warped)*{args.mi_weight:g}"
+    if args.mask != "equispaced" or args.sparsity != 0.25:
+        what = what.replace("4x equispaced mask", f"{1 / args.sparsity:g}x {args.mask} mask")
     return {"workload": what, "reg": args.reg,
             "batch_per_gpu": args.batch, "global_batch": args.batch * world,
             "shape": args.shape, "cascades": args.cascades, "coils": 1, "parallelism": f"dp{world}",

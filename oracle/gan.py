@@ -10,6 +10,8 @@ import torch
 import torch.nn.functional as F
 
 from . import align, losses, varnet
+from .signal import rss
+from .step import registration_terms
 
 SN_EPS = 1e-12
 
@@ -102,7 +104,7 @@ def loss_gan(predict, real=True, D_loss=True):
 
 def mixed_step(sd_T, sd_R, sd_G, sd_D, inp, pruned, shape, sparsity, num_cascades, g_levels, d_blocks,
                weight_smooth=1000.0, weight_sim=1.0, weight_gan=0.1, weight_gan_sim=1.0, with_R=True,
-               sens_pools=4, pools=4, levels_T=4):
+               sens_pools=4, pools=4, levels_T=4, weight_lncc=0.0, weight_mi=0.0):
     """forwardT + forwardG (+ forwardR) + forwardD(False), then forwardD(True) (model.py:123-190,217-260).
     Returns the generator-side and the discriminator-side results."""
     aux_abs = inp["img_aux"].abs()
@@ -116,8 +118,9 @@ def mixed_step(sd_T, sd_R, sd_G, sd_D, inp, pruned, shape, sparsity, num_cascade
     TR = netG(sd_G, "unet.", R, g_levels)
     synth, aligned = torch.cat((R, T), 0), torch.cat((TR, RT), 0)
     loss_gan_sim = F.l1_loss(aligned, inp["img_full_rss"])
-    loss_all = loss_smooth * weight_smooth + loss_gan_sim * weight_gan_sim
-    out = dict(img_offset=offset, img_warped=warped, img_synth=synth, img_aligned=aligned, loss_smooth=loss_smooth,
+    extra, extra_sum = registration_terms(inp["img_full_rss"], rss(warped), weight_lncc, weight_mi)
+    loss_all = loss_smooth * weight_smooth + loss_gan_sim * weight_gan_sim + extra_sum
+    out = dict(**extra, img_offset=offset, img_warped=warped, img_synth=synth, img_aligned=aligned, loss_smooth=loss_smooth,
                loss_gan_sim=loss_gan_sim)
     if with_R:
         rec = varnet.varnet(sd_R, "", inp["img_k_sampled"], torch.logical_not(pruned), warped,

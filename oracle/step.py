@@ -49,9 +49,23 @@ def set_input(img_full, img_aux, pruned):
                 img_aux_rss=rss(img_aux))
 
 
+def registration_terms(full_rss, warped_rss, weight_lncc=0.0, weight_mi=0.0):
+    """Optional similarity terms of BASELINE configs 3 / 5 between the target and the warped reference modality:
+    lncc_loss (lnccloss.py:7-56) and ms_mi_loss (miloss.py:59-67).  The reference ships both losses but has them
+    switched off in its live path (model.py:12); they enter ``loss_all`` with the given weights."""
+    out, total = {}, 0.0
+    if weight_lncc:
+        out["loss_lncc"] = losses.lncc_loss(full_rss, warped_rss)
+        total = total + out["loss_lncc"] * weight_lncc
+    if weight_mi:
+        out["loss_mi"] = losses.ms_mi_loss(full_rss, warped_rss)
+        total = total + out["loss_mi"] * weight_mi
+    return out, total
+
+
 def rec_step(sd_T, sd_R, inp, pruned, shape, sparsity, num_cascades,
              weight_smooth=1000.0, weight_sim=1.0, training=True,
-             sens_pools=4, pools=4, levels_T=4):
+             sens_pools=4, pools=4, levels_T=4, weight_lncc=0.0, weight_mi=0.0):
     """forwardT + forwardR (model.py:142-169) under ``reg='Rec'``; returns dict with
     loss_all, loss_smooth, loss_sim, img_offset, img_grid, img_warped, img_rec."""
     offset, grid = align.spatial_transformer(sd_T, "", inp["img_aux"].abs(), inp["img_sampled"].abs(),
@@ -61,6 +75,7 @@ def rec_step(sd_T, sd_R, inp, pruned, shape, sparsity, num_cascades,
     rec = varnet.varnet(sd_R, "", inp["img_k_sampled"], torch.logical_not(pruned), warped,
                         int(shape * sparsity * 0.32), num_cascades, sens_pools, pools, use_ref=True)
     loss_sim = losses.ssimloss(inp["img_full_rss"], rec)
-    loss_all = loss_smooth * weight_smooth + loss_sim * weight_sim
+    extra, extra_sum = registration_terms(inp["img_full_rss"], rss(warped), weight_lncc, weight_mi)
+    loss_all = loss_smooth * weight_smooth + loss_sim * weight_sim + extra_sum
     return dict(loss_all=loss_all, loss_smooth=loss_smooth, loss_sim=loss_sim, img_offset=offset,
-                img_grid=grid, img_warped=warped, img_rec=rec)
+                img_grid=grid, img_warped=warped, img_rec=rec, **extra)

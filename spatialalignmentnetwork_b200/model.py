@@ -18,7 +18,9 @@ from . import ops
 from .basemodel import BaseModel, Config  # noqa: F401
 from .cross import SpatialTransformer
 from .gan import NetD, NetG, loss_gan
+from .lnccloss import lncc_loss
 from .masks import masks
+from .miloss import ms_mi_loss
 from .optim import AdamW
 from .signal_utils import fft2, fftshift2, ifft2, rss
 from .ssimloss import ssimloss
@@ -121,6 +123,15 @@ class CSModel(BaseModel):
         self.img_warped_rss = rss(self.img_warped)
         self.loss_smooth = gradient_loss(self.img_offset)
         self.loss_all = self.loss_all + self.loss_smooth * self.cfg.weight_smooth
+        # Optional registration similarity terms of BASELINE configs 3 and 5 (the reference carries both losses,
+        # lnccloss.py / miloss.py, but its live path has them commented out, model.py:12): absent unless the
+        # config names a weight.
+        if "weight_lncc" in self.cfg and self.cfg.weight_lncc:
+            self.loss_lncc = lncc_loss(self.img_full_rss, self.img_warped_rss)
+            self.loss_all = self.loss_all + self.loss_lncc * self.cfg.weight_lncc
+        if "weight_mi" in self.cfg and self.cfg.weight_mi:
+            self.loss_mi = ms_mi_loss(self.img_full_rss, self.img_warped_rss)
+            self.loss_all = self.loss_all + self.loss_mi * self.cfg.weight_mi
 
     def forwardR(self):
         self.img_rec = self.net_R(masked_kspace=self.img_k_sampled, mask=torch.logical_not(self.net_mask.pruned),

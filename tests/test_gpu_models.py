@@ -265,3 +265,38 @@ def test_train_entry_point_mixed_mode_with_augmentation(tmp_path):
             assert l[k] == l[k], (k, l)                                                # present and finite
     ck = [d for d in os.listdir(logdir) if d.endswith("_final.pt")]
     assert len(ck) == 1 and {"config", "net_T", "net_R", "net_G", "net_D", "net_mask"} <= set(os.listdir(os.path.join(logdir, ck[0])))
+
+
+def test_optional_registration_terms():
+    """BASELINE configs 3 / 5: lncc_loss / ms_mi_loss between the target and the warped reference modality enter
+    ``loss_all`` when the config names ``weight_lncc`` / ``weight_mi`` (absent by default, as in the reference's
+    live path).  Values against the CPU oracle on the same tensors; gradients reach net_T."""
+    from oracle import losses as ol
+    from spatialalignmentnetwork_b200 import model as M
+    torch.manual_seed(5)
+    random.seed(5)
+    cfg = M.Config(sparsity=0.25, lr=1e-4, shape=64, coils=1, reg="Rec", mask="standard", weight_smooth=1000.0,
+                   weight_sim=1.0, weight_gan=0.1, weight_gan_sim=1.0, num_cascades=1, weight_lncc=1.0, weight_mi=0.5,
+                   gan_layers_G=[8, 16, 16], gan_layers_D=[[8, 8], [16, 16]])
+    net = M.CSModel(cfg)
+    with torch.no_grad():
+        torch.nn.init.normal_(net.net_T.net[-1].weight, 0, 1e-2)
+    net.to("cuda").train()
+    full = torch.rand(2, 1, 64, 64).cuda() + 0j
+    aux = torch.rand(2, 1, 64, 64).cuda() + 0j
+    net.set_input(full.to(torch.complex64), aux.to(torch.complex64))
+    net.loss_all = 0
+    net.forwardT()
+    f, w = net.img_full_rss.detach().cpu(), net.img_warped_rss.detach().cpu()
+    ref_lncc, ref_mi = ol.lncc_loss(f, w).item(), ol.ms_mi_loss(f, w).item()
+    assert abs(net.loss_lncc.item() - ref_lncc) < 1e-3 * max(0.1, abs(ref_lncc))
+    assert abs(net.loss_mi.item() - ref_mi) < 1e-3 * max(0.1, abs(ref_mi))
+    expect = net.loss_smooth.item() * 1000.0 + ref_lncc * 1.0 + ref_mi * 0.5
+    assert abs(net.loss_all.item() - expect) < 1e-3 * max(0.1, abs(expect))
+    net.loss_all.backward()
+    g = net.net_T.net[-1].weight.grad
+    assert g is not None and torch.isfinite(g).all() and g.abs().max() > 0
+    net.forwardR()          # and the full step still runs with the extra terms
+    net.set_input(full.to(torch.complex64), aux.to(torch.complex64))
+    net.update()
+    assert {"loss_lncc", "loss_mi"} <= set(net.get_vis("scalars")["scalars"])

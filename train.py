@@ -57,6 +57,10 @@ def main(args):
     cfg = Config(sparsity=args.sparsity, lr=args.lr, shape=args.crop, coils=args.coils, reg=args.reg, mask=args.mask,
                  weight_smooth=args.smooth_weight, weight_gan=args.gan_weight, weight_gan_sim=args.gan_sim_weight,
                  weight_sim=args.sim_weight, use_amp=False, num_cascades=args.num_cascades)
+    if args.lncc_weight:
+        cfg.weight_lncc = args.lncc_weight
+    if args.mi_weight:
+        cfg.weight_mi = args.mi_weight
     if args.gan_layers_G:
         cfg.gan_layers_G = [int(c) for c in args.gan_layers_G.split(",")]
     if args.gan_layers_D:
@@ -129,6 +133,8 @@ if __name__ == "__main__":
     p.add_argument("--aux_aug", type=str, default="None", choices=["None", "Rigid", "BSpline", "PBSpline"])
     p.add_argument("--force_gpu", action="store_true")
     p.add_argument("--num_cascades", type=int, default=8)
+    p.add_argument("--lncc_weight", type=float, default=0.0, help="extra registration term lncc_loss(full, warped) (BASELINE cfg3)")
+    p.add_argument("--mi_weight", type=float, default=0.0, help="extra registration term ms_mi_loss(full, warped) (BASELINE cfg5)")
     p.add_argument("--gan_layers_G", type=str, default="", help="e.g. 8,16,16 (default: the reference's 64,128,256,512,512)")
     p.add_argument("--gan_layers_D", type=str, default="", help="e.g. '8,8;16,16' (default: the reference's widths)")
     p.add_argument("--log_every", type=int, default=50)
