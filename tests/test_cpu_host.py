@@ -328,3 +328,49 @@ def test_fft_small_host(tmp_path):
     assert b.returncode == 0, b.stderr[-2000:]
     r = subprocess.run([exe], capture_output=True, text=True, timeout=60)
     assert r.returncode == 0, r.stdout + r.stderr
+
+
+_WORKER_ATTACH = r'''
+import os, random, sys, torch, torch.distributed as dist
+sys.path.insert(0, sys.argv[1])
+from spatialalignmentnetwork_b200 import model as M, parallel
+dist.init_process_group("gloo", init_method="tcp://127.0.0.1:" + sys.argv[2], rank=int(sys.argv[3]), world_size=2)
+r = dist.get_rank()
+random.seed(7)                      # identical column masks on every rank (train.py seeds python random the same way)
+torch.manual_seed(100 + r)          # different initial weights: attach() must make them identical
+cfg = M.Config(sparsity=0.25, lr=1e-4, shape=32, coils=1, reg="Mixed", mask="equispaced", weight_smooth=1000.0,
+               weight_sim=1.0, weight_gan=0.1, weight_gan_sim=1.0, num_cascades=1, fused_adamw=False,
+               gan_layers_G=[4, 8, 8], gan_layers_D=[[4, 4], [8, 8]])
+net = M.CSModel(cfg)
+parallel.attach(net)
+for name in ("net_mask", "net_G", "net_D", "net_T", "net_R"):
+    for k, v in getattr(net, name).state_dict().items():
+        both = [torch.zeros_like(v) for _ in range(2)]
+        dist.all_gather(both, v.contiguous())
+        assert torch.equal(both[0], both[1]), (name, k)
+# the hook CSModel.update() calls between backward and the optimiser steps: mean over ranks, per network list
+for p in net.net_G.parameters():
+    p.grad = torch.full_like(p, float(r + 1))
+for p in net.net_D.parameters():
+    p.grad = torch.full_like(p, 10.0 * (r + 1))
+net._sync([net.net_T, net.net_G])   # net_T has no gradients yet: skipped
+assert all(torch.all(p.grad == 1.5) for p in net.net_G.parameters())
+assert all(torch.all(p.grad == 10.0 * (r + 1)) for p in net.net_D.parameters())
+net._sync([net.net_D])
+assert all(torch.all(p.grad == 15.0) for p in net.net_D.parameters())
+dist.destroy_process_group()
+print("ok", r)
+'''
+
+
+def test_attach_broadcasts_all_networks_world_size_2(tmp_path):
+    """parallel.attach on a CSModel with the GAN networks: every parameter / buffer (spectral-norm u, v and
+    BatchNorm statistics included) identical on both ranks afterwards; the gradient hook averages exactly the
+    networks ``update()`` names (T, G, R in the generator step, D in the discriminator step)."""
+    script = tmp_path / "w.py"
+    script.write_text(_WORKER_ATTACH)
+    port = str(29950 + random.randint(0, 40))
+    procs = [subprocess.Popen([sys.executable, str(script), ROOT, port, str(r)], stdout=subprocess.PIPE,
+                              stderr=subprocess.STDOUT) for r in range(2)]
+    outs = [p.communicate(timeout=300)[0].decode() for p in procs]
+    assert all(p.returncode == 0 for p in procs), outs
