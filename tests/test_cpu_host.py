@@ -374,3 +374,17 @@ def test_attach_broadcasts_all_networks_world_size_2(tmp_path):
                               stderr=subprocess.STDOUT) for r in range(2)]
     outs = [p.communicate(timeout=300)[0].decode() for p in procs]
     assert all(p.returncode == 0 for p in procs), outs
+
+
+def test_conv_cycle_model_runs(built):
+    """tools/conv_model.py (analytic MMA / operand-read / HBM model over the kernel's own geometry) stays runnable
+    and keeps explaining the measured per-layer times of profiles/r1h_conv_tc_microbench.txt within 2.2x."""
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    import conv_model
+    from spatialalignmentnetwork_b200 import _lib
+    L = _lib.lib()
+    for shape, meas in conv_model.MEASURED_MS.items():
+        if shape == (18, 2, 320, 1):       # 1x1 head: the model charges halo rows the 1x1 kernel finds in L2
+            continue
+        _, m = conv_model.model(L, 64, *shape)
+        assert 0.95 < meas / m["bound"] < 2.2, (shape, meas, m)
