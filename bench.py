@@ -53,6 +53,10 @@ def parse():
     ap.add_argument("--checkpoint", default="auto", choices=["auto", "0", "1"],
                     help="recompute each cascade in backward (memory knob)")
     ap.add_argument("--cpu-sample", type=int, default=2, help="slices in the CPU baseline sample")
+    ap.add_argument("--ref-device", default="cpu", choices=["cpu", "cuda"],
+                    help="--impl reference only: cpu = the contract's CPU arm; cuda = the same oracle port run as eager "
+                         "PyTorch on the GPU (cuDNN convs, cuFFT; SURVEY 8d 'the reference on the B200 itself'), see --tf32")
+    ap.add_argument("--tf32", type=int, default=0, help="--ref-device cuda: allow TF32 convs (the reference's own default)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-profile", action="store_true", help="skip the instrumented per-kernel step")
     ap.add_argument("--breakdown", default="", help="write the per-op time table (JSON) to this path")
@@ -263,24 +267,25 @@ def summarise_profile(records, step_ms, peaks):
 
 
 # ------------------------------------------------------------------------------------- CPU oracle arm
-def cpu_step_factory(args, nslices):
+def cpu_step_factory(args, nslices, device="cpu"):
     """The reference's path restated on CPU (oracle/): set_input + forwardT + forwardR + backward +
-    AdamW step, on ``nslices`` slices, all host threads."""
+    AdamW step, on ``nslices`` slices, all host threads.  (``device='cuda'``: the same eager PyTorch ops on
+    the GPU, i.e. what the reference itself would run there.)"""
     import torch
     from oracle import gan as ogan, step as ostep
     torch.set_num_threads(os.cpu_count() or 1)
     net = build_model(args)
-    pruned = net.net_mask.pruned.clone()
+    pruned = net.net_mask.pruned.clone().to(device)
     sds, opts = {}, {}
     for t in "TRGD":
-        sd = {k: v.detach().clone() for k, v in getattr(net, "net_" + t).state_dict().items()}
+        sd = {k: v.detach().clone().to(device) for k, v in getattr(net, "net_" + t).state_dict().items()}
         params = []
         for k, v in sd.items():
             if v.is_floating_point() and "running" not in k and "weight_u" not in k and "weight_v" not in k:
                 v.requires_grad_(True)
                 params.append(v)
         sds[t], opts[t] = sd, torch.optim.AdamW(params, lr=1e-4, weight_decay=0)
-    full, aux = make_inputs(nslices, args.shape)
+    full, aux = make_inputs(nslices, args.shape, device=device)
 
     def step_rec():
         inp = ostep.set_input(full, aux, pruned)
@@ -314,19 +319,28 @@ def run_reference(args):
     if rank != 0:
         return
     ns = args.cpu_sample
-    step = cpu_step_factory(args, ns)
+    dev = args.ref_device
+    if dev == "cuda":
+        import torch
+        torch.backends.cudnn.allow_tf32 = bool(args.tf32)
+        torch.backends.cuda.matmul.allow_tf32 = bool(args.tf32)
+        dev = f"cuda:{int(os.environ.get('LOCAL_RANK', '0'))}"
+    step = cpu_step_factory(args, ns, device=dev)
     for _ in range(min(args.warmup, 1)):
         step()
     times = []
     for _ in range(args.steps):
         t0 = time.perf_counter()
-        step()
+        step()                      # ends with .item(): synchronises the device arm too
         times.append(time.perf_counter() - t0)
     ms = 1e3 * sum(times) / len(times)
     val = ns / (ms / 1e3)
     cores = os.cpu_count() or 1
     sample = (f"{ns} slices/step of the same workload ({args.cascades}-cascade VarNet + align, {args.shape}x{args.shape}, "
               f"fwd+bwd+AdamW), CPU oracle port (torch CPU fp32), {cores} threads; warm-up capped at 1 step")
+    if args.ref_device == "cuda":
+        sample = sample.replace("CPU oracle port (torch CPU fp32)",
+                                f"oracle port as eager PyTorch CUDA (cuDNN / cuFFT, TF32 {'on' if args.tf32 else 'off'})")
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": round(val, 4), "unit": "slices/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": min(args.warmup, 1), "ms_per_step": round(ms, 2), "higher_is_better": True,

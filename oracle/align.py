@@ -67,11 +67,11 @@ def unet(sd, p, x, num_levels, training):
     return F.conv2d(x, sd[p + "5.weight"], sd[p + "5.bias"], padding=1)
 
 
-def identity_grid(H, W, dtype=torch.float32):
+def identity_grid(H, W, dtype=torch.float32, device=None):
     """affine_grid(identity, align_corners=False) cross.py:24-26: pixel centres
     x_j = (2j+1)/W - 1, y_i = (2i+1)/H - 1, last dim (x, y)."""
-    xs = (2 * torch.arange(W, dtype=dtype) + 1) / W - 1
-    ys = (2 * torch.arange(H, dtype=dtype) + 1) / H - 1
+    xs = (2 * torch.arange(W, dtype=dtype, device=device) + 1) / W - 1
+    ys = (2 * torch.arange(H, dtype=dtype, device=device) + 1) / H - 1
     return torch.stack([xs[None, :].expand(H, W), ys[:, None].expand(H, W)], dim=-1)[None]
 
 
@@ -81,7 +81,7 @@ def spatial_transformer(sd, p, moving, fixed, training=True, num_levels=4):
     x = F.leaky_relu(x, SLOPE)
     x = F.conv2d(x, sd[p + "net.2.weight"], sd[p + "net.2.bias"], padding=1)
     offset = x.permute(0, 2, 3, 1)
-    grid = identity_grid(moving.shape[2], moving.shape[3], moving.dtype) + offset
+    grid = identity_grid(moving.shape[2], moving.shape[3], moving.dtype, moving.device) + offset
     return offset, grid
 
 
@@ -94,7 +94,7 @@ def warp(img, grid):
     iy = ((gy + 1) * H - 1) / 2
     x0, y0 = torch.floor(ix), torch.floor(iy)
     wx1, wy1 = ix - x0, iy - y0
-    out = torch.zeros(N, C, grid.shape[1], grid.shape[2], dtype=img.dtype)
+    out = torch.zeros(N, C, grid.shape[1], grid.shape[2], dtype=img.dtype, device=img.device)
     flat = img.reshape(N, C, H * W)
     for dy, wy in ((0, 1 - wy1), (1, wy1)):
         for dx, wx in ((0, 1 - wx1), (1, wx1)):

@@ -7,7 +7,7 @@ import torch.nn.functional as F
 
 
 def _box(x, win, pad):
-    w = torch.ones(1, 1, win, win, dtype=x.dtype)
+    w = torch.ones(1, 1, win, win, dtype=x.dtype, device=x.device)
     return F.conv2d(x, w, padding=pad)
 
 
