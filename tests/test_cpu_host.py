@@ -388,3 +388,22 @@ def test_conv_cycle_model_runs(built):
             continue
         _, m = conv_model.model(L, 64, *shape)
         assert 0.95 < meas / m["bound"] < 2.2, (shape, meas, m)
+
+
+def test_fft_v2_kernels_under_host_emulation(tmp_path):
+    """The opt-in v2 FFT kernels (csrc/fft_v2.cuh, SAN_FFT_V2=1), compiled from the SAME source for the host with one
+    OS thread per CUDA thread and a barrier for __syncthreads(): every fused load / store variant (plain, ACS column
+    mask, planar, sens expand + soft DC, coil-reducing stores with 1 and 2 coils, a ragged column CTA), forward and
+    inverse, against a direct fp64 2-D DFT at 320x320."""
+    import shutil
+    import subprocess
+    cxx = shutil.which("g++")
+    assert cxx, "g++ not found"
+    exe = str(tmp_path / "fft_v2_emul")
+    src = os.path.join(ROOT, "tests", "host", "fft_v2_emul.cpp")
+    b = subprocess.run([cxx, "-std=c++17", "-O2", "-pthread", "-I/usr/local/cuda/include", "-DSAN_FFT_EMULATE", "-o", exe, src],
+                       capture_output=True, text=True, timeout=300)
+    assert b.returncode == 0, b.stderr[-2000:]
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "worst relative error" in r.stdout
