@@ -407,3 +407,35 @@ def test_fft_v2_kernels_under_host_emulation(tmp_path):
     r = subprocess.run([exe], capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout + r.stderr
     assert "worst relative error" in r.stdout
+
+
+def test_abi_argument_validation_without_gpu(built):
+    """Error behaviour of the C ABI (reference: bare asserts in Python; here return codes + san_last_error): bad
+    arguments are rejected before any CUDA call, so this runs without a GPU."""
+    from spatialalignmentnetwork_b200 import _lib
+    L = _lib.lib()
+    ARG, UNSUP = -1, -3
+    p = 0x1000      # a non-null "device pointer" that is never dereferenced: validation fails first
+    cases = [
+        (L.san_fft2(None, 0, None, p, 0, None, p, 1, 8, 8, 0, None), "null"),
+        (L.san_fft2(p, 1, p, p, 0, None, p, 1, 8, 8, 0, None), "column mask"),
+        (L.san_fft_expand_dc(p, p, p, None, None, None, p, p, 1, 1, 8, 8, 0, None), "k0"),
+        (L.san_pair_loss_fwd(p, None, 16, 0, 1.0, p, p, None), "bad args"),          # L1 without y
+        (L.san_pair_loss_fwd(p, p, 16, 3, 1.0, p, p, None), "bad args"),             # unknown mode
+        (L.san_mi_metric(p, p, 1, 64, 65, 0.0, 1.0, p, None), "bins"),
+        (L.san_mi_metric(p, p, 1, 64, 64, 1.0, 1.0, p, None), "maxv"),
+        (L.san_warp_reflect(p, p, p, 1, 1, 8, 8, 8, 8, 3, None), "bad args"),
+        (L.san_filter2d(p, p, p, 1, 8, 8, 4, None), "bad args"),                     # even window
+        (L.san_sn_sigma(p, p, p, p, p, 0, 4, 1e-12, 1, None), "bad args"),
+        (L.san_adamw_step(p, p, p, p, p, 1, 1e-4, 0.9, 0.999, 1e-8, 0.0, 0, None), "bad args"),     # step counts from 1
+        (L.san_tc_conv(p, p, None, p, 1, 8, 8, 4, 4, 5, 0, None), "unsupported shape"),  # 5x5 filter
+        (L.san_tc_stage_terms(p, 1, 8, 8, 16, p, 7, None), "bad args"),              # more than 6 terms
+    ]
+    for rc, msg in cases:
+        assert rc == ARG, (rc, msg)
+    import ctypes
+    out = (ctypes.c_int * 16)()
+    assert L.san_tc_describe(8, 8, 4, 4, 5, ctypes.addressof(out)) == UNSUP
+    assert L.san_tc_wgrad_describe(8, 8, 4, 4, 3, ctypes.addressof(out)) == UNSUP       # image narrower than 16 pixels
+    # the message of the LAST failure on this thread
+    assert L.san_mi_metric(p, p, 1, 64, 65, 0.0, 1.0, p, None) == ARG and b"bins" in L.san_last_error()
