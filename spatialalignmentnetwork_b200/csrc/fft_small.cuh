@@ -129,11 +129,16 @@ template <> FS_HD void dft<true, 16>(float2 (&v)[16]) { dft16<true>(v); }
 template <> FS_HD void dft<false, 20>(float2 (&v)[20]) { dft20<false>(v); }
 template <> FS_HD void dft<true, 20>(float2 (&v)[20]) { dft20<true>(v); }
 
-// shared-memory exchange layout of one line between the phases: element (k1, l) at k1 * (N2 + 1) + l
+// shared-memory exchange layout of one line between the phases: element (k1, l) at k1 * (N2 + 1) + l.
+// Bank behaviour (8-byte elements, 16 per wavefront half): the row pass walks l (phase 1) and k1 (phase 2, stride
+// LD = 21 = 5 mod 16, coprime) within a line; the column pass puts 8 adjacent columns = 8 LINES in consecutive
+// threads, so the line pitch SIZE must not be a multiple of 16 elements (336 would be an 8-way conflict): it is
+// padded to 2 mod 16, which makes the 16 threads of a half-warp (2 values of l or k1 x 8 lines) hit 16 distinct
+// bank pairs in both phases.
 template <int N1, int N2>
 struct Exchange {
   static constexpr int LD = N2 + 1;
-  static constexpr int SIZE = N1 * LD;
+  static constexpr int SIZE = N1 * LD + (18 - (N1 * LD) % 16) % 16;
   FS_HD static int at(int k1, int l) { return k1 * LD + l; }
 };
 
