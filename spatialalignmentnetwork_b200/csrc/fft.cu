@@ -323,10 +323,12 @@ __global__ void __launch_bounds__(256) fft_cols_kernel(const FftArgs a) {
   }
 }
 
-bool fft_v2_enabled() {
-  static const bool on = [] { const char* e = getenv("SAN_FFT_V2"); return e && atoi(e) != 0; }();
-  return on;
+// SAN_FFT_V2: 0 / unset = Stockham kernels; 1 = register FFT, 8 columns per column-pass CTA; 2 = 16 columns per CTA
+int fft_v2_mode() {
+  static const int mode = [] { const char* e = getenv("SAN_FFT_V2"); return e ? atoi(e) : 0; }();
+  return mode;
 }
+bool fft_v2_enabled() { return fft_v2_mode() != 0; }
 
 template <bool INV, int LOAD>
 int launch_rows(const FftArgs& a, cudaStream_t st) {
@@ -350,9 +352,15 @@ template <bool INV, int STORE>
 int launch_cols(const FftArgs& a, cudaStream_t st) {
   const bool reducing = (STORE == ST_REDUCE || STORE == ST_RSS);
   if (fft_v2_enabled() && a.H == V2_N) {
-    dim3 grid2(san_cdiv(a.W, V2_LINES), reducing ? a.B / a.C : a.B);
-    if (reducing && a.C > 1) fft_cols_v2_kernel<INV, STORE, true><<<grid2, V2_THREADS, 0, st>>>(a);
-    else fft_cols_v2_kernel<INV, STORE, false><<<grid2, V2_THREADS, 0, st>>>(a);
+    const int lines = fft_v2_mode() == 2 ? 16 : 8;
+    dim3 grid2(san_cdiv(a.W, lines), reducing ? a.B / a.C : a.B);
+    if (reducing && a.C > 1) {
+      if (lines == 16) fft_cols_v2_kernel<INV, STORE, true, 16><<<grid2, 16 * V2_N2, 0, st>>>(a);
+      else fft_cols_v2_kernel<INV, STORE, true, 8><<<grid2, 8 * V2_N2, 0, st>>>(a);
+    } else {
+      if (lines == 16) fft_cols_v2_kernel<INV, STORE, false, 16><<<grid2, 16 * V2_N2, 0, st>>>(a);
+      else fft_cols_v2_kernel<INV, STORE, false, 8><<<grid2, 8 * V2_N2, 0, st>>>(a);
+    }
     SAN_LAUNCH_CHECK();
     return SAN_OK;
   }

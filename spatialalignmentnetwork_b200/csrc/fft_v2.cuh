@@ -137,17 +137,18 @@ SAN_GLOBAL void SAN_LAUNCH_BOUNDS(V2_THREADS) fft_rows_v2_kernel(const FftArgs a
   }
 }
 
-// grid: (ceil(W / V2_LINES), G), G = N for the coil-reducing stores and B otherwise; H == 320, any W.
+// grid: (ceil(W / LINES), G), G = N for the coil-reducing stores and B otherwise; H == 320, any W; LINES * 20 threads.
+// LINES = adjacent columns per CTA: 8 (64 B global segments, 24 KB smem) or 16 (128 B segments, 45 KB smem).
 // MULTI: coil-reducing store with C > 1 (per-thread register accumulators across the coil loop).
-template <bool INV, int STORE, bool MULTI>
-SAN_GLOBAL void SAN_LAUNCH_BOUNDS(V2_THREADS) fft_cols_v2_kernel(const FftArgs a) {
-  SAN_SHARED float2 z[V2_LINES * V2Ex::SIZE];
+template <bool INV, int STORE, bool MULTI, int LINES>
+SAN_GLOBAL void SAN_LAUNCH_BOUNDS(LINES * V2_N2) fft_cols_v2_kernel(const FftArgs a) {
+  SAN_SHARED float2 z[LINES * V2Ex::SIZE];
   SAN_SHARED float2 tws[V2_N];
   load_twiddles(tws, a.twH, V2_N);
   constexpr int H = V2_N;
   const int W = a.W;
-  const int w0 = blockIdx.x * V2_LINES;
-  const int ncol = (W - w0) < V2_LINES ? (W - w0) : V2_LINES;
+  const int w0 = blockIdx.x * LINES;
+  const int ncol = (W - w0) < LINES ? (W - w0) : LINES;
   const long long HW = (long long)H * W;
   constexpr bool reducing = (STORE == ST_REDUCE || STORE == ST_RSS);
   const int ncoil = MULTI ? a.C : 1;
@@ -160,7 +161,7 @@ SAN_GLOBAL void SAN_LAUNCH_BOUNDS(V2_THREADS) fft_cols_v2_kernel(const FftArgs a
     const float2* src = a.tmp + b * HW;
     __syncthreads();                                 // twiddles visible / previous coil's phase 2 done with z
     {
-      const int l = threadIdx.x / V2_LINES, col = threadIdx.x - l * V2_LINES;
+      const int l = threadIdx.x / LINES, col = threadIdx.x - l * LINES;
       if (col < ncol) {
         float2 v[V2_N1];
 #pragma unroll
@@ -171,8 +172,8 @@ SAN_GLOBAL void SAN_LAUNCH_BOUNDS(V2_THREADS) fft_cols_v2_kernel(const FftArgs a
       }
     }
     __syncthreads();
-    if (threadIdx.x < V2_LINES * V2_N1) {
-      const int k1 = threadIdx.x / V2_LINES, col = threadIdx.x - k1 * V2_LINES;
+    if (threadIdx.x < LINES * V2_N1) {
+      const int k1 = threadIdx.x / LINES, col = threadIdx.x - k1 * LINES;
       if (col < ncol) {
         float2 v[V2_N2];
 #pragma unroll

@@ -103,16 +103,17 @@ struct Case {
     a.dcmask = dcmask.data(); a.dcw = &dcw; a.B = (int)B; a.C = C; a.H = H; a.W = W;
     a.scale = (float)(1.0 / sqrt((double)H * W)); a.twW = twW.data(); a.twH = twH.data();
   }
-  template <int LOAD, int STORE, bool MULTI>
+  // LINES: columns per column-pass CTA (8 or 16), alternated between the cases below
+  template <int LOAD, int STORE, bool MULTI, int LINES = 8>
   void run() {
     const bool reducing = (STORE == ST_REDUCE || STORE == ST_RSS);
     const int nrows = a.B * H;
     if (inv) {
       launch(fft_rows_v2_kernel<true, LOAD>, (nrows + V2_LINES - 1) / V2_LINES, 1, V2_THREADS, a);
-      launch(fft_cols_v2_kernel<true, STORE, MULTI>, (W + V2_LINES - 1) / V2_LINES, reducing ? a.B / C : a.B, V2_THREADS, a);
+      launch(fft_cols_v2_kernel<true, STORE, MULTI, LINES>, (W + LINES - 1) / LINES, reducing ? a.B / C : a.B, LINES * V2_N2, a);
     } else {
       launch(fft_rows_v2_kernel<false, LOAD>, (nrows + V2_LINES - 1) / V2_LINES, 1, V2_THREADS, a);
-      launch(fft_cols_v2_kernel<false, STORE, MULTI>, (W + V2_LINES - 1) / V2_LINES, reducing ? a.B / C : a.B, V2_THREADS, a);
+      launch(fft_cols_v2_kernel<false, STORE, MULTI, LINES>, (W + LINES - 1) / LINES, reducing ? a.B / C : a.B, LINES * V2_N2, a);
     }
   }
   // reference transform of slice b of the loaded input (LOAD semantics), ortho-scaled times `extra`
@@ -153,7 +154,7 @@ int main() {
   }
   {  // planar(ifft2(colmask * k)) and its adjoint (varnet.py:395-407)
     Case c(2, 1, H, W, true);
-    c.run<LD_C64_COLMASK, ST_PLANAR, false>();
+    c.run<LD_C64_COLMASK, ST_PLANAR, false, 16>();
     double e = 0;
     const size_t P = (size_t)H * W;
     for (int b = 0; b < 2; ++b) {
@@ -174,7 +175,7 @@ int main() {
   }
   {  // sens_expand + soft DC (varnet.py:508-509,525-530), 2 coils
     Case c(1, 2, H, W, false);
-    c.run<LD_PLANAR_S, ST_DC, false>();
+    c.run<LD_PLANAR_S, ST_DC, false, 16>();
     double e = 0;
     const size_t P = (size_t)H * W;
     for (int b = 0; b < 2; ++b) {
@@ -189,7 +190,7 @@ int main() {
   }
   for (int C = 1; C <= 2; ++C) {  // sens_reduce (varnet.py:511-512) and rss(ifft2(k)) (varnet.py:486)
     Case c(1, C, H, W, true);
-    if (C == 1) c.run<LD_C64, ST_REDUCE, false>(); else c.run<LD_C64, ST_REDUCE, true>();
+    if (C == 1) c.run<LD_C64, ST_REDUCE, false, 16>(); else c.run<LD_C64, ST_REDUCE, true, 16>();
     const size_t P = (size_t)H * W;
     std::vector<cd> acc(P, cd(0, 0));
     double e = 0, eu = 0;
@@ -232,12 +233,21 @@ int main() {
         }
       refs.push_back(dft2(x, H, Wn, false));
     }
-    launch(fft_cols_v2_kernel<false, ST_C64, false>, (Wn + V2_LINES - 1) / V2_LINES, 2, V2_THREADS, c.a);
+    launch(fft_cols_v2_kernel<false, ST_C64, false, 8>, (Wn + 7) / 8, 2, 8 * V2_N2, c.a);
+    {
+      double e8 = 0;
+      for (int b = 0; b < 2; ++b)
+        for (size_t i = 0; i < P; ++i)
+          e8 = fmax(e8, std::abs(refs[b][i] * (double)c.a.scale - cd(c.out_c[b * P + i].x, c.out_c[b * P + i].y)));
+      track("column pass, W = 20, 8 per CTA", e8, 0.5);
+      for (auto& v : c.out_c) v = make_float2(0.f, 0.f);
+    }
+    launch(fft_cols_v2_kernel<false, ST_C64, false, 16>, (Wn + 15) / 16, 2, 16 * V2_N2, c.a);
     double e = 0;
     for (int b = 0; b < 2; ++b)
       for (size_t i = 0; i < P; ++i)
         e = fmax(e, std::abs(refs[b][i] * (double)c.a.scale - cd(c.out_c[b * P + i].x, c.out_c[b * P + i].y)));
-    track("column pass, W = 20 (ragged CTA)", e, 0.5);
+    track("column pass, W = 20, 16 per CTA", e, 0.5);
   }
   printf("worst relative error %.3e\n", g_worst);
   return g_worst < 2e-5 ? 0 : 1;

@@ -9,7 +9,7 @@ mkdir -p gpurun_out
 SAN_FFT_V2=1 timeout 200 python -m pytest tests/test_gpu_ops.py tests/test_gpu_models.py -m gpu -q --tb=short -p no:cacheprovider \
     -k "fft or dc or rss or varnet or rec_step" > gpurun_out/ab_v2_tests.log 2>&1
 tail -3 gpurun_out/ab_v2_tests.log
-for v in 0 1; do
+for v in 0 1 2; do   # 0 = Stockham, 1 = register FFT with 8 columns per CTA, 2 = with 16
   SAN_FFT_V2=$v python tools/bench_fft.py 64 20 > gpurun_out/ab_fft_v$v.txt 2>&1
   echo "--- SAN_FFT_V2=$v"; cat gpurun_out/ab_fft_v$v.txt
   SAN_FFT_V2=$v python bench.py --steps 3 --warmup 3 --no-cpu-baseline > gpurun_out/ab_bench_v$v.json 2> gpurun_out/ab_bench_v$v.err
