@@ -22,7 +22,7 @@ def main(args):
     for b0 in range(0, n, args.batch_size):
         net.set_input(full[b0:b0 + args.batch_size], aux[b0:b0 + args.batch_size])
         net.test()
-        rows.append({k: getattr(net, k) for k in ("metric_PSNR", "metric_SSIM", "metric_MAE", "metric_MSE")})
+        rows.append({k: getattr(net, k) for k in ("metric_PSNR", "metric_SSIM", "metric_MAE", "metric_MSE", "metric_MI")})
     mean = {k: sum(r[k] for r in rows) / len(rows) for k in rows[0]}
     print(json.dumps(mean))
     if args.save:
