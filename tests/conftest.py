@@ -86,15 +86,19 @@ def kink_tolerant_failures(ours, ref, bar, floor_frac=1e-3):
     that fail the per-tensor criterion of ``assert_grads_kink_tolerant``)."""
     names = [k for k in ref if k in ours and ours[k] is not None]
     assert names, "no gradients to compare"
-    cat = lambda d: torch.cat([torch.as_tensor(d[k]).detach().cpu().double().flatten() for k in names])
+    def flat(t):
+        t = torch.as_tensor(t).detach().cpu()
+        return (torch.view_as_real(t.to(torch.complex128)) if torch.is_complex(t) else t.double()).flatten()
+
+    cat = lambda d: torch.cat([flat(d[k]) for k in names])
     glob = rel_l2(cat(ours), cat(ref))
-    fl = floor_frac * max(torch.as_tensor(ref[k]).double().norm().item() for k in names)
+    fl = floor_frac * max(flat(ref[k]).norm().item() for k in names)
     bad = []
     for k in names:
         e = rel_l2(ours[k], ref[k], fl)
         if e < 4 * bar:
             continue
-        na, nb = torch.as_tensor(ours[k]).double().norm().item(), torch.as_tensor(ref[k]).double().norm().item()
+        na, nb = flat(ours[k]).norm().item(), flat(ref[k]).norm().item()
         c = cosine(ours[k], ref[k])
         if not (c > 0.98 and 0.75 < na / max(nb, 1e-30) < 1.3333):
             bad.append((k, e, c, na / max(nb, 1e-30)))

@@ -1,9 +1,9 @@
-"""CPU stand-ins for the C-ABI ops the fused network walkers call (test infrastructure).
+"""CPU stand-ins for the C-ABI ops the host modules call (test infrastructure).
 
-``tests/test_cpu_gan_host.py`` monkeypatches them into ``spatialalignmentnetwork_b200.{tc, ops}`` so that the
-HOST logic of the walkers (which tensors are concatenated / summed, which BatchNorm slice normalises which
-source, weight re-orderings, buffer updates) can be checked against the reference's golden vectors without a
-GPU.  Each stand-in states the documented semantics of the op it replaces (include/san_b200.h,
+``tests/test_cpu_gan_host.py`` / ``tests/test_cpu_path_host.py`` monkeypatch them into
+``spatialalignmentnetwork_b200.{tc, ops, varnet, cross}`` so that the HOST logic (which tensors are concatenated /
+summed, which BatchNorm slice normalises which source, weight re-orderings, padding, hoisting, buffer updates, the
+order of the steps of ``CSModel``) can be checked against the reference's golden vectors without a GPU.  Each stand-in states the documented semantics of the op it replaces (include/san_b200.h,
 spatialalignmentnetwork_b200/tc.py) with plain torch CPU calls; none of this is reachable from the package."""
 import torch
 import torch.nn.functional as F
@@ -51,6 +51,15 @@ class _Apply:
         self.apply = fn
 
 
+class Raw:
+    """Stand-in for ``tc.Raw`` (same fields; any floating dtype, so the walkers can also be run in fp64 for an
+    exact graph comparison with the oracle)."""
+
+    def __init__(self, y, norm=None, slope=1.0, d2s=False, bn=None, up=False):
+        assert y.dim() == 4 and (norm == "bn") == (bn is not None)
+        self.y, self.norm, self.slope, self.d2s, self.bn, self.up = y, norm, float(slope), bool(d2s), bn, bool(up)
+
+
 def _bn_lrelu(y, gamma, beta, rm, rv, training, momentum, eps, slope):
     return F.leaky_relu(F.batch_norm(y, rm, rv, gamma, beta, training, momentum, eps), slope)
 
@@ -73,13 +82,116 @@ def _pair_loss(x, y, mode, sign):
     return (sign * x).mean()
 
 
+# ---- FFT / data consistency / sensitivity maps (include/san_b200.h, "FFT / data consistency") ----------------
+def _planar(c):            # complex [N,1,H,W] -> planar [N,2,H,W]
+    return torch.cat([c.real, c.imag], dim=1)
+
+
+def _cplx(p):              # planar [N,2,H,W] -> complex [N,1,H,W]
+    return torch.complex(p[:, :1], p[:, 1:])
+
+
+def _fft2(x, inverse):
+    return (torch.fft.ifft2 if inverse else torch.fft.fft2)(x, norm="ortho")
+
+
+def _ifft_masked_planar(k, colmask):
+    N, C, H, W = k.shape
+    img = torch.fft.ifft2(k * colmask.to(k.real.dtype), norm="ortho").reshape(N * C, 1, H, W)
+    return _planar(img)
+
+
+def _fft_reduce(k, sens):
+    return _planar((torch.fft.ifft2(k, norm="ortho") * sens.conj()).sum(dim=1, keepdim=True))
+
+
+def _fft_expand_dc(x, sens, k, k0, mask, dc_weight):
+    zero = torch.zeros(1, 1, 1, 1, dtype=k.dtype)
+    return k - torch.where(mask, k - k0, zero) * dc_weight - torch.fft.fft2(_cplx(x) * sens, norm="ortho")
+
+
+def _expand(xp, sens):
+    return torch.fft.fft2(_cplx(xp) * sens, norm="ortho")
+
+
+def _fft_rss(k):
+    return torch.linalg.vector_norm(torch.fft.ifft2(k, norm="ortho"), 2, dim=1, keepdim=True)
+
+
+def _rss(x):
+    return torch.linalg.vector_norm(x, 2, dim=1, keepdim=True)
+
+
+def _sens_normalize(s, N, C):
+    _, _, H, W = s.shape
+    c = _cplx(s).reshape(N, C, H, W)
+    return c / (_rss(c) + 1e-6)
+
+
+# ---- layer-wise norm / resampling ops ---------------------------------------------------------------------------
+def _plane_stats(x):
+    N, C, H, W = x.shape
+    mean = x.mean(dim=(2, 3))
+    # d m2 / dx = 2 (x - mean) exactly (ops.PlaneStats.backward): centring on the detached mean drops the term
+    # -2 sum(x - mean) / P, zero in exact arithmetic but rounding noise in fp32
+    return mean, ((x - mean.detach()[:, :, None, None]) ** 2).sum(dim=(2, 3))
+
+
+def _plane_affine(x, mu, a, b):
+    N, C = x.shape[:2]
+    v = x if mu is None else x - mu.reshape(N, C, 1, 1)
+    v = v * a.reshape(N, C, 1, 1)
+    return v if b is None else v + b.reshape(N, C, 1, 1)
+
+
+def _in_lrelu(y, slope, eps):
+    return F.leaky_relu(F.instance_norm(y, eps=eps), slope)
+
+
+# ---- alignment / losses ---------------------------------------------------------------------------------------------
+def _grid_from_offset(x):
+    N, _, H, W = x.shape
+    theta = torch.eye(2, 3, dtype=x.dtype)[None].expand(N, 2, 3)
+    return F.affine_grid(theta, (N, 1, H, W), align_corners=False) + x.permute(0, 2, 3, 1)
+
+
+def _warp(img, grid):
+    return F.grid_sample(img, grid, mode="bilinear", padding_mode="zeros", align_corners=False)
+
+
+def _gradient_loss(s):
+    dx = s[:, :, 1:, :] - s[:, :, :-1, :]
+    dy = s[:, 1:, :, :] - s[:, :-1, :, :]
+    return ((dx * dx).mean() + (dy * dy).mean()) / 2.0
+
+
 def install(monkeypatch):
-    """Route the walkers' op calls to the stand-ins above."""
-    from spatialalignmentnetwork_b200 import ops, tc
+    """Route the op calls of the host modules to the stand-ins above."""
+    from oracle import losses as ol
+    from spatialalignmentnetwork_b200 import cross, ops, tc, varnet
     monkeypatch.setattr(tc, "fused_conv", fused_conv)
+    monkeypatch.setattr(tc, "Raw", Raw)
     monkeypatch.setattr(ops, "add", lambda a, b: a + b)
     monkeypatch.setattr(ops, "BatchNormLReLU", _Apply(_bn_lrelu))
     monkeypatch.setattr(ops, "SpaceToDepth2", _Apply(lambda x: F.pixel_unshuffle(x, 2)))
     monkeypatch.setattr(ops, "AvgPool2", _Apply(lambda x: F.avg_pool2d(x, 2)))
     monkeypatch.setattr(ops, "SpectralNormWeight", _Apply(_sn_weight))
     monkeypatch.setattr(ops, "PairLoss", _Apply(_pair_loss))
+    monkeypatch.setattr(ops, "l1_loss", lambda x, y: (x - y).abs().mean())
+    monkeypatch.setattr(ops, "Fft2", _Apply(_fft2))
+    monkeypatch.setattr(ops, "IfftMaskedPlanar", _Apply(_ifft_masked_planar))
+    monkeypatch.setattr(ops, "FftReduce", _Apply(_fft_reduce))
+    monkeypatch.setattr(ops, "FftExpandDC", _Apply(_fft_expand_dc))
+    monkeypatch.setattr(ops, "FftRss", _Apply(_fft_rss))
+    monkeypatch.setattr(ops, "Rss", _Apply(_rss))
+    monkeypatch.setattr(ops, "SensNormalize", _Apply(_sens_normalize))
+    monkeypatch.setattr(ops, "PlaneStats", _Apply(_plane_stats))
+    monkeypatch.setattr(ops, "PlaneAffine", _Apply(_plane_affine))
+    monkeypatch.setattr(ops, "InstanceNormLReLU", _Apply(_in_lrelu))
+    monkeypatch.setattr(ops, "GridFromOffset", _Apply(_grid_from_offset))
+    monkeypatch.setattr(ops, "Warp", _Apply(_warp))
+    monkeypatch.setattr(ops, "GradientLoss", _Apply(_gradient_loss))
+    monkeypatch.setattr(ops, "SsimLoss", _Apply(ol.ssimloss))
+    monkeypatch.setattr(ops, "LnccLoss", _Apply(ol.lncc_loss))
+    monkeypatch.setattr(varnet, "_Expand", _Apply(_expand))
+    monkeypatch.setattr(cross, "_LReLUFn", _Apply(lambda x, slope: F.leaky_relu(x, slope)))
