@@ -145,3 +145,45 @@ def test_mixed_step_host_logic(monkeypatch):
         assert abs(getattr(net, k).item() - g[k].item()) < 2e-4 * max(1e-3, abs(g[k].item())), k
     net.loss_all.backward()
     assert_grads_kink_tolerant({k: p.grad for k, p in net.net_D.named_parameters()}, sub(g, "gD."), 6e-2, "gD.")
+
+
+def test_optional_registration_terms_wiring(monkeypatch):
+    """weight_lncc / weight_mi (BASELINE configs 3 / 5): the terms enter loss_all, appear in get_vis and survive a
+    full update() - the host side of tests/test_gpu_models.py::test_optional_registration_terms."""
+    from oracle import losses as ol
+    from spatialalignmentnetwork_b200 import model as M, unet as U, varnet as V
+    emulation.install(monkeypatch)
+    monkeypatch.setattr(V, "USE_TC", True)
+    monkeypatch.setattr(U, "USE_TC", True)
+    monkeypatch.setattr(M, "ms_mi_loss", ol.ms_mi_loss)
+    monkeypatch.setattr(M, "lncc_loss", ol.lncc_loss)
+    torch.manual_seed(5)
+    random.seed(5)
+    cfg = M.Config(sparsity=0.25, lr=1e-4, shape=64, coils=1, reg="Rec", mask="standard", weight_smooth=1000.0,
+                   weight_sim=1.0, weight_gan=0.1, weight_gan_sim=1.0, num_cascades=1, weight_lncc=1.0, weight_mi=0.5,
+                   gan_layers_G=[8, 16], gan_layers_D=[[8, 8]], fused_adamw=False)
+    net = M.CSModel(cfg)
+    with torch.no_grad():
+        torch.nn.init.normal_(net.net_T.net[-1].weight, 0, 1e-2)
+    net.train()
+    full, aux = (torch.rand(2, 1, 64, 64) + 0j).to(torch.complex64), (torch.rand(2, 1, 64, 64) + 0j).to(torch.complex64)
+    net.set_input(full, aux)
+    net.loss_all = 0
+    net.forwardT()
+    expect = (net.loss_smooth * 1000.0 + ol.lncc_loss(net.img_full_rss, net.img_warped_rss) * 1.0 +
+              ol.ms_mi_loss(net.img_full_rss, net.img_warped_rss) * 0.5).item()
+    assert abs(net.loss_all.item() - expect) < 1e-5 * abs(expect)
+    before = net.net_T.net[-1].weight.detach().clone()
+    net.set_input(full, aux)
+    net.update()
+    assert not torch.equal(before, net.net_T.net[-1].weight.detach())
+    assert {"loss_lncc", "loss_mi", "loss_smooth", "loss_sim"} <= set(net.get_vis("scalars")["scalars"])
+    # absent weights -> absent terms (the reference's live path)
+    cfg2 = M.Config(sparsity=0.25, lr=1e-4, shape=64, coils=1, reg="Rec", mask="standard", weight_smooth=1000.0,
+                    weight_sim=1.0, num_cascades=1, gan_layers_G=[8, 16], gan_layers_D=[[8, 8]], fused_adamw=False)
+    net2 = M.CSModel(cfg2)
+    net2.train()
+    net2.set_input(full, aux)
+    net2.loss_all = 0
+    net2.forwardT()
+    assert not hasattr(net2, "loss_lncc") and not hasattr(net2, "loss_mi")
