@@ -165,9 +165,14 @@ def _gradient_loss(s):
     return ((dx * dx).mean() + (dy * dy).mean()) / 2.0
 
 
+def _error_sums(a, b):
+    d = a.double() - b.double()
+    return (d * d).sum().item(), d.abs().sum().item(), (a.double() ** 2).sum().item()
+
+
 def install(monkeypatch):
     """Route the op calls of the host modules to the stand-ins above."""
-    from oracle import losses as ol
+    from oracle import gan as og, losses as ol
     from spatialalignmentnetwork_b200 import cross, ops, tc, varnet
     monkeypatch.setattr(tc, "fused_conv", fused_conv)
     monkeypatch.setattr(tc, "Raw", Raw)
@@ -193,5 +198,7 @@ def install(monkeypatch):
     monkeypatch.setattr(ops, "GradientLoss", _Apply(_gradient_loss))
     monkeypatch.setattr(ops, "SsimLoss", _Apply(ol.ssimloss))
     monkeypatch.setattr(ops, "LnccLoss", _Apply(ol.lncc_loss))
+    monkeypatch.setattr(ops, "error_sums", _error_sums)
+    monkeypatch.setattr(ops, "mi_metric", lambda gt, pred, bins=64, minVal=0.0, maxVal=1.0: og.metric_mi(gt, pred, bins, minVal, maxVal))
     monkeypatch.setattr(varnet, "_Expand", _Apply(_expand))
     monkeypatch.setattr(cross, "_LReLUFn", _Apply(lambda x, slope: F.leaky_relu(x, slope)))

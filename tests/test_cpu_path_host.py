@@ -187,3 +187,37 @@ def test_optional_registration_terms_wiring(monkeypatch):
     net2.loss_all = 0
     net2.forwardT()
     assert not hasattr(net2, "loss_lncc") and not hasattr(net2, "loss_mi")
+
+
+@pytest.mark.parametrize("reg", ["Rec", "GAN-Only"])
+def test_test_method_metrics_and_return_value(monkeypatch, reg):
+    """CSModel.test() (model.py:265-286): runs forwardT / forwardG / forwardR in eval mode, fills the five metrics
+    and returns -PSNR (-MI for GAN-Only); odd batches are rejected like in the reference (chunk of the batch)."""
+    import math
+    from oracle import gan as og
+    from spatialalignmentnetwork_b200 import model as M, unet as U, varnet as V
+    emulation.install(monkeypatch)
+    monkeypatch.setattr(V, "USE_TC", True)
+    monkeypatch.setattr(U, "USE_TC", True)
+    torch.manual_seed(6)
+    random.seed(6)
+    cfg = M.Config(sparsity=0.25, lr=1e-4, shape=32, coils=1, reg=reg, mask="equispaced", weight_smooth=1000.0,
+                   weight_sim=1.0, weight_gan=0.1, weight_gan_sim=1.0, num_cascades=1, gan_layers_G=[4, 8],
+                   gan_layers_D=[[4, 4]], fused_adamw=False)
+    net = M.CSModel(cfg)
+    net.eval()
+    full = (torch.rand(4, 1, 32, 32) + 0j).to(torch.complex64)
+    aux = (torch.rand(4, 1, 32, 32) + 0j).to(torch.complex64)
+    net.set_input(full, aux)
+    r = net.test()
+    m = og.metric_sums(net.img_full_rss, net.img_rec)
+    assert abs(net.metric_MSE - m["mse"]) < 1e-12 and abs(net.metric_MAE - m["mae"]) < 1e-12
+    assert abs(net.metric_PSNR - 10 * math.log10(1 / m["mse"])) < 1e-9
+    assert abs(net.metric_MI - og.metric_mi(net.img_full_rss, net.img_warped_rss)) < 1e-12
+    assert abs(net.metric_SSIM - (1 - net.loss_sim.item())) < 1e-12
+    assert r == (-net.metric_MI if reg == "GAN-Only" else -net.metric_PSNR)
+    assert net.img_aligned.shape == net.img_full_rss.shape and net.img_synth.shape == net.img_full_rss.shape
+    assert not any(p.grad is not None for p in net.net_R.parameters())          # no_grad
+    vis = net.get_vis()
+    assert {"metric_PSNR", "metric_SSIM", "metric_MAE", "metric_MSE", "metric_MI"} <= set(vis["scalars"])
+    assert {"img_rec", "img_warped", "img_aligned", "img_synth"} <= set(vis["images"])
