@@ -8,6 +8,8 @@ reference train.py:198-253), same checkpoint directory format (basemodel.ckpt_sa
   * ``--train synthetic[:N]`` / ``--val synthetic[:N]`` generate seeded phantom slice pairs on the device instead
     of reading the fastMRI h5 volumes (h5py and the data are not available offline); csv paths are accepted only
     when ``h5py`` is importable;
+  * ``--use_amp`` is refused (fp32 parity path), ``--prefetch`` / ``--protocals`` are accepted and ignored for synthetic
+    data, ``--intel_stop`` keeps ``<logdir>/best.pt`` like the reference;
   * ``--gan_layers_G`` / ``--gan_layers_D`` (not in the reference) shrink the GAN
     networks for smoke runs.
 """
@@ -15,6 +17,7 @@ import argparse
 import json
 import os
 import random
+import shutil
 import time
 
 import torch
@@ -39,6 +42,7 @@ def synthetic_pairs(n, shape, coils, device, seed):
 
 
 def main(args):
+    assert not args.use_amp, "--use_amp: the san_b200 path computes in fp32 (BF16x3 tensor-core convs); no AMP mode"
     import torch.distributed as dist
     from spatialalignmentnetwork_b200 import parallel
     from spatialalignmentnetwork_b200.augment import augment_funcs, center_crop
@@ -78,6 +82,7 @@ def main(args):
     if rank == 0:
         os.makedirs(args.logdir, exist_ok=True)
     it, t0 = 0, time.time()
+    loss_best, iter_best = None, 0
     for epoch in range(args.epoch):
         net.train()
         perm = torch.randperm(n_train, generator=torch.Generator().manual_seed(epoch)).to(device)
@@ -96,14 +101,27 @@ def main(args):
             if rank == 0 and it % args.ckpt_every == 0:
                 net.save(os.path.join(args.logdir, f"ckpt_{it:010d}.pt"))
         net.eval()
-        vals = []
+        vals, stat_loss = [], []
         for b0 in range(0, n_val, max(1, args.batch_size // world)):
             net.set_input(full_v[b0:b0 + args.batch_size], aux_v[b0:b0 + args.batch_size])
-            net.test()
+            stat_loss.append(net.test())
             vals.append((net.metric_PSNR, net.metric_SSIM))
         if rank == 0:
             print(json.dumps({"epoch": epoch, "val_PSNR": sum(v[0] for v in vals) / len(vals),
                               "val_SSIM": sum(v[1] for v in vals) / len(vals)}), flush=True)
+        if args.intel_stop > 0:                             # early stopping of reference train.py:293-307
+            loss_current = sum(stat_loss) / len(stat_loss)
+            if loss_best is None or loss_current < loss_best:
+                loss_best, iter_best = loss_current, it
+                if rank == 0:
+                    best = os.path.join(args.logdir, "best.pt")
+                    if os.path.exists(best):
+                        shutil.rmtree(best)
+                    net.save(best)
+            elif it >= args.intel_stop + iter_best:
+                if rank == 0:
+                    print("signal_end set due to intel_stop", flush=True)
+                break
     if rank == 0:
         net.save(os.path.join(args.logdir, f"ckpt_{it:010d}_final.pt"))
     if world > 1:
@@ -132,6 +150,11 @@ if __name__ == "__main__":
     p.add_argument("--coils", type=int, default=1)
     p.add_argument("--aux_aug", type=str, default="None", choices=["None", "Rigid", "BSpline", "PBSpline"])
     p.add_argument("--force_gpu", action="store_true")
+    p.add_argument("--intel_stop", type=int, default=0, metavar="N",
+                   help="stop when the validation loss has not improved for N iterations; keeps <logdir>/best.pt")
+    p.add_argument("--protocals", type=str, default=None, nargs="*", help="input modalities (h5 datasets only; ignored for synthetic data)")
+    p.add_argument("--prefetch", action="store_true", help="accepted for CLI compatibility: synthetic data is already device-resident")
+    p.add_argument("--use_amp", action="store_true", help="not supported: the san_b200 path is the fp32 parity path")
     p.add_argument("--num_cascades", type=int, default=8)
     p.add_argument("--lncc_weight", type=float, default=0.0, help="extra registration term lncc_loss(full, warped) (BASELINE cfg3)")
     p.add_argument("--mi_weight", type=float, default=0.0, help="extra registration term ms_mi_loss(full, warped) (BASELINE cfg5)")
