@@ -73,6 +73,20 @@ def augment(img, rigid=True, bspline=True, grid=None):
     return sample(img, grid), grid
 
 
+def augment_aux(batch, factor=1):
+    """eval.py:15-27 of the reference: misalign the auxiliary modality by ``factor`` times a random rigid + b-spline
+    displacement (robustness evaluation); the identity grid comes from the same grid kernel."""
+    assert factor > 0
+    img_full, img_aux = batch
+    N, _, H, W = img_aux.shape
+    _, grid = augment(img_aux, rigid=True, bspline=True)
+    theta_id = np.tile(np.array([[[1.0, 0.0, 0.0], [0.0, 1.0, 0.0]]]), (N, 1, 1))
+    identity = _grid(theta_id, None, N, H, W, img_aux.device)
+    grid = identity + (grid - identity) * factor
+    img_aux, _ = augment(img_aux, rigid=False, bspline=False, grid=grid)
+    return (img_full, img_aux)
+
+
 # the four ``--aux_aug`` modes of train.py:35-59
 def augment_None(batch):
     return batch
