@@ -50,8 +50,8 @@ def bspline_grid(img):
 def sample(img, grid):
     """grid_sample(bilinear, reflection, align_corners=False); complex input: real and imaginary parts."""
     assert img.dim() == 4 and grid.dim() == 4 and grid.shape[-1] == 2 and grid.shape[0] == img.shape[0]
-    img = img.contiguous()
     k = 2 if torch.is_complex(img) else 1
+    img = (img.resolve_conj() if k == 2 else img).contiguous()      # (a lazy .conj() view cannot be viewed as real)
     assert img.dtype in (torch.float32, torch.complex64), img.dtype
     N, C, H, W = img.shape
     out = torch.empty(N, C, grid.shape[1], grid.shape[2], dtype=img.dtype, device=img.device)
