@@ -79,6 +79,8 @@ def _ptr(x, name, arg):
             raise RuntimeError(f"{name}: argument '{arg}' must be a CUDA tensor (no CPU fallback)")
         if not x.is_contiguous():
             raise RuntimeError(f"{name}: argument '{arg}' must be contiguous")
+        if x.is_conj() or x.is_neg():
+            raise RuntimeError(f"{name}: argument '{arg}' is a lazy conj / neg view; resolve it before the call")
         return x.data_ptr()
     return int(x)
 

@@ -14,6 +14,8 @@ from ._lib import call
 
 
 def _c(x):
+    if x.is_conj() or x.is_neg():       # lazy .conj() / negative-bit views share storage: the kernels read raw memory
+        x = x.resolve_conj().resolve_neg()
     return x if x.is_contiguous() else x.contiguous()
 
 

@@ -314,7 +314,7 @@ class _Expand(torch.autograd.Function):
     def backward(ctx, G):
         xp, sens = ctx.saved_tensors
         N, C, H, W = sens.shape
-        G = G.contiguous()
+        G = ops._c(G)
         dx = torch.empty_like(xp)
         u = torch.empty_like(sens)
         tmp = torch.empty_like(sens)
