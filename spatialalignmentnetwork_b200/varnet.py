@@ -304,6 +304,7 @@ class _Expand(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, xp, sens):
+        xp, sens = ops._c(xp), ops._c(sens)
         N, C, H, W = sens.shape
         out = torch.empty_like(sens)
         ops.call("fft_expand_dc", xp, sens, None, None, None, None, out, out, N, C, H, W, 0)
