@@ -11,23 +11,33 @@ import torch.nn.functional as F
 MODE_DIRECT, MODE_POOL, MODE_D2S, MODE_UP = 0, 1, 2, 3
 
 
+def _activated(r, up):
+    """act(norm(raw)) of a ``Raw``, computed ONCE per raw tensor like ``tc.Raw.coef()`` caches its coefficient
+    table (a BatchNorm term consumed by two convolutions updates its running statistics once)."""
+    key = "_emu_up" if up else "_emu"
+    if not hasattr(r, key):
+        x = r.y
+        if r.d2s:                               # ConvTranspose2d(2, 2) as 1x1 conv + pixel shuffle, then InstanceNorm
+            x = F.pixel_shuffle(x, 2)
+        if up:                                  # nn.Upsample(nearest x2) BEFORE the normalisation (unet.py:128-133)
+            x = x.repeat_interleave(2, dim=2).repeat_interleave(2, dim=3)
+        if r.norm == "in":
+            x = F.instance_norm(x, eps=1e-5)
+        elif r.norm == "bn":
+            bn = r.bn
+            training = bn.training or not bn.track_running_stats
+            if training and bn.track_running_stats:
+                bn.num_batches_tracked.add_(1)
+            x = F.batch_norm(x, bn.running_mean, bn.running_var, bn.weight, bn.bias, training, bn.momentum, bn.eps)
+        if r.slope != 1.0:
+            x = F.leaky_relu(x, r.slope)
+        setattr(r, key, x)
+    return getattr(r, key)
+
+
 def _term(r, mode):
-    """act(norm(resample(raw))) of one ``tc.Raw`` term, in the reference's order of operations."""
-    x = r.y
-    if r.d2s:                                   # ConvTranspose2d(2, 2) as 1x1 conv + pixel shuffle, then InstanceNorm
-        x = F.pixel_shuffle(x, 2)
-    if mode == MODE_UP:                         # nn.Upsample(nearest x2) BEFORE the normalisation (unet.py:128-133)
-        x = x.repeat_interleave(2, dim=2).repeat_interleave(2, dim=3)
-    if r.norm == "in":
-        x = F.instance_norm(x, eps=1e-5)
-    elif r.norm == "bn":
-        bn = r.bn
-        training = bn.training or not bn.track_running_stats
-        if training and bn.track_running_stats:
-            bn.num_batches_tracked.add_(1)
-        x = F.batch_norm(x, bn.running_mean, bn.running_var, bn.weight, bn.bias, training, bn.momentum, bn.eps)
-    if r.slope != 1.0:
-        x = F.leaky_relu(x, r.slope)
+    """resample(act(norm(raw))) of one ``tc.Raw`` term, in the reference's order of operations."""
+    x = _activated(r, mode == MODE_UP)
     if mode == MODE_POOL:                       # avg_pool2d of the ACTIVATED tensor (varnet.py:98)
         x = F.avg_pool2d(x, 2)
     return x

@@ -58,16 +58,34 @@ def test_netG_netD_walkers(monkeypatch):
 
 
 def test_alignment_unet_walker(monkeypatch):
-    """The same stand-ins under the (GPU-verified) alignment U-Net walker reproduce the reference: pins the
-    emulation itself."""
-    from spatialalignmentnetwork_b200 import unet as U
+    """The same stand-ins under the (GPU-verified) SpatialTransformer / alignment U-Net walker reproduce the
+    reference: training forward + backward, running statistics and batch counters afterwards, eval forward."""
+    from spatialalignmentnetwork_b200 import cross, model as M, unet as U
     emulation.install(monkeypatch)
     monkeypatch.setattr(U, "USE_TC", True)
     g = load_golden("align_s")
-    sd = sub(g, "sd.")
-    net = U.UNet(2, 32, (32, 64, 64, 64, 64))
-    net.load_state_dict({k[len("net.0."):]: v for k, v in sd.items() if k.startswith("net.0.")})
-    net.train()
-    y = net.forward_sources([g["moving"], g["fixed"]])
-    y = torch.nn.functional.conv2d(torch.nn.functional.leaky_relu(y, 0.01), sd["net.2.weight"], sd["net.2.bias"], padding=1)
-    assert rel_l2(y.permute(0, 2, 3, 1), g["offset"]) < 1e-4
+    st = cross.SpatialTransformer(1)
+    st.load_state_dict(sub(g, "sd."))
+    st.train()
+    img = g["img"].clone().requires_grad_(True)
+    offset, grid = st(g["moving"], g["fixed"])
+    warped = st.warp(img, grid)
+    assert rel_l2(offset, g["offset"]) < 1e-4 and rel_l2(grid, g["grid"]) < 1e-5 and rel_l2(warped, g["warped"]) < 1e-4
+    ls = M.gradient_loss(offset)
+    loss = ((warped - g["tgt"]) ** 2).mean() + 1000.0 * ls
+    assert abs(ls.item() - g["loss_smooth"].item()) < 1e-4 * abs(g["loss_smooth"].item())
+    assert abs(loss.item() - g["loss"].item()) < 1e-4 * abs(g["loss"].item())
+    loss.backward()
+    assert rel_l2(img.grad, g["g_img"]) < 1e-3
+    from conftest import assert_grads_kink_tolerant
+    assert_grads_kink_tolerant({k: p.grad for k, p in st.named_parameters()}, sub(g, "g."), 2e-2, "net_T ")
+    sd = st.state_dict()
+    for name, ref_v in sub(g, "sd_after.").items():
+        if name.endswith("num_batches_tracked"):
+            assert int(sd[name]) == int(ref_v), name
+        else:
+            assert rel_l2(sd[name], ref_v) < 1e-4, name
+    st.eval()
+    with torch.no_grad():
+        off_e, _ = st(g["moving"], g["fixed"])
+    assert rel_l2(off_e, g["offset_eval"]) < 1e-4
