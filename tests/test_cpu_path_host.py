@@ -221,3 +221,46 @@ def test_test_method_metrics_and_return_value(monkeypatch, reg):
     vis = net.get_vis()
     assert {"metric_PSNR", "metric_SSIM", "metric_MAE", "metric_MSE", "metric_MI"} <= set(vis["scalars"])
     assert {"img_rec", "img_warped", "img_aligned", "img_synth"} <= set(vis["images"])
+
+
+def test_checkpointed_cascades_and_reg_none(monkeypatch):
+    """Host-side knobs: per-cascade recomputation (``VarNet.checkpoint_cascades``) changes nothing; ``reg='None'``
+    (model.py:194-205) trains net_R only, with the alignment network evaluated under no_grad."""
+    from spatialalignmentnetwork_b200 import model as M, unet as U, varnet as V
+    emulation.install(monkeypatch)
+    monkeypatch.setattr(V, "USE_TC", True)
+    monkeypatch.setattr(U, "USE_TC", True)
+    g = load_golden("varnet_s")
+    nc, ch, pools, sch, sp = [int(v) for v in g["cfg"]]
+    outs = []
+    for ck in (False, True):
+        net = V.VarNet(num_cascades=nc, sens_chans=sch, sens_pools=sp, chans=ch, pools=pools, use_ref=True)
+        net.load_state_dict(sub(g, "sd."))
+        net.checkpoint_cascades = ck
+        ks = g["kspace"].clone().requires_grad_(True)
+        rec = net(ks, ~g["pruned"], g["ref"], int(g["nlf"]))
+        ((rec - g["tgt"]) ** 2).mean().backward()
+        outs.append((rec.detach(), ks.grad.clone(), net.cascades[0].dc_weight.grad.clone()))
+    for a, b in zip(*outs):
+        assert rel_l2(b, a) < 1e-6
+    torch.manual_seed(8)
+    random.seed(8)
+    cfg = M.Config(sparsity=0.25, lr=1e-4, shape=32, coils=1, reg="None", mask="equispaced", weight_smooth=1000.0,
+                   weight_sim=1.0, weight_gan=0.1, weight_gan_sim=1.0, num_cascades=1, gan_layers_G=[4, 8],
+                   gan_layers_D=[[4, 4]], fused_adamw=False)
+    net = M.CSModel(cfg)
+    net.net_R = V.VarNet(num_cascades=1, sens_chans=2, sens_pools=2, chans=4, pools=2, use_ref=True)
+    net.optim_R = torch.optim.AdamW(net.net_R.parameters(), lr=1e-4, weight_decay=0)
+    net.train()
+    snapT = [p.detach().clone() for p in net.net_T.parameters()]
+    snapR = [p.detach().clone() for p in net.net_R.parameters()]
+    full = (torch.rand(2, 1, 32, 32) + 0j).to(torch.complex64)
+    net.set_input(full, full.flip(-1))
+    net.update()
+    assert all(torch.equal(a, b.detach()) for a, b in zip(snapT, net.net_T.parameters()))
+    assert any(not torch.equal(a, b.detach()) for a, b in zip(snapR, net.net_R.parameters()))
+    assert all(p.grad is None for p in net.net_T.parameters())
+    with pytest.raises(AssertionError):
+        net.cfg.reg = "bogus"
+        net.set_input(full, full)
+        net.update()
