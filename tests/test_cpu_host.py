@@ -439,3 +439,12 @@ def test_abi_argument_validation_without_gpu(built):
     assert L.san_tc_wgrad_describe(8, 8, 4, 4, 3, ctypes.addressof(out)) == UNSUP       # image narrower than 16 pixels
     # the message of the LAST failure on this thread
     assert L.san_mi_metric(p, p, 1, 64, 65, 0.0, 1.0, p, None) == ARG and b"bins" in L.san_last_error()
+
+
+def test_tap_pairing_design_study():
+    """tools/tap_pairing_model.py: the proposed K-padding-free formulation for the 18- / 36-channel layers (leftover
+    channel group of two filter taps in one K = 16 UMMA step, via the descriptor's leading-dimension offset) checked at
+    the level of descriptor arithmetic against conv2d."""
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    import tap_pairing_model
+    tap_pairing_model.main()
