@@ -414,7 +414,7 @@ def run_b200(args):
         a = aux_h.to(dev, non_blocking=True)
         net.set_input(f, a)
         net.update()
-        return net.loss_all.item()      # D2H of the step's result
+        return net.loss_sim.item()      # D2H of the step's result (update() releases loss_all like the reference)
 
     def barrier():
         if world > 1:

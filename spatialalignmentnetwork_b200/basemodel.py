@@ -117,5 +117,10 @@ class BaseModel(object):
         self.build(cfg)
         saveable = self.get_saveable()
         for k in (objects or saveable.keys()):
-            if k in ckpt:
-                saveable[k].load_state_dict(ckpt[k])
+            # a requested network that is not in the checkpoint is an error, like the reference's ckpt[k]
+            # (basemodel.py:178-181): a typo in --load_nets must not leave a network at random init
+            if k not in ckpt:
+                raise KeyError(f"{k!r} requested but not in the checkpoint (has {sorted(ckpt)})")
+            if k not in saveable:
+                raise KeyError(f"{k!r} is not a network of this model (has {sorted(saveable)})")
+            saveable[k].load_state_dict(ckpt[k])

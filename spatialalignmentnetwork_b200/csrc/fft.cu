@@ -323,9 +323,10 @@ __global__ void __launch_bounds__(256) fft_cols_kernel(const FftArgs a) {
   }
 }
 
-// SAN_FFT_V2: 0 / unset = Stockham kernels; 1 = register FFT, 8 columns per column-pass CTA; 2 = 16 columns per CTA
+// SAN_FFT_V2: 1 / unset = register FFT for 320-point lines, 8 columns per column-pass CTA (default since round 2:
+// fft_expand_dc 0.147 -> 0.111 ms at bs 64, profiles/r2a_fft_v2_ab.txt); 2 = 16 columns per CTA; 0 = Stockham kernels only
 int fft_v2_mode() {
-  static const int mode = [] { const char* e = getenv("SAN_FFT_V2"); return e ? atoi(e) : 0; }();
+  static const int mode = [] { const char* e = getenv("SAN_FFT_V2"); return e ? atoi(e) : 1; }();
   return mode;
 }
 bool fft_v2_enabled() { return fft_v2_mode() != 0; }

@@ -69,7 +69,7 @@ struct FftArgs {
 
 
 // ------------------------------------------------------------------------------------------------------------
-// v2 line FFT for the benchmark length 320 = 16 x 20 (opt-in: SAN_FFT_V2=1; not yet measured on a B200).
+// v2 line FFT for the benchmark length 320 = 16 x 20 (default; SAN_FFT_V2=0 selects the Stockham kernels; measured 1.33-2.3x over them, profiles/r2a_fft_v2_ab.txt).
 // The Stockham kernels above make 4 shared-memory round trips per line with ~2000 warp instructions per line
 // (ncu: instruction / latency bound at 0.26 of the HBM roofline).  Here every thread owns one sub-transform in
 // REGISTERS (csrc/fft_small.cuh, checked on the host by tests/host/fft_small_test.cu): phase 1 = 16-point DFT of the

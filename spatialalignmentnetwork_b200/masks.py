@@ -72,10 +72,20 @@ class LowpassMask(Mask):
 
     def __init__(self, sparsity, shape):
         super().__init__(shape)
-        center_len = round(shape * sparsity)
+        center_len = math.floor(shape * sparsity)                  # reference masks.py:121
         pruned = torch.zeros(shape, dtype=torch.bool)
         pruned[center_len // 2:center_len // 2 - center_len] = True
         self.pruned = pruned
 
 
-masks = {"standard": StandardMask, "equispaced": EquispacedMask, "lowpass": LowpassMask}
+class _Unsupported(dict):
+    """``masks[name]`` with an explicit error for the reference's learned masks (LOUPE / Taylor pruning,
+    reference masks.py:141-244): they sit before the hot path and are not part of this build."""
+
+    def __missing__(self, name):
+        raise KeyError(f"unsupported mask {name!r}: this build provides {sorted(self)} "
+                       "(the learned 'loupe' / 'taylor' masks of the reference are out of scope)")
+
+
+# 'mask' = the plain fully-sampled ``Mask(shape)`` the reference registers under that name (model.py:30-37)
+masks = _Unsupported({"mask": Mask, "standard": StandardMask, "equispaced": EquispacedMask, "lowpass": LowpassMask})

@@ -45,12 +45,13 @@ class CSModel(BaseModel):
     def __init__(self, *args, **kwargs):
         super().__init__(*args, **kwargs)
         self.grad_sync = None  # callable(list_of_params) installed by parallel.attach()
+        self.grad_buckets = None  # parallel.GradBuckets (overlapped per-cascade all-reduce) installed by parallel.attach()
         self.memo_init = (set(self.__dict__.keys()) | {"memo_init"}).copy()
 
     def build(self, cfg):
         super().build(cfg)
         assert cfg.lr == 1e-4
-        if cfg.mask in ("mask", "taylor"):
+        if cfg.mask in ("mask", "taylor"):                 # reference model.py:53-56 ('taylor' raises: out of scope)
             self.net_mask = masks[cfg.mask](cfg.shape)
         else:
             self.net_mask = masks[cfg.mask](cfg.sparsity, cfg.shape)
@@ -140,8 +141,20 @@ class CSModel(BaseModel):
         self.loss_sim = ssimloss(self.img_full_rss, self.img_rec)
         self.loss_all = self.loss_all + self.loss_sim * self.cfg.weight_sim
 
+    def _names(self, nets):
+        return [k for n in nets for k, v in self.__dict__.items() if v is n]
+
+    def _arm(self, nets):
+        """Before ``backward()``: route the gradients of ``nets`` into the flat all-reduce buckets (parallel.GradBuckets),
+        whose exchange then overlaps the rest of the backward.  No-op on one GPU."""
+        if self.grad_buckets is not None:
+            self.grad_buckets.arm(self._names(nets))
+
     def _sync(self, nets):
-        if self.grad_sync is not None:
+        """After ``backward()``: gradients of ``nets`` are the mean over ranks when this returns."""
+        if self.grad_buckets is not None:
+            self.grad_buckets.sync(self._names(nets))
+        elif self.grad_sync is not None:
             self.grad_sync([p for n in nets for p in n.parameters()])
 
     def update(self):
@@ -153,6 +166,7 @@ class CSModel(BaseModel):
             self.loss_all = 0
             self.forwardR()
             self.optim_R.zero_grad()
+            self._arm([self.net_R])
             self.loss_all.backward()
             self._sync([self.net_R])
             self.optim_R.step()
@@ -162,6 +176,7 @@ class CSModel(BaseModel):
             self.forwardR()
             self.optim_T.zero_grad()
             self.optim_R.zero_grad()
+            self._arm([self.net_T, self.net_R])
             self.loss_all.backward()
             self._sync([self.net_T, self.net_R])
             self.optim_T.step()
@@ -179,6 +194,7 @@ class CSModel(BaseModel):
             opts = [self.optim_T, self.optim_G] + ([self.optim_R] if with_R else [])
             for o in opts:
                 o.zero_grad()
+            self._arm(nets)
             self.loss_all.backward()
             self._sync(nets)
             for o in opts:
@@ -186,11 +202,13 @@ class CSModel(BaseModel):
             self.loss_all = 0
             self.forwardD(D_loss=True)
             self.optim_D.zero_grad()
+            self._arm([self.net_D])
             self.loss_all.backward()
             self._sync([self.net_D])
             self.optim_D.step()
         else:
             assert False, f"unknown reg {self.cfg.reg!r}"
+        del self.loss_all          # reference model.py:261: the graph is released, get_vis() does not log it
 
     def test(self):
         assert not self.training

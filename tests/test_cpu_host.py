@@ -90,6 +90,42 @@ def test_checkpoint_roundtrip(tmp_path):
     assert torch.equal(a.net_mask.pruned, b.net_mask.pruned) and b.cfg.num_cascades == 1
 
 
+def test_resume_cli_config_wins_and_missing_nets_raise(tmp_path):
+    """Reference train.py:121 resumes with ``Model(ckpt=ckpt, cfg=cfg, objects=args.load_nets)``: the CLI config wins
+    over the checkpoint's (the staged recipe of commands_train_test.sh changes --reg between stages), and a
+    requested network that is not in the checkpoint is a KeyError (reference basemodel.py:178-181)."""
+    import pytest
+    from spatialalignmentnetwork_b200 import model as M
+    random.seed(3)
+    kw = dict(sparsity=0.25, lr=1e-4, shape=32, coils=1, mask="equispaced", weight_smooth=1000.0, weight_sim=1.0,
+              num_cascades=1, gan_layers_G=[4, 8, 8], gan_layers_D=[[4, 4], [8, 8]])
+    a = M.CSModel(M.Config(reg="None", **kw))
+    a.save(str(tmp_path / "ckpt_1.pt"), objects=["net_mask", "net_R"])
+    b = M.CSModel(ckpt=str(tmp_path / "ckpt_1.pt"), cfg=M.Config(reg="Mixed", **kw), objects=["net_mask", "net_R"])
+    assert b.cfg.reg == "Mixed"
+    assert all(torch.equal(v, b.net_R.state_dict()[k]) for k, v in a.net_R.state_dict().items())
+    assert M.CSModel(ckpt=str(tmp_path / "ckpt_1.pt"), objects=["net_R"]).cfg.reg == "None"   # no cfg: the checkpoint's
+    with pytest.raises(KeyError):
+        M.CSModel(ckpt=str(tmp_path / "ckpt_1.pt"), cfg=M.Config(reg="Mixed", **kw), objects=["net_T"])
+    with pytest.raises(KeyError):
+        M.CSModel(ckpt=str(tmp_path / "ckpt_1.pt"), cfg=M.Config(reg="Mixed", **kw))      # all nets, but only 2 saved
+    # train.py passes the CLI config on --resume and refuses --load_nets without it
+    src = open(os.path.join(ROOT, "train.py")).read()
+    assert "CSModel(ckpt=args.resume, cfg=cfg, objects=args.load_nets)" in src and "assert args.load_nets is None" in src
+
+
+def test_mask_registry_and_lowpass_floor():
+    """LowpassMask keeps floor(shape * sparsity) centre columns (reference masks.py:121); 'mask' is the plain
+    fully-sampled Mask (reference model.py:30); the learned masks fail with an explicit message."""
+    import pytest
+    from spatialalignmentnetwork_b200 import masks as K
+    m = K.masks["lowpass"](0.33, 320)
+    assert int((~m.pruned).sum()) == 105                     # round() would give 106
+    assert int(K.masks["mask"](320).pruned.sum()) == 0
+    with pytest.raises(KeyError, match="unsupported mask"):
+        K.masks["taylor"]
+
+
 _WORKER = r'''
 import os, sys, torch, torch.distributed as dist
 sys.path.insert(0, sys.argv[1])
@@ -348,19 +384,108 @@ for name in ("net_mask", "net_G", "net_D", "net_T", "net_R"):
         both = [torch.zeros_like(v) for _ in range(2)]
         dist.all_gather(both, v.contiguous())
         assert torch.equal(both[0], both[1]), (name, k)
-# the hook CSModel.update() calls between backward and the optimiser steps: mean over ranks, per network list
+# the bracket CSModel.update() puts around backward(): _arm(nets) ... _sync(nets) = mean over ranks of exactly those
+# networks (T, G, R in the generator step, D in the discriminator step)
+net._arm([net.net_T, net.net_G])
 for p in net.net_G.parameters():
-    p.grad = torch.full_like(p, float(r + 1))
+    p.grad.fill_(float(r + 1))          # .grad is a view of the flat bucket buffer
 for p in net.net_D.parameters():
     p.grad = torch.full_like(p, 10.0 * (r + 1))
-net._sync([net.net_T, net.net_G])   # net_T has no gradients yet: skipped
+net._sync([net.net_T, net.net_G])   # net_T received no gradients: zeros
 assert all(torch.all(p.grad == 1.5) for p in net.net_G.parameters())
+assert all(torch.all(p.grad == 0.0) for p in net.net_T.parameters())
 assert all(torch.all(p.grad == 10.0 * (r + 1)) for p in net.net_D.parameters())
+net._arm([net.net_D])
+for p in net.net_D.parameters():
+    p.grad.fill_(10.0 * (r + 1))
 net._sync([net.net_D])
 assert all(torch.all(p.grad == 15.0) for p in net.net_D.parameters())
+# blocking fallback (attach(overlap=False)): same result through grad_sync
+net.grad_buckets = None
+for p in net.net_G.parameters():
+    p.grad = torch.full_like(p, float(r + 1))
+net._sync([net.net_G])
+assert all(torch.all(p.grad == 1.5) for p in net.net_G.parameters())
 dist.destroy_process_group()
 print("ok", r)
 '''
+
+
+_WORKER_BUCKETS = r"""
+import os, sys, torch, torch.distributed as dist
+sys.path.insert(0, sys.argv[1])
+from spatialalignmentnetwork_b200 import parallel
+dist.init_process_group("gloo", init_method="tcp://127.0.0.1:" + sys.argv[2], rank=int(sys.argv[3]), world_size=2)
+r = dist.get_rank()
+
+class R(torch.nn.Module):            # parameter names like the VarNet's: sens_net.*, cascades.<i>.*
+    def __init__(self):
+        super().__init__()
+        self.sens_net = torch.nn.Linear(6, 6)
+        self.cascades = torch.nn.ModuleList([torch.nn.Linear(6, 6) for _ in range(3)])
+        self.unused = torch.nn.Parameter(torch.ones(2))       # receives no gradient: its bucket leaves in sync()
+    def forward(self, x):
+        x = self.sens_net(x)
+        for c in self.cascades:
+            x = torch.tanh(c(x))
+        return x
+
+class Model:
+    pass
+
+torch.manual_seed(5 + r)
+m = Model()
+m.net_R, m.net_T = R(), torch.nn.Linear(6, 6)
+parallel.attach(m)
+gb = m.grad_buckets
+assert [b.key for b in gb.buckets["net_R"]] == ["unused", "sens_net", "cascades.0", "cascades.1", "cascades.2"]
+assert [b.key for b in gb.buckets["net_T"]] == ["net_T"]
+x = parallel.shard(torch.arange(24.).reshape(4, 6) / 10, r, 2)
+for step in range(2):                # second step: buffers are re-zeroed, aliasing survives zero_grad(set_to_none)
+    for p in list(m.net_R.parameters()) + list(m.net_T.parameters()):
+        p.grad = None
+    gb.arm(["net_T", "net_R"])
+    n0 = gb.launched
+    loss = m.net_R(m.net_T(x)).pow(2).sum()
+    loss.backward()
+    assert gb.launched - n0 == 5, gb.launched - n0   # net_T + sens + 3 cascades left from the hooks (overlapped)
+    gb.sync(["net_T", "net_R"])
+    got = [p.grad.clone() for p in list(m.net_T.parameters()) + list(m.net_R.parameters())]
+    for p, v in zip(gb.params["net_R"], gb.views["net_R"]):
+        assert p.grad.data_ptr() == v.data_ptr()             # .grad is a view of the flat buffer: no copies
+    # reference: plain local gradients, blocking all-reduce
+    for p in list(m.net_R.parameters()) + list(m.net_T.parameters()):
+        p.grad = None
+    m.net_R(m.net_T(x)).pow(2).sum().backward()
+    m.net_R.unused.grad = torch.zeros(2)
+    ps = list(m.net_T.parameters()) + list(m.net_R.parameters())
+    parallel.allreduce_mean_grads(ps)
+    for a, p in zip(got, ps):
+        assert torch.allclose(a, p.grad, rtol=1e-6, atol=1e-7)
+# a network that is not armed is left alone (Mixed mode: net_D collects gradients in the generator step)
+for p in m.net_T.parameters():
+    p.grad = None
+gb.arm(["net_R"])
+m.net_R(m.net_T(x)).sum().backward()
+gb.sync(["net_R"])
+both = [torch.zeros_like(m.net_T.weight.grad) for _ in range(2)]
+dist.all_gather(both, m.net_T.weight.grad)
+assert not torch.equal(both[0], both[1])
+dist.destroy_process_group()
+print("ok", r)
+"""
+
+
+def test_grad_buckets_overlapped_world_size_2(tmp_path):
+    """parallel.GradBuckets: per-cascade buckets in one flat buffer per network, launched from autograd hooks during
+    backward (SURVEY 8e), equal to the blocking flat all-reduce; .grad aliases the flat buffer."""
+    script = tmp_path / "w.py"
+    script.write_text(_WORKER_BUCKETS)
+    port = str(29850 + random.randint(0, 40))
+    procs = [subprocess.Popen([sys.executable, str(script), ROOT, port, str(r)], stdout=subprocess.PIPE,
+                              stderr=subprocess.STDOUT) for r in range(2)]
+    outs = [p.communicate(timeout=300)[0].decode() for p in procs]
+    assert all(p.returncode == 0 for p in procs), outs
 
 
 def test_attach_broadcasts_all_networks_world_size_2(tmp_path):

@@ -69,7 +69,13 @@ def main(args):
         cfg.gan_layers_G = [int(c) for c in args.gan_layers_G.split(",")]
     if args.gan_layers_D:
         cfg.gan_layers_D = [[int(c) for c in blk.split(",")] for blk in args.gan_layers_D.split(";")]
-    net = CSModel(ckpt=args.resume, objects=args.load_nets) if args.resume else CSModel(cfg)
+    if args.resume:
+        # the CLI config wins over the checkpoint's (reference train.py:121): the staged recipe of
+        # commands_train_test.sh resumes each stage with a different --reg and --load_nets
+        net = CSModel(ckpt=args.resume, cfg=cfg, objects=args.load_nets)
+    else:
+        assert args.load_nets is None, "--load_nets needs --resume (reference train.py:123)"
+        net = CSModel(cfg)
     net.to(device)
     if world > 1:
         parallel.attach(net)
@@ -100,17 +106,27 @@ def main(args):
                                   **{k: round(float(v), 6) for k, v in sc.items()}}), flush=True)
             if rank == 0 and it % args.ckpt_every == 0:
                 net.save(os.path.join(args.logdir, f"ckpt_{it:010d}.pt"))
+        # ---- validation (reference train.py:267-308): disjoint windows of the global batch size (drop_last like the
+        # reference's val loader), each window sharded over the ranks; metric sums are all-reduced so that every rank
+        # sees the same numbers and takes the same early-stop decision.  BatchNorm running statistics are rank-local
+        # during training: they are averaged first so that eval-mode outputs (and the saved checkpoint) agree.
+        parallel.average_buffers(net)
         net.eval()
-        vals, stat_loss = [], []
-        for b0 in range(0, n_val, max(1, args.batch_size // world)):
-            net.set_input(full_v[b0:b0 + args.batch_size], aux_v[b0:b0 + args.batch_size])
-            stat_loss.append(net.test())
-            vals.append((net.metric_PSNR, net.metric_SSIM))
+        sums = torch.zeros(4, dtype=torch.float64, device=device)       # loss, PSNR, SSIM, windows
+        for b0 in range(0, n_val - args.batch_size + 1, args.batch_size):
+            fv = parallel.shard(full_v[b0:b0 + args.batch_size], rank, world)
+            av = parallel.shard(aux_v[b0:b0 + args.batch_size], rank, world)
+            if fv.shape[0] < 2:                             # forwardG splits the batch in two halves (model.py:125-126)
+                continue
+            net.set_input(fv, av)
+            sums += torch.tensor([net.test(), net.metric_PSNR, net.metric_SSIM, 1.0], dtype=torch.float64, device=device)
+        if world > 1:
+            dist.all_reduce(sums)
+        nwin = max(sums[3].item(), 1.0)
+        loss_current, val_psnr, val_ssim = (sums[:3] / nwin).tolist()
         if rank == 0:
-            print(json.dumps({"epoch": epoch, "val_PSNR": sum(v[0] for v in vals) / len(vals),
-                              "val_SSIM": sum(v[1] for v in vals) / len(vals)}), flush=True)
+            print(json.dumps({"epoch": epoch, "val_PSNR": val_psnr, "val_SSIM": val_ssim}), flush=True)
         if args.intel_stop > 0:                             # early stopping of reference train.py:293-307
-            loss_current = sum(stat_loss) / len(stat_loss)
             if loss_best is None or loss_current < loss_best:
                 loss_best, iter_best = loss_current, it
                 if rank == 0:
@@ -118,8 +134,8 @@ def main(args):
                     if os.path.exists(best):
                         shutil.rmtree(best)
                     net.save(best)
-            elif it >= args.intel_stop + iter_best:
-                if rank == 0:
+            elif it >= args.intel_stop + iter_best:         # identical on every rank (all-reduced loss): no rank is left
+                if rank == 0:                               # waiting in a gradient all-reduce
                     print("signal_end set due to intel_stop", flush=True)
                 break
     if rank == 0:
