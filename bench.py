@@ -41,7 +41,12 @@ def parse():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--batch", type=int, default=64, help="slices per GPU per step (weak scaling)")
-    ap.add_argument("--shape", type=int, default=320)
+    ap.add_argument("--shape", default="320", help="H (square) or HxW, e.g. 640x368 (BASELINE cfg4)")
+    ap.add_argument("--coils", type=int, default=1, help="coils per slice (cfg4: 15)")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="weak: --batch slices per GPU; strong: --batch is the GLOBAL batch, split over the GPUs")
+    ap.add_argument("--no-parity", action="store_true", help="skip the 2-slice parity block (oracle fp32 + fp64 on the host)")
+    ap.add_argument("--no-overlap", action="store_true", help="N > 1: blocking flat all-reduce instead of the overlapped buckets")
     ap.add_argument("--cascades", type=int, default=12)
     ap.add_argument("--reg", default="Rec", choices=["Rec", "Mixed"],
                     help="training mode of the step: Rec = the headline cfg2 step; Mixed = BASELINE cfg5 (adds NetG twice, "
@@ -61,7 +66,11 @@ def parse():
     ap.add_argument("--no-profile", action="store_true", help="skip the instrumented per-kernel step")
     ap.add_argument("--breakdown", default="", help="write the per-op time table (JSON) to this path")
     ap.add_argument("--min-warmup", type=int, default=3, help="lower bound on warm-up steps (profiler runs only use < 3)")
-    return ap.parse_args()
+    a = ap.parse_args()
+    hw = str(a.shape).lower().split("x")
+    a.H, a.W = (int(hw[0]), int(hw[-1]))
+    a.shape = a.W                     # the column mask / num_low_frequencies live on the last axis (model.py:160-163)
+    return a
 
 
 def load_peaks():
@@ -127,12 +136,13 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------- inputs
-def make_inputs(batch, shape, device="cpu", pin=False):
+def make_inputs(batch, args, device="cpu", pin=False):
     """"rand" set of SURVEY.md 8(d): real & imag ~ U[0,1), complex64 (mirrors reference model.py:372-375)."""
     import torch
     g = torch.Generator().manual_seed(SEED + 1)
-    full = torch.complex(torch.rand(batch, 1, shape, shape, generator=g), torch.rand(batch, 1, shape, shape, generator=g))
-    aux = torch.complex(torch.rand(batch, 1, shape, shape, generator=g), torch.rand(batch, 1, shape, shape, generator=g))
+    shp = (batch, args.coils, args.H, args.W)
+    full = torch.complex(torch.rand(*shp, generator=g), torch.rand(*shp, generator=g))
+    aux = torch.complex(torch.rand(*shp, generator=g), torch.rand(*shp, generator=g))
     if pin:
         full, aux = full.pin_memory(), aux.pin_memory()
     if device != "cpu":
@@ -145,7 +155,7 @@ def build_model(args):
     from spatialalignmentnetwork_b200 import model as M
     torch.manual_seed(SEED)
     random.seed(SEED)
-    cfg = M.Config(sparsity=args.sparsity, lr=1e-4, shape=args.shape, coils=1, reg=args.reg, mask=args.mask,
+    cfg = M.Config(sparsity=args.sparsity, lr=1e-4, shape=args.shape, coils=args.coils, reg=args.reg, mask=args.mask,
                    weight_smooth=1000.0, weight_gan=0.1, weight_gan_sim=1.0, weight_sim=1.0, use_amp=False,
                    num_cascades=args.cascades)
     if args.lncc_weight:
@@ -190,16 +200,22 @@ def algorithmic(name, a):
     return 0.0, 0.0
 
 
-# dram__bytes_read.sum + dram__bytes_write.sum of ONE launch from the committed `ncu --set full` capture
-# (profiles/r1d_tc_ncu_summary.txt: 3x3 conv 18->18, 320x320, bs 64).  The roofline's `achieved` averages over
-# all launches of the step, so the traffic figure is given for that named launch together with its algorithmic
-# bytes (staged BF16 hi/lo operand in + fp32 result out): no re-reads reach DRAM.
+# dram__bytes_read.sum + dram__bytes_write.sum from the committed `ncu --set full` captures, per launch, next to the
+# ALGORITHMIC bytes of SURVEY 8(d): a conv reads its fp32 input once and writes its fp32 output once,
+# 4*N*H*W*(Cin+Cout).  The conv's real traffic includes the operand-staging pass that feeds it (fp32 in, BF16 hi/lo
+# out) and the staged operand read back by the GEMM, so both kernels are counted.
 NCU_TRAFFIC = {
-    "tc_conv": {"launch": "3x3 18->18 @320x320 bs64", "dram_bytes": 849.5e6 + 436.5e6,
-                "algorithmic_bytes": 64 * 2 * 4 * 322 * 322 * 16.0 + 64 * 18 * 320 * 320 * 4.0,
+    "tc_conv": {"launch": "3x3 18->18 @320x320 bs64 (stage_act_kernel + conv_tc_kernel)",
+                "dram_bytes": (472.1e6 + 794.1e6) + (849.5e6 + 436.5e6),
+                "algorithmic_bytes": 4.0 * 64 * 320 * 320 * (18 + 18),
                 "source": "profiles/r1d_tc_ncu_summary.txt"},
-    "tc_wgrad": {"launch": "3x3 18->18 @320x320 bs64", "dram_bytes": 1693.6e6 + 4.1e6,
-                 "algorithmic_bytes": 2 * 64 * 2 * 4 * 322 * 322 * 16.0, "source": "profiles/r1d_tc_ncu_summary.txt"},
+    "tc_wgrad": {"launch": "3x3 18->18 @320x320 bs64 (wgrad_tc_kernel on the two staged operands)",
+                 "dram_bytes": 1693.6e6 + 4.1e6,
+                 "algorithmic_bytes": 4.0 * 64 * 320 * 320 * (18 + 18), "source": "profiles/r1d_tc_ncu_summary.txt"},
+    # fft_rows_v2_kernel + fft_cols_v2_kernel of one fft_expand_dc call, bs 64, 320x320, 1 coil: (32C+8)*P algorithmic
+    "fft_expand_dc": {"launch": "fft_expand_dc bs64 320x320 C=1 (fft_rows_v2_kernel + fft_cols_v2_kernel)",
+                      "dram_bytes": (104.9e6 + 21.4e6) + (157.3e6 + 34.6e6), "algorithmic_bytes": 40.0 * 64 * 320 * 320,
+                      "source": "profiles/r2a_fft_v2_ab.txt"},
 }
 
 CLASSES = {
@@ -260,7 +276,8 @@ def summarise_profile(records, step_ms, peaks):
         ach = f["bytes"] / f["ms"] / 1e6
         roof_fft = dict(kernel="fft_expand_dc (x*S -> fft2 -> soft-DC + residual; and its adjoint use)", bound="hbm",
                         achieved=round(ach, 1), peak=peaks["hbm"], unit="GB/s", frac=round(ach / peaks["hbm"], 4),
-                        peak_source=f"copy bandwidth, {peaks['src']}", traffic=None, launches=f["launches"],
+                        peak_source=f"copy bandwidth, {peaks['src']}", traffic=NCU_TRAFFIC.get("fft_expand_dc"),
+                        launches=f["launches"],
                         avg_launch_ms=round(f["ms"] / f["launches"], 4),
                         share_of_kernel_time=round(f["ms"] / total, 4))
     return roof, roof_fft, breakdown
@@ -285,7 +302,7 @@ def cpu_step_factory(args, nslices, device="cpu"):
                 v.requires_grad_(True)
                 params.append(v)
         sds[t], opts[t] = sd, torch.optim.AdamW(params, lr=1e-4, weight_decay=0)
-    full, aux = make_inputs(nslices, args.shape, device=device)
+    full, aux = make_inputs(nslices, args, device=device)
 
     def step_rec():
         inp = ostep.set_input(full, aux, pruned)
@@ -326,7 +343,8 @@ def run_reference(args):
         torch.backends.cuda.matmul.allow_tf32 = bool(args.tf32)
         dev = f"cuda:{int(os.environ.get('LOCAL_RANK', '0'))}"
     step = cpu_step_factory(args, ns, device=dev)
-    for _ in range(min(args.warmup, 1)):
+    nwarm = args.warmup             # the same W warm-up and K timed steps as the b200 arm (a step is ~1.5 s on 2 slices)
+    for _ in range(nwarm):
         step()
     times = []
     for _ in range(args.steps):
@@ -336,28 +354,41 @@ def run_reference(args):
     ms = 1e3 * sum(times) / len(times)
     val = ns / (ms / 1e3)
     cores = os.cpu_count() or 1
-    sample = (f"{ns} slices/step of the same workload ({args.cascades}-cascade VarNet + align, {args.shape}x{args.shape}, "
-              f"fwd+bwd+AdamW), CPU oracle port (torch CPU fp32), {cores} threads; warm-up capped at 1 step")
+    sample = (f"{ns} slices/step of the same workload ({args.cascades}-cascade VarNet + align, {args.H}x{args.W}"
+              f"{' x %d coils' % args.coils if args.coils > 1 else ''}, fwd+bwd+AdamW), CPU oracle port (torch CPU fp32), "
+              f"{cores} threads; {nwarm} warm-up step(s)")
     if args.ref_device == "cuda":
         sample = sample.replace("CPU oracle port (torch CPU fp32)",
                                 f"oracle port as eager PyTorch CUDA (cuDNN / cuFFT, TF32 {'on' if args.tf32 else 'off'})")
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": round(val, 4), "unit": "slices/s", "n_gpus": args.gpus,
-        "steps": args.steps, "warmup": min(args.warmup, 1), "ms_per_step": round(ms, 2), "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": workload_config(args, max(args.gpus, 1), checkpoint=False),
+        "steps": args.steps, "warmup": nwarm, "ms_per_step": round(ms, 2), "higher_is_better": True,
+        "scaling": args.scaling, "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(args, max(args.gpus, 1), checkpoint=False, sample=ns),
+        "ranks_running": 1,   # under torchrun only rank 0 runs this arm: its value does NOT scale with --gpus
         "cpu_baseline": {"value": round(val, 4), "unit": "slices/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": round(val, 4), "unit": "slices/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0}))
 
 
+def per_gpu_batch(args, world):
+    if args.scaling == "strong":
+        assert args.batch % world == 0, "--scaling strong: --batch (global) must divide over the GPUs"
+        return args.batch // world
+    return args.batch
+
+
 def workload_config(args, world, checkpoint, sample=None):
+    """``sample``: slices per step the arm REALLY ran when that is a bounded sample of the workload (reference arm)."""
+    bpg = per_gpu_batch(args, world)
+    dims = f"{args.H}x{args.W}" + (f" x {args.coils} coils" if args.coils > 1 else "")
     if args.reg == "Mixed":
-        what = (f"cfg5 step: bs={args.batch}/GPU {args.shape}x{args.shape} synthetic T1/T2 pairs, {args.cascades}-cascade "
+        what = (f"cfg5 step: bs={bpg}/GPU {dims} synthetic T1/T2 pairs, {args.cascades}-cascade "
                 "VarNet + alignment U-Net + NetG (x2) + NetD, reg='Mixed' (smooth*1000 + L1 gan_sim + SSIM + hinge*0.1, "
                 "then the discriminator step), 4x equispaced mask, fwd+bwd+AdamW x4")
     else:
-        what = (f"cfg2: bs={args.batch}/GPU {args.shape}x{args.shape} synthetic T1/T2 pairs, "
+        name = "cfg4" if args.coils > 1 else ("cfg3" if args.lncc_weight else "cfg2")
+        what = (f"{name}: bs={bpg}/GPU {dims} synthetic T1/T2 pairs, "
                 f"{args.cascades}-cascade VarNet + alignment U-Net, reg='Rec' (smooth*1000 + SSIM), "
                 "4x equispaced mask, fwd+bwd+AdamW")
     if args.lncc_weight:
@@ -366,14 +397,78 @@ def workload_config(args, world, checkpoint, sample=None):
         what += f" + ms_mi_loss(full, warped)*{args.mi_weight:g}"
     if args.mask != "equispaced" or args.sparsity != 0.25:
         what = what.replace("4x equispaced mask", f"{1 / args.sparsity:g}x {args.mask} mask")
-    return {"workload": what, "reg": args.reg,
-            "batch_per_gpu": args.batch, "global_batch": args.batch * world,
-            "shape": args.shape, "cascades": args.cascades, "coils": 1, "parallelism": f"dp{world}",
-            "checkpoint_cascades": bool(checkpoint),
-            "l2": "inputs (105 MB/step) + activations (GBs) exceed the 126 MB L2; no flush needed"}
+    step_mb = 2 * bpg * args.coils * args.H * args.W * 8 / 1e6
+    cfg = {"workload": what, "reg": args.reg,
+           "batch_per_gpu": bpg, "global_batch": bpg * world,
+           "shape": args.shape if args.H == args.W else [args.H, args.W], "cascades": args.cascades, "coils": args.coils,
+           "parallelism": f"dp{world}", "checkpoint_cascades": bool(checkpoint),
+           "l2": f"inputs ({step_mb:.0f} MB/step) + activations (GBs) exceed the 126 MB L2; no flush needed"}
+    if sample is not None:
+        # the reference arm times a BOUNDED SAMPLE of the workload: say what really ran
+        cfg.update({"batch_per_gpu": sample, "global_batch": sample, "workload_batch_per_gpu": bpg,
+                    "sample_mismatch": sample != bpg,
+                    "workload": what + f" [this arm ran a bounded sample: {sample} slices/step on ONE process]"})
+    return cfg
 
 
 # ------------------------------------------------------------------------------------- CUDA arm
+def gpu_reference_recorded(args):
+    """The reference's own path as eager PyTorch CUDA (cuDNN / cuFFT) on a B200 of this pool, measured with
+    ``bench.py --impl reference --ref-device cuda`` (SURVEY 8d "the real bar"); recorded, not re-timed here: it needs
+    the whole GPU (bs 64 does not fit 180 GB in eager autograd; bs 32 is the largest that does)."""
+    if args.reg != "Rec" or args.coils != 1 or args.H != 320 or args.W != 320 or args.cascades != 12:
+        return None
+    try:
+        with open(os.path.join(ROOT, "profiles", "r2a_gpu_reference_eager.json")) as f:
+            r = json.load(f)["results"]
+        return {"unit": "slices/s", "batch": 32, "tf32_off": r["tf0_bs32"]["slices_per_s"], "tf32_on": r["tf1_bs32"]["slices_per_s"],
+                "bs64": "OOM (176 GiB)", "bs4_tf32_off": r["tf0_bs4"]["slices_per_s"],
+                "source": "profiles/r2a_gpu_reference_eager.json (recorded run on a B200 of this pool, 5 steps, CUDA-synchronised wall clock)"}
+    except Exception:
+        return None
+
+
+def parity_block(args, net, dev, nslices=2):
+    """Headline-config parity inside the bench run: the same network (current weights) steps once on ``nslices``
+    slices; outputs and EVERY parameter gradient are compared with the CPU oracle in fp32 and fp64, plus PSNR / SSIM
+    of img_rec against the oracle's (BASELINE.json metric).  oracle/parity.py is test infrastructure: checker only."""
+    import torch
+    from oracle import parity
+    full, aux = make_inputs(nslices, args)
+    sd_T = {k: v.detach().cpu().clone() for k, v in net.net_T.state_dict().items()}
+    sd_R = {k: v.detach().cpu().clone() for k, v in net.net_R.state_dict().items()}
+    pruned = net.net_mask.pruned.detach().cpu().clone()
+    net.train()
+    net.set_input(full.to(dev), aux.to(dev))
+    net.loss_all = 0
+    net.forwardT()
+    net.forwardR()
+    for p in list(net.net_T.parameters()) + list(net.net_R.parameters()):
+        p.grad = None
+    net.loss_all.backward()
+    torch.cuda.synchronize()
+    out = {k: getattr(net, k).detach().cpu() for k in ("img_rec", "img_warped", "img_offset")}
+    out["loss_all"] = net.loss_all.item()
+    grads = {"T." + k: p.grad.detach().cpu() for k, p in net.net_T.named_parameters() if p.grad is not None}
+    grads.update({"R." + k: p.grad.detach().cpu() for k, p in net.net_R.named_parameters() if p.grad is not None})
+    rep = parity.rec_step_report(sd_T, sd_R, full, aux, pruned, args.shape, args.sparsity, args.cascades, out, grads)
+    fw, g = rep["forward"], rep["grad"]
+    return {"config": rep["config"], "oracle": "CPU restatement of the reference (oracle/), fp32 = reference arithmetic, fp64 = calibration",
+            "forward_rel_l2_vs_fp32": {k: float(f"{v['vs_fp32']:.3e}") for k, v in fw.items()},
+            "forward_fp32_oracle_vs_fp64": {k: float(f"{v['fp32_vs_fp64']:.3e}") for k, v in fw.items()},
+            "grad_all_params_vs_fp64": float(f"{g['all_concatenated']['vs_fp64']:.3e}"),
+            "grad_cpu_fp32_oracle_vs_fp64": float(f"{g['all_concatenated']['fp32_vs_fp64']:.3e}"),
+            "grad_cosine_vs_fp64": round(g["all_concatenated"]["cosine_vs_fp64"], 6),
+            "grad_tensors": g["tensors"], "grad_worst": g["worst"][:3],
+            "psnr_rec_vs_reference_rec_db": round(rep["image_metrics"]["psnr_rec_vs_reference_rec_db"], 2),
+            "ssim_rec_vs_reference_rec": round(rep["image_metrics"]["ssim_rec_vs_reference_rec"], 7),
+            "psnr_vs_full": {"b200": round(rep["image_metrics"]["psnr_rec_vs_full"], 3),
+                             "reference": round(rep["image_metrics"]["psnr_reference_rec_vs_full"], 3)},
+            "ssim_vs_full": {"b200": round(rep["image_metrics"]["ssim_rec_vs_full"], 5),
+                             "reference": round(rep["image_metrics"]["ssim_reference_rec_vs_full"], 5)},
+            "oracle_seconds": rep["oracle_seconds"]}
+
+
 def run_b200(args):
     import torch
     import torch.distributed as dist
@@ -392,15 +487,16 @@ def run_b200(args):
 
     net = build_model(args)
     total_mem = torch.cuda.get_device_properties(dev).total_memory
-    est = args.batch * (args.cascades * 0.08 + 0.45) * 2 ** 30 * (args.shape / 320.0) ** 2   # raw conv outputs only
+    bpg = per_gpu_batch(args, world)
+    est = bpg * (args.cascades * 0.08 + 0.45) * 2 ** 30 * (args.H * args.W / 102400.0) * (0.5 + 0.5 * args.coils)   # raw conv outputs only
     ckpt = {"auto": est > 0.7 * total_mem, "0": False, "1": True}[args.checkpoint]
     net.net_R.checkpoint_cascades = ckpt
     net.to(dev).train()
     if world > 1:
-        parallel.attach(net)
+        parallel.attach(net, overlap=not args.no_overlap)
 
-    # per-rank shard of the global batch (weak scaling: args.batch slices per GPU)
-    full_h, aux_h = make_inputs(args.batch, args.shape, pin=True)
+    # per-rank shard of the global batch (weak: args.batch slices per GPU; strong: args.batch / world)
+    full_h, aux_h = make_inputs(bpg, args, pin=True)
     if rank:
         full_h, aux_h = full_h.roll(rank, 0).pin_memory(), aux_h.roll(rank, 0).pin_memory()
     full_d, aux_d = full_h.to(dev), aux_h.to(dev)
@@ -473,19 +569,30 @@ def run_b200(args):
                     "sample": f"1 step on {ns} slices of the same workload (CPU oracle port, torch CPU fp32, {cores} threads, "
                               f"{dt:.1f} s)"}
 
+    par = None
+    if rank == 0 and world == 1 and not args.no_parity and args.reg == "Rec" and not args.lncc_weight and not args.mi_weight:
+        par = parity_block(args, net, dev)
+
     if rank == 0:
-        gb = args.batch * world
+        gb = bpg * world
         val = gb * args.steps / (ms_res / 1e3)
         e2e = gb * args.steps / (ms_e2e / 1e3)
-        inbytes = full_h.numel() * 8 + aux_h.numel() * 8
+        inbytes = (full_h.numel() * 8 + aux_h.numel() * 8) * world
         out = {"metric": METRIC, "value": round(val, 3), "unit": "slices/s", "n_gpus": world, "steps": args.steps,
                "warmup": max(args.warmup, args.min_warmup), "ms_per_step": round(ms_res / args.steps, 3), "higher_is_better": True,
-               "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-               "config": workload_config(args, world, ckpt),
+               "scaling": args.scaling, "vs_baseline": None,
+               "dtype": "bf16x3 (convs: BF16 hi/lo split operands, 3 tcgen05 MMAs, fp32 accumulate; fp32 storage and FFT)",
+               "data": "synthetic", "config": workload_config(args, world, ckpt),
                "e2e": {"value": round(e2e, 3), "unit": "slices/s", "h2d_bytes_per_step": inbytes, "d2h_bytes_per_step": 4,
                        "ms_per_step": round(ms_e2e / args.steps, 3)},
                "gpu_launches": int(launches), "clocks": clk, "roofline": roof, "roofline_fft_dc": roof_fft,
-               "cpu_baseline": cpu_base, "peak_mem_gb": round(peak_mem / 2 ** 30, 2), "impl": "b200"}
+               "cpu_baseline": cpu_base, "gpu_reference": gpu_reference_recorded(args), "parity": par,
+               "peak_mem_gb": round(peak_mem / 2 ** 30, 2), "impl": "b200"}
+        if world > 1:
+            gbk = getattr(net, "grad_buckets", None)
+            out["grad_allreduce"] = ({"mode": "bucketed by cascade, launched from autograd hooks during backward",
+                                      "buckets_launched_in_backward": gbk.launched} if gbk is not None
+                                     else {"mode": "one blocking flat all-reduce after backward"})
         if breakdown is not None:
             out["kernel_time_shares"] = {k: v["share_of_kernel_time"] for k, v in breakdown["classes"].items()}
             if args.breakdown:

@@ -87,8 +87,16 @@ int san_conv2d_wgrad(const float* x, const float* dy, float* dw, float* dbias, i
 int san_depth_to_space2(const float* x, float* y, int N, int Co, int H, int W, void* stream);
 int san_space_to_depth2(const float* y, float* x, int N, int Co, int H, int W, void* stream);
 
-/* ---- tcgen05 tensor-core convolutions (same call sites as above; BF16x3 split, fp32 TMEM accumulate) ----
- * Activations are staged as Xs[n][hl][kg][(H+2)*(W+2)][8] bf16 (hl = hi/lo halves of the fp32 value,
+/* ---- tcgen05 tensor-core convolutions (same call sites as above; 16-bit pair split, fp32 TMEM accumulate) ----
+ * Every fp32 operand value is staged as a PAIR of 16-bit numbers (hi, lo) and a product is accumulated as
+ * hi*hi + lo*hi + hi*lo (3 tcgen05.mma per K-step).  Two pair formats (`fmt` arguments below):
+ *   0  bf16 pair: hi = bf16(v), lo = bf16(v - hi): full fp32 exponent range, ~17 significant bits (gradients);
+ *   1  fp16 pair: z = s*v (static power-of-two s: 16 for activations, 256 for weights), hi = fp16(z),
+ *      lo = fp16(z - hi): 22 significant bits, fp32-class products, for operands of O(1) magnitude (normalised
+ *      activations, network inputs, weights); the kernels undo the scale exactly in their epilogues.
+ * For san_tc_conv / san_tc_wgrad `fmt` is a bit mask: bit 0 = the A operand (activations / dY) is an fp16 pair,
+ * bit 1 = the B operand (weights / X) is an fp16 pair; the two operands of one MMA may differ in format.
+ * Activations are staged as Xs[n][hl][kg][(H+2)*(W+2)][8] 16-bit (hl = hi/lo halves of the fp32 value,
  * kg = groups of 8 channels, Cin padded to 16, one-pixel zero border); weights as
  * Ws[nsplit][KS][taps][hl][2][Npad][8].  Element counts of the caller-allocated buffers: */
 long long san_tc_staged_act_elems(int N, int H, int W, int C);
@@ -97,6 +105,10 @@ int san_tc_supported(int H, int W, int Cin, int Cout, int K);
 /* host-only: strip geometry of san_tc_conv for this shape; out[16] = Cin_pad, KG, KS, nsplit, Npad, Wp, Hp, R, T,
  * S_alloc, strips, stages, acc_stages, a_bytes, b_bytes, smem_bytes (host pointer) */
 int san_tc_describe(int H, int W, int Cin, int Cout, int K, int* out);
+/* host-only: out[4] = dxn (1 = "DXN" form for 3x3 layers with <= 40 output channels: the three horizontal taps sit in
+ * the MMA N dimension, B row = dx * Np + co, and the epilogue adds the column blocks across neighbouring pixels),
+ * Np (Cout padded to 8), wtaps (weight blocks per K-step: 9, 3 or 1), xchg_bytes (host pointer) */
+int san_tc_describe_form(int H, int W, int Cin, int Cout, int K, int* out);
 /* Fused operand producer: up to 3 channel-concatenated sources (varnet.py:116 concat order),
  * each out = leaky_relu(a[plane]*(y - mu[plane]) + b[plane], slope) (a NULL = identity), i.e. the
  * InstanceNorm / BatchNorm + LeakyReLU of varnet.py:141-145 / unet.py:124-126 applied on the fly;
@@ -106,7 +118,7 @@ int san_tc_stage_act(void* xs, int N, int H, int W, int Cpad,
                      const float* y0, const float* mu0, const float* a0, const float* b0, float slope0, int C0, int mode0,
                      const float* y1, const float* mu1, const float* a1, const float* b1, float slope1, int C1, int mode1,
                      const float* y2, const float* mu2, const float* a2, const float* b2, float slope2, int C2, int mode2,
-                     void* stream);
+                     int fmt, void* stream);
 /* General form: an ordered list of terms; a term with accumulate = 0 starts a new channel range right after
  * the previous range (concatenation), accumulate = 1 ADDS onto the previous term's range (the residual sums of
  * unet.py:15-24: x + subnet(x) of two activated tensors).  At most 6 terms; host memory. */
@@ -120,17 +132,19 @@ typedef struct san_stage_term {
   int mode;         /* 0 direct, 1 avg-pool 2x2, 2 depth-to-space, 3 nearest x2 */
   int accumulate;
 } san_stage_term;
-int san_tc_stage_terms(void* xs, int N, int H, int W, int Cpad, const san_stage_term* terms, int nterms, void* stream);
+int san_tc_stage_terms(void* xs, int N, int H, int W, int Cpad, const san_stage_term* terms, int nterms, int fmt,
+                       void* stream);
 /* x[N,C,H,W] = hi + lo of a staged tensor (input of the fp32 weight-gradient kernel) */
-int san_tc_unstage_act(const void* xs, float* x, int N, int C, int H, int W, void* stream);
+int san_tc_unstage_act(const void* xs, float* x, int N, int C, int H, int W, int fmt, void* stream);
 /* OIHW fp32 -> staged hi/lo for images of H x W (the output-channel split depends on the strip geometry);
  * dgrad = 1 stages the flipped, transposed filter so that the data gradient is san_tc_conv run on the
  * staged dY (Cout/Cin below are always the ORIGINAL ones of the OIHW tensor) */
-int san_tc_stage_weights(const float* w, void* ws, int H, int W, int Cout, int Cin, int K, int dgrad, void* stream);
+int san_tc_stage_weights(const float* w, void* ws, int H, int W, int Cout, int Cin, int K, int dgrad, int fmt,
+                         void* stream);
 /* y[N,Cout,H,W] (+ bias) = conv2d(staged x, staged w), stride 1, padding K/2, K in {1,3};
  * Cin/Cout are the channel counts of THIS launch (for dgrad: Cin = original Cout, Cout = original Cin) */
 int san_tc_conv(const void* xs, const void* ws, const float* bias, float* y, int N, int H, int W, int Cin, int Cout,
-                int K, long long y_bs, void* stream);
+                int K, long long y_bs, int fmt, void* stream);
 
 /* dW[Cout,Cin,K,K] (and dbias[Cout] from the fp32 dy, both optional-bias) from the staged dY and the staged
  * input of the forward conv: tcgen05 GEMM over the pixel dimension, MN-major operands, BF16x3 */
@@ -139,7 +153,7 @@ int san_tc_wgrad_supported(int H, int W, int Cin, int Cout, int K);
  * nchunks, Wp, PS, range0, range_len (host pointer) */
 int san_tc_wgrad_describe(int H, int W, int Cin, int Cout, int K, int* out);
 int san_tc_wgrad(const void* dys, const void* xs, float* dw, float* dbias, const float* dy, int N, int H, int W, int Cin,
-                 int Cout, int K, void* stream);
+                 int Cout, int K, int fmt, void* stream);
 
 /* ---- normalisation / activation / resampling (varnet.py:98,139-146,235,257-273; unet.py:119-140) ---- */
 /* per-plane mean and centred sum of squares (two-pass) */

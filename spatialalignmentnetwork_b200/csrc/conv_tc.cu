@@ -19,6 +19,15 @@
 // ADDRESS of the same staged tile -- no im2col copies, each input element is loaded once per
 // strip.  Columns x >= W (2 per row) are computed and dropped (0.6 % waste at W = 320).
 //
+// Narrow layers ("DXN" form, 3x3 with <= 40 output channels: the full- and half-resolution layers that carry the
+// step): an MMA with N = 32 reads its 4 KB A tile from shared memory in 32 clk but keeps the tensor pipe busy for
+// 16, and the 9 taps x 3 hi/lo products re-read A 27 times per K-step.  There the three horizontal taps are moved
+// into the MMA's N dimension: B = [W(dy,dx=0) | W(dy,dx=1) | W(dy,dx=2)] (N = 3*pad8(Cout), padded to 16), one A
+// window per filter ROW, so A is read 9 times per K-step (and N = 80 balances operand read and tensor time).
+// The accumulator then holds E_dx[q] = sum_dy A[q + dy*Wp] W[dy][dx], and y[q] = E_0[q] + E_1[q+1] + E_2[q+2]:
+// the epilogue adds the three column blocks across neighbouring TMEM lanes (warp shuffles; the two lanes at a
+// 32-lane quarter boundary are completed through a small shared-memory exchange).
+//
 // Work unit = (image n, strip of R rows, N-split); persistent CTAs walk units.  Warp roles:
 //   warp 0      TMA producer  (bulk copies of the A row span + the B weight block per K-step)
 //   warp 1      TMEM allocator + single-thread tcgen05.mma issuer
@@ -46,7 +55,54 @@ struct TcGeom {
   int R, T, S_alloc;       // rows per strip, 128-pixel M-tiles per strip, smem slots per (hl, kk)
   int strips, stages, acc_stages;
   int a_bytes, b_bytes, stage_bytes, smem_bytes;
+  int dxn, Np;             // DXN form: horizontal taps in the MMA N dimension, Np = Cout padded to 8 (Npad = pad16(3*Np))
+  int wtaps;               // weight blocks per K-step: 9 (3x3), 3 (DXN: one per filter row) or 1 (1x1)
+  int xchg_bytes;          // DXN: shared-memory exchange area of the epilogue (quarter-boundary lanes)
 };
+
+inline int pad8(int c) { return (c + 7) / 8 * 8; }
+int tc_env_int(const char* name, int dflt) {
+  const char* e = getenv(name);
+  return e ? atoi(e) : dflt;
+}
+// SAN_TC_DXN = 0 disables the DXN form (A/B runs); SAN_TC_DXN_R = r forces its strip height (tuning runs)
+int tc_dxn_enabled() { static const int v = tc_env_int("SAN_TC_DXN", 1); return v; }
+int tc_dxn_force_r() { static const int v = tc_env_int("SAN_TC_DXN_R", 0); return v; }
+
+// DXN geometry; false if the layer does not qualify.  The strip height minimises a cycle estimate per output row:
+// MMA phase (9 MMAs per tile and K-step, each max(operand read at 128 B/clk, tensor N/2 clk)) against the epilogue's
+// TMEM read (64 B/clk per SM), overlapped only when the accumulators are double-buffered.
+bool tc_geometry_dxn(int H, int W, int Cin, int Cout, TcGeom* g) {
+  const int Np = pad8(Cout);
+  if (Np > 40) return false;
+  const int Ndx = pad16(3 * Np), Wp = W + 2, KS = pad16(Cin) / 16;
+  const int b_bytes = 3 * 4 * Ndx * 16;
+  const int force = tc_dxn_force_r();
+  int bestR = 0;
+  double best = 1e30;
+  for (int R = 1; R <= H; ++R) {
+    const int T = (R * Wp + 127) / 128;
+    if (T * Ndx > 512) break;
+    const int S = ((128 * T + 2 * Wp + 2) + 7) / 8 * 8;
+    const int xchg = (80 * T * Np + 127) / 128 * 128;
+    if (2 * (4 * S * 16 + b_bytes) + TC_SMEM_HEADER + xchg > TC_SMEM_MAX) break;
+    if (force && R != force) continue;
+    const double mma = (double)T * KS * 9.0 * fmax((4096.0 + Ndx * 32.0) / 128.0, Ndx / 2.0);
+    const double epi = (double)T * Ndx * 8.0;
+    const bool dbl = 2 * T * Ndx <= 512;
+    const int strips = (H + R - 1) / R;
+    const double per_row = (dbl ? fmax(mma, epi) : mma + epi) * strips / (double)H * (1.0 + 0.1 / R);   // mild halo penalty
+    if (per_row < best - 1e-9) { best = per_row; bestR = R; }
+  }
+  if (!bestR) return false;
+  g->dxn = 1; g->Np = Np; g->wtaps = 3;
+  g->nsplit = 1; g->Npad = Ndx; g->b_bytes = b_bytes;
+  g->R = bestR;
+  g->T = (g->R * Wp + 127) / 128;
+  g->xchg_bytes = (80 * g->T * Np + 127) / 128 * 128;
+  return true;
+}
+
 
 // Rows per strip for a given output-channel split; 0 if nothing fits (shared memory / TMEM columns).
 static int tc_pick_rows(int H, int W, int K, int Npad, int b_bytes) {
@@ -74,26 +130,29 @@ bool tc_geometry(int H, int W, int Cin, int Cout, int K, TcGeom* g) {
   g->Cin_pad = pad16(Cin); g->KG = g->Cin_pad / 8; g->KS = g->Cin_pad / 16;
   g->Wp = W + 2; g->Hp = H + 2; g->PS = g->Hp * g->Wp;
   const int ntaps = K * K;
-  // split the output channels until a strip (A rows + the weight block of one K-step, two stages) fits
-  int bestR = 0;
-  for (g->nsplit = (pad16(Cout) + TC_NMAX - 1) / TC_NMAX; g->nsplit <= 16; ++g->nsplit) {
-    g->Npad = pad16((Cout + g->nsplit - 1) / g->nsplit);
-    g->b_bytes = ntaps * 4 * g->Npad * 16;
-    bestR = tc_pick_rows(H, W, K, g->Npad, g->b_bytes);
-    if (bestR || g->Npad == 16) break;
+  g->dxn = 0; g->Np = 0; g->wtaps = ntaps; g->xchg_bytes = 0;
+  if (!(K == 3 && tc_dxn_enabled() && tc_geometry_dxn(H, W, Cin, Cout, g))) {
+    // split the output channels until a strip (A rows + the weight block of one K-step, two stages) fits
+    int bestR = 0;
+    for (g->nsplit = (pad16(Cout) + TC_NMAX - 1) / TC_NMAX; g->nsplit <= 16; ++g->nsplit) {
+      g->Npad = pad16((Cout + g->nsplit - 1) / g->nsplit);
+      g->b_bytes = ntaps * 4 * g->Npad * 16;
+      bestR = tc_pick_rows(H, W, K, g->Npad, g->b_bytes);
+      if (bestR || g->Npad == 16) break;
+    }
+    if (bestR == 0) return false;
+    g->R = bestR;
+    g->T = (g->R * g->Wp + 127) / 128;
   }
-  if (bestR == 0) return false;
-  g->R = bestR;
-  g->T = (g->R * g->Wp + 127) / 128;
   g->S_alloc = ((128 * g->T + 2 * g->Wp + 2) + 7) / 8 * 8;
   g->a_bytes = 4 * g->S_alloc * 16;
   g->stage_bytes = g->a_bytes + g->b_bytes;
-  g->stages = (TC_SMEM_MAX - TC_SMEM_HEADER) / g->stage_bytes;
+  g->stages = (TC_SMEM_MAX - TC_SMEM_HEADER - g->xchg_bytes) / g->stage_bytes;
   if (g->stages > 4) g->stages = 4;
   if (g->stages < 2) return false;
   g->strips = (H + g->R - 1) / g->R;
   g->acc_stages = (2 * g->T * g->Npad <= 512) ? 2 : 1;
-  g->smem_bytes = TC_SMEM_HEADER + g->stages * g->stage_bytes;
+  g->smem_bytes = TC_SMEM_HEADER + g->xchg_bytes + g->stages * g->stage_bytes;
   if (g->smem_bytes < 120 * 1024) g->smem_bytes = 120 * 1024;  // one CTA per SM (each allocates all 512 TMEM columns)
   return true;
 }
@@ -106,6 +165,8 @@ struct ConvTcParams {
   long long y_bs;
   int N, H, W, Cout, ntaps;
   int nunits;
+  int fmt;                  // TC_FMT_* bits: which operands are fp16 pairs (else bf16 pairs)
+  float out_scale;          // exact inverse of the operands' static scales
   TcGeom g;
 };
 
@@ -114,7 +175,7 @@ template <int NTAPS>
 __device__ __forceinline__ void mma_issue_loop(const ConvTcParams& p, const TcGeom& g, uint32_t tmem_base,
                                                uint32_t stage0, uint32_t bar_full, uint32_t bar_empty,
                                                uint32_t bar_accf, uint32_t bar_acce) {
-  const uint32_t idesc = umma_idesc_bf16(128, g.Npad);
+  const uint32_t idesc = umma_idesc_16(128, g.Npad, p.fmt);
   // descriptor templates (address field = 0) and per-tap offsets in 16 B units
   const uint64_t a_tmpl = umma_desc(0, (uint32_t)g.S_alloc * 16, 128);
   const uint64_t b_tmpl = umma_desc(0, (uint32_t)g.Npad * 16, 128);
@@ -122,7 +183,8 @@ __device__ __forceinline__ void mma_issue_loop(const ConvTcParams& p, const TcGe
   const uint32_t a_lo0 = (uint32_t)a_tmpl, b_lo0 = (uint32_t)b_tmpl;
   uint32_t tap_off[NTAPS];
 #pragma unroll
-  for (int tap = 0; tap < NTAPS; ++tap) tap_off[tap] = (NTAPS == 9) ? (uint32_t)((tap / 3) * g.Wp + (tap % 3)) : (uint32_t)(g.Wp + 1);
+  for (int tap = 0; tap < NTAPS; ++tap)     // 9: (dy, dx) windows; 3: DXN form, one window per filter row; 1: 1x1 centre
+    tap_off[tap] = (NTAPS == 9) ? (uint32_t)((tap / 3) * g.Wp + (tap % 3)) : (NTAPS == 3) ? (uint32_t)(tap * g.Wp) : (uint32_t)(g.Wp + 1);
   const uint32_t a_losplit = 2u * g.S_alloc;     // hi -> lo half of A, 16 B units
   const uint32_t b_losplit = 2u * g.Npad;        // hi -> lo half of B
   const uint32_t b_tapstride = 4u * g.Npad;
@@ -171,7 +233,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const ConvTcPara
   const uint32_t hdr = smem_u32(smem);
   const uint32_t bar_full = hdr, bar_empty = hdr + 32, bar_accf = hdr + 64, bar_acce = hdr + 80;
   volatile uint32_t* tmem_slot = (volatile uint32_t*)(smem + 96);
-  const uint32_t stage0 = hdr + TC_SMEM_HEADER;
+  const uint32_t stage0 = hdr + TC_SMEM_HEADER + (uint32_t)g.xchg_bytes;
 
   if (warp == 0 && lane == 0) {
     for (int i = 0; i < g.stages; ++i) { mbar_init(bar_full + 8 * i, 1); mbar_init(bar_empty + 8 * i, 1); }
@@ -228,7 +290,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const ConvTcPara
     // shared-memory descriptors are built once and advanced by adding 16-byte-unit offsets to
     // their low word; taps and the three hi/lo products are fully unrolled.
     // (whole warp: the loops are warp-uniform, one elected lane issues)
-    if (p.ntaps == 9) mma_issue_loop<9>(p, g, tmem_base, stage0, bar_full, bar_empty, bar_accf, bar_acce);
+    if (g.wtaps == 9) mma_issue_loop<9>(p, g, tmem_base, stage0, bar_full, bar_empty, bar_accf, bar_acce);
+    else if (g.wtaps == 3) mma_issue_loop<3>(p, g, tmem_base, stage0, bar_full, bar_empty, bar_accf, bar_acce);
     else mma_issue_loop<1>(p, g, tmem_base, stage0, bar_full, bar_empty, bar_accf, bar_acce);
   } else {
     // ================================ epilogue ====================================
@@ -248,6 +311,65 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const ConvTcPara
       mbar_wait(bar_accf + 8 * as, aph);
       tc_fence_after();
       float* yn = p.y + (long long)n * p.y_bs;
+      if (g.dxn) {
+        // ---- DXN form: columns = (dx, co); y[q] = E_0[q] + E_1[q+1] + E_2[q+2] across TMEM lanes
+        const int Np = g.Np;
+        float* xch = (float*)(smem + TC_SMEM_HEADER);      // [T][4 quarters][5][Np]
+        for (int t = egrp; t < g.T; t += EG) {
+          const int q = t * 128 + wq * 32 + lane;
+          const int r = q / g.Wp, x = q - r * g.Wp;
+          const int yy = y0 + r;
+          const bool valid = (r < g.R) && (x < p.W) && (yy < p.H) && lane < 30;
+          float* dst = yn + (long long)yy * p.W + x;
+          float* xc = xch + (size_t)((t * 4 + wq) * 5) * Np;
+          const uint32_t trow = tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)(as * g.T * g.Npad + t * g.Npad);
+          for (int c0 = 0; c0 < Np; c0 += 8) {
+            float e0[8], e1[8], e2[8];
+            tc_ld8x3(trow + c0, trow + Np + c0, trow + 2 * Np + c0, e0, e1, e2);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const int c = c0 + j;
+              const float s1 = __shfl_down_sync(0xffffffffu, e1[j], 1);
+              const float s2 = __shfl_down_sync(0xffffffffu, e2[j], 2);
+              const float pe = e0[j] + s1;          // complete up to E_2 for lanes <= 30
+              if (lane == 0) { xc[c] = e1[j]; xc[Np + c] = e2[j]; }
+              else if (lane == 1) xc[2 * Np + c] = e2[j];
+              else if (lane == 30) xc[3 * Np + c] = pe;
+              else if (lane == 31) xc[4 * Np + c] = e0[j];
+              if (valid && c < p.Cout) {
+                const float bv = p.bias ? __ldg(p.bias + c) : 0.f;
+                dst[(long long)c * HW] = fmaf(pe + s2, p.out_scale, bv);
+              }
+            }
+          }
+        }
+        // the accumulators have been read: hand them back to the MMA warp before the lane fix-up
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_acce + 8 * as);
+        if (++as == g.acc_stages) { as = 0; aph ^= 1; }
+        asm volatile("bar.sync 1, %0;" ::"n"(TC_EPI_WARPS * 32) : "memory");
+        // lanes 30 / 31 of every quarter: E_2 (and E_1) of the next quarter's lanes 0 / 1
+        for (int t = egrp; t < g.T; t += EG) {
+          const int tn = (wq == 3) ? t + 1 : t, wn = (wq == 3) ? 0 : wq + 1;
+          if (tn >= g.T) continue;
+          const float* xc = xch + (size_t)((t * 4 + wq) * 5) * Np;
+          const float* xn = xch + (size_t)((tn * 4 + wn) * 5) * Np;
+          for (int idx = lane; idx < 2 * Np; idx += 32) {
+            const int l = idx >= Np ? 1 : 0, c = idx - l * Np;
+            const int q = t * 128 + wq * 32 + 30 + l;
+            const int r = q / g.Wp, x = q - r * g.Wp;
+            const int yy = y0 + r;
+            if (r < g.R && x < p.W && yy < p.H && c < p.Cout) {
+              const float v = l ? (xc[4 * Np + c] + xn[c]) + xn[2 * Np + c] : xc[3 * Np + c] + xn[Np + c];
+              const float bv = p.bias ? __ldg(p.bias + c) : 0.f;
+              yn[(long long)c * HW + (long long)yy * p.W + x] = fmaf(v, p.out_scale, bv);
+            }
+          }
+        }
+        asm volatile("bar.sync 1, %0;" ::"n"(TC_EPI_WARPS * 32) : "memory");   // exchange area free for the next unit
+        continue;
+      }
       for (int t = egrp; t < g.T; t += EG) {
         const int q = t * 128 + wq * 32 + lane;
         const int r = q / g.Wp, x = q - r * g.Wp;
@@ -264,7 +386,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const ConvTcPara
               const int c = c0 + j;
               if (c < c_cnt) {
                 const float bv = p.bias ? __ldg(p.bias + c_base + c) : 0.f;
-                dst[(long long)(c_base + c) * HW] = v[j] + bv;
+                dst[(long long)(c_base + c) * HW] = fmaf(v[j], p.out_scale, bv);
               }
             }
           }
@@ -302,6 +424,7 @@ struct StageArgs {
   int nterms;
   __nv_bfloat16* xs;
   int N, H, W, Wp, PS, KG;
+  int fmt;           // 0: bf16 pairs (gradients), 1: fp16 pairs scaled by TC_SX (forward operands)
 };
 
 __device__ __forceinline__ float act1(float v, float mu, float a, float b, float slope) {
@@ -340,15 +463,16 @@ __device__ __forceinline__ SlotOffs slot_offsets(int slot, const StageArgs& A, i
 __device__ __forceinline__ int pick_off(int mode, const SlotOffs& o) {
   return mode == 0 ? o.off0 : (mode == 2 ? o.offs2 : (mode == 3 ? o.offu : 0));
 }
-__device__ __forceinline__ void store_split(__nv_bfloat16* xs, long long o_hi, long long o_lo, int slot, const float* v) {
+__device__ __forceinline__ void store_split(__nv_bfloat16* xs, long long o_hi, long long o_lo, int slot, const float* v,
+                                            bool f16) {
   uint32_t hw[4], lw[4];
 #pragma unroll
   for (int j = 0; j < 4; ++j) {
-    const __nv_bfloat16 h0 = __float2bfloat16_rn(v[2 * j]), h1 = __float2bfloat16_rn(v[2 * j + 1]);
-    const __nv_bfloat16 l0 = __float2bfloat16_rn(v[2 * j] - __bfloat162float(h0));
-    const __nv_bfloat16 l1 = __float2bfloat16_rn(v[2 * j + 1] - __bfloat162float(h1));
-    hw[j] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
-    lw[j] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
+    unsigned short h0, l0, h1, l1;
+    split16(v[2 * j], f16, TC_SX, h0, l0);
+    split16(v[2 * j + 1], f16, TC_SX, h1, l1);
+    hw[j] = (uint32_t)h0 | ((uint32_t)h1 << 16);
+    lw[j] = (uint32_t)l0 | ((uint32_t)l1 << 16);
   }
   *(uint4*)(xs + (o_hi + slot) * 8) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
   *(uint4*)(xs + (o_lo + slot) * 8) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
@@ -387,6 +511,7 @@ __global__ void __launch_bounds__(256, 3) stage_act_kernel(const StageArgs A) {
   __syncthreads();
   const int kmax = s_kmax;
   const bool pooled = s_pool != 0;
+  const bool f16 = A.fmt != 0;
   const long long o_hi = ((long long)(n * 2 + 0) * A.KG + kg) * A.PS;
   const long long o_lo = ((long long)(n * 2 + 1) * A.KG + kg) * A.PS;
   const int Wh = A.W / 2, HWq = (A.H / 2) * Wh, W2 = 2 * A.W;
@@ -436,8 +561,8 @@ __global__ void __launch_bounds__(256, 3) stage_act_kernel(const StageArgs A) {
     }
 #pragma unroll
     for (int j = 0; j < 8; ++j) { vA[j] = oA.inb ? vA[j] : 0.f; vB[j] = oB.inb ? vB[j] : 0.f; }
-    store_split(A.xs, o_hi, o_lo, slot, vA);
-    if (slotB < A.PS) store_split(A.xs, o_hi, o_lo, slotB, vB);
+    store_split(A.xs, o_hi, o_lo, slot, vA, f16);
+    if (slotB < A.PS) store_split(A.xs, o_hi, o_lo, slotB, vB, f16);
   }
   // zero lead-in / trailing slack of the buffer (see TC_LEAD / TC_TRAIL)
   if (blockIdx.x == 0 && blockIdx.y == 0) {
@@ -449,7 +574,7 @@ __global__ void __launch_bounds__(256, 3) stage_act_kernel(const StageArgs A) {
 
 // staged activations back to fp32 NCHW (x = hi + lo): feeds the fp32 weight-gradient kernel
 __global__ void __launch_bounds__(256) unstage_act_kernel(const __nv_bfloat16* __restrict__ xs, float* __restrict__ x,
-                                                          int N, int C, int H, int W, int KG) {
+                                                          int N, int C, int H, int W, int KG, int fmt) {
   const int Wp = W + 2, PS = (H + 2) * Wp;
   const long long total = (long long)N * C * H * W;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
@@ -463,7 +588,7 @@ __global__ void __launch_bounds__(256) unstage_act_kernel(const __nv_bfloat16* _
     const int slot = (h + 1) * Wp + w + 1;
     const long long o_hi = (((long long)(n * 2 + 0) * KG + (c >> 3)) * PS + slot) * 8 + (c & 7);
     const long long o_lo = (((long long)(n * 2 + 1) * KG + (c >> 3)) * PS + slot) * 8 + (c & 7);
-    x[i] = __bfloat162float(xs[o_hi]) + __bfloat162float(xs[o_lo]);
+    x[i] = unsplit16(__bfloat16_as_ushort(xs[o_hi]), __bfloat16_as_ushort(xs[o_lo]), fmt != 0, 1.f / TC_SX);
   }
 }
 
@@ -471,9 +596,35 @@ __global__ void __launch_bounds__(256) unstage_act_kernel(const __nv_bfloat16* _
 // dgrad = 1: the transposed, spatially flipped filter (data gradient = the same conv run on dY):
 // "output" channel = original ci, "input" channel = original co.
 __global__ void stage_weights_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ ws, int Cout, int Cin,
-                                     int KK, int dgrad, int nsplit, int KS, int Npad) {
+                                     int KK, int dgrad, int nsplit, int KS, int Npad, int fmt, int dxn_np) {
   const int Co_k = dgrad ? Cin : Cout;   // kernel-view output channels
   const int Ci_k = dgrad ? Cout : Cin;   // kernel-view input channels
+  if (dxn_np) {
+    // DXN form: Ws[KS][dy][hl][kk][Npad][8], B row nn = dx * Np + co  (3x3 only, nsplit = 1)
+    const long long total = (long long)KS * 3 * 2 * 2 * Npad * 8;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+         i += (long long)gridDim.x * blockDim.x) {
+      long long t = i;
+      const int j = (int)(t % 8); t /= 8;
+      const int nn = (int)(t % Npad); t /= Npad;
+      const int kk = (int)(t % 2); t /= 2;
+      const int hl = (int)(t % 2); t /= 2;
+      const int dy = (int)(t % 3);
+      const int ks = (int)(t / 3);
+      const int dx = nn / dxn_np, co = nn - dx * dxn_np;
+      const int ci = ks * 16 + kk * 8 + j;
+      const int tap = dy * 3 + dx;
+      float v = 0.f;
+      if (dx < 3 && co < Co_k && ci < Ci_k) {
+        if (!dgrad) v = w[((long long)co * Cin + ci) * 9 + tap];
+        else v = w[((long long)ci * Cin + co) * 9 + (8 - tap)];
+      }
+      unsigned short hi, lo;
+      split16(v, fmt != 0, TC_SW, hi, lo);
+      ws[i] = __ushort_as_bfloat16(hl ? lo : hi);
+    }
+    return;
+  }
   const long long total = (long long)nsplit * KS * KK * 2 * 2 * Npad * 8;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
@@ -492,8 +643,9 @@ __global__ void stage_weights_kernel(const float* __restrict__ w, __nv_bfloat16*
       if (!dgrad) v = w[((long long)co * Cin + ci) * KK + tap];
       else v = w[((long long)ci * Cin + co) * KK + (KK - 1 - tap)];
     }
-    const __nv_bfloat16 hi = __float2bfloat16_rn(v);
-    ws[i] = hl ? __float2bfloat16_rn(v - __bfloat162float(hi)) : hi;
+    unsigned short hi, lo;
+    split16(v, fmt != 0, TC_SW, hi, lo);
+    ws[i] = __ushort_as_bfloat16(hl ? lo : hi);
   }
 }
 
@@ -514,7 +666,7 @@ long long san_tc_staged_act_elems(int N, int H, int W, int C) {
 long long san_tc_staged_weight_elems(int H, int W, int Cout, int Cin, int K) {
   TcGeom g;
   if (!tc_geometry(H, W, Cin, Cout, K, &g)) return -1;
-  return (long long)g.nsplit * g.KS * K * K * 4 * g.Npad * 8;
+  return (long long)g.nsplit * g.KS * g.wtaps * 4 * g.Npad * 8;
 }
 
 // Host-only: the strip geometry the kernel would use, for tests / tooling.  out[0..15] = Cin_pad, KG, KS, nsplit,
@@ -528,12 +680,23 @@ int san_tc_describe(int H, int W, int Cin, int Cout, int K, int* out) {
   return SAN_OK;
 }
 
+// Host-only: which formulation the kernel uses.  out[0..3] = dxn (1: horizontal taps in the MMA N dimension), Np (Cout padded
+// to 8 in that form), wtaps (weight blocks per K-step: 9, 3 or 1), xchg_bytes (epilogue exchange area).
+int san_tc_describe_form(int H, int W, int Cin, int Cout, int K, int* out) {
+  TcGeom g;
+  if (!out || !tc_geometry(H, W, Cin, Cout, K, &g)) return SAN_ERR_UNSUPPORTED;
+  out[0] = g.dxn; out[1] = g.Np; out[2] = g.wtaps; out[3] = g.xchg_bytes;
+  return SAN_OK;
+}
+
 int san_tc_supported(int H, int W, int Cin, int Cout, int K) {
   TcGeom g;
   return tc_geometry(H, W, Cin, Cout, K, &g) ? 1 : 0;
 }
 
-static int launch_stage(StageArgs& A, void* xs, int N, int H, int W, int Cpad, cudaStream_t st) {
+static int launch_stage(StageArgs& A, void* xs, int N, int H, int W, int Cpad, int fmt, cudaStream_t st) {
+  SAN_CHECK_ARG(fmt == 0 || fmt == 1, "san_tc_stage: fmt must be 0 (bf16 pairs) or 1 (fp16 pairs)");
+  A.fmt = fmt;
   int ctot = 0;
   for (int i = 0; i < A.nterms; ++i) {
     SAN_CHECK_ARG(A.s[i].y && A.s[i].C > 0, "san_tc_stage: term %d has no tensor / channels", i);
@@ -554,7 +717,8 @@ static int launch_stage(StageArgs& A, void* xs, int N, int H, int W, int Cpad, c
   return SAN_OK;
 }
 
-int san_tc_stage_terms(void* xs, int N, int H, int W, int Cpad, const san_stage_term* terms, int nterms, void* stream) {
+int san_tc_stage_terms(void* xs, int N, int H, int W, int Cpad, const san_stage_term* terms, int nterms, int fmt,
+                       void* stream) {
   SAN_CHECK_ARG(xs && terms && nterms >= 1 && nterms <= STAGE_MAX_TERMS && N > 0 && H > 0 && W > 0 && Cpad % 16 == 0,
                 "san_tc_stage_terms: bad args");
   StageArgs A{};
@@ -569,48 +733,51 @@ int san_tc_stage_terms(void* xs, int N, int H, int W, int Cpad, const san_stage_
     c_prev = c0;
     if (!t.accumulate) c_next = c0 + t.C;
   }
-  return launch_stage(A, xs, N, H, W, Cpad, (cudaStream_t)stream);
+  return launch_stage(A, xs, N, H, W, Cpad, fmt, (cudaStream_t)stream);
 }
 
 int san_tc_stage_act(void* xs, int N, int H, int W, int Cpad,
                      const float* y0, const float* mu0, const float* a0, const float* b0, float slope0, int C0, int mode0,
                      const float* y1, const float* mu1, const float* a1, const float* b1, float slope1, int C1, int mode1,
                      const float* y2, const float* mu2, const float* a2, const float* b2, float slope2, int C2, int mode2,
-                     void* stream) {
+                     int fmt, void* stream) {
   SAN_CHECK_ARG(xs && y0 && N > 0 && H > 0 && W > 0 && Cpad % 16 == 0 && C0 > 0, "san_tc_stage_act: bad args");
   StageArgs A{};
   A.s[0] = StageTerm{y0, mu0, a0, b0, slope0, C0, mode0, 0};
   A.nterms = 1;
   if (y1) { A.s[1] = StageTerm{y1, mu1, a1, b1, slope1, C1, mode1, C0}; A.nterms = 2; }
   if (y2) { SAN_CHECK_ARG(y1, "san_tc_stage_act: source 2 without source 1"); A.s[2] = StageTerm{y2, mu2, a2, b2, slope2, C2, mode2, C0 + C1}; A.nterms = 3; }
-  return launch_stage(A, xs, N, H, W, Cpad, (cudaStream_t)stream);
+  return launch_stage(A, xs, N, H, W, Cpad, fmt, (cudaStream_t)stream);
 }
 
-int san_tc_unstage_act(const void* xs, float* x, int N, int C, int H, int W, void* stream) {
+int san_tc_unstage_act(const void* xs, float* x, int N, int C, int H, int W, int fmt, void* stream) {
   SAN_CHECK_ARG(xs && x && N > 0 && C > 0 && H > 0 && W > 0, "san_tc_unstage_act: bad args");
   const long long total = (long long)N * C * H * W;
   unstage_act_kernel<<<ew_blocks(total), 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)xs + TC_LEAD, x, N, C, H, W,
-                                                                         pad16(C) / 8);
+                                                                         pad16(C) / 8, fmt);
   SAN_LAUNCH_CHECK();
   return SAN_OK;
 }
 
-int san_tc_stage_weights(const float* w, void* ws, int H, int W, int Cout, int Cin, int K, int dgrad, void* stream) {
+int san_tc_stage_weights(const float* w, void* ws, int H, int W, int Cout, int Cin, int K, int dgrad, int fmt,
+                         void* stream) {
   SAN_CHECK_ARG(w && ws && Cout > 0 && Cin > 0 && (K == 1 || K == 3), "san_tc_stage_weights: bad args");
   TcGeom g;
   const int Co_k = dgrad ? Cin : Cout, Ci_k = dgrad ? Cout : Cin;
   SAN_CHECK_ARG(tc_geometry(H, W, Ci_k, Co_k, K, &g), "san_tc_stage_weights: unsupported shape");
-  const long long total = (long long)g.nsplit * g.KS * K * K * 4 * g.Npad * 8;
+  const long long total = (long long)g.nsplit * g.KS * g.wtaps * 4 * g.Npad * 8;
   stage_weights_kernel<<<ew_blocks(total), 256, 0, (cudaStream_t)stream>>>(w, (__nv_bfloat16*)ws, Cout, Cin, K * K, dgrad,
-                                                                           g.nsplit, g.KS, g.Npad);
+                                                                           g.nsplit, g.KS, g.Npad, fmt, g.dxn ? g.Np : 0);
   SAN_LAUNCH_CHECK();
   return SAN_OK;
 }
 
 int san_tc_conv(const void* xs, const void* ws, const float* bias, float* y, int N, int H, int W, int Cin, int Cout,
-                int K, long long y_bs, void* stream) {
-  SAN_CHECK_ARG(xs && ws && y && N > 0 && H > 0 && W > 0 && Cin > 0 && Cout > 0, "san_tc_conv: bad args");
+                int K, long long y_bs, int fmt, void* stream) {
+  SAN_CHECK_ARG(xs && ws && y && N > 0 && H > 0 && W > 0 && Cin > 0 && Cout > 0 && fmt >= 0 && fmt <= 3, "san_tc_conv: bad args");
   ConvTcParams p{};
+  p.fmt = fmt;
+  p.out_scale = ((fmt & TC_FMT_A_F16) ? 1.f / TC_SX : 1.f) * ((fmt & TC_FMT_B_F16) ? 1.f / TC_SW : 1.f);
   SAN_CHECK_ARG(tc_geometry(H, W, Cin, Cout, K, &p.g), "san_tc_conv: unsupported shape H=%d W=%d Cin=%d Cout=%d K=%d", H, W,
                 Cin, Cout, K);
   p.xs = (const __nv_bfloat16*)xs + TC_LEAD; p.ws = (const __nv_bfloat16*)ws; p.bias = bias; p.y = y;

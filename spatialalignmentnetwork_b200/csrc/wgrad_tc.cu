@@ -90,6 +90,8 @@ struct WgParams {
   float* dw;                  // [Cout][Cin][K][K], pre-zeroed
   int N, Cin, Cout, K;
   int ngroups, ctas_per_group;
+  int fmt;                    // TC_FMT_* bits: A = dY pair format, B = X pair format
+  float out_scale;
   WgGeom g;
 };
 
@@ -186,7 +188,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_tc_kernel(const WgParams 
     // whole warp runs the (warp-uniform) loops; one elected lane issues the tcgen05 instructions
     const bool stacked = 2 * kga <= 16;                // [hi; lo] of dY as one A operand
     const int M = (2 * kga <= 8) ? 64 : 128;
-    const uint32_t idesc = umma_idesc_bf16(M, g.Nn, /*mn_major=*/1);
+    const uint32_t idesc = umma_idesc_16(M, g.Nn, p.fmt, /*mn_major=*/1);
     // MN-major, no swizzle: LBO = 128 B between 8-slot K groups, SBO = one staged plane between channel groups
     const uint64_t a_tmpl = umma_desc(0, 128, (uint32_t)g.KC * 16);
     const uint64_t b_tmpl = umma_desc(0, 128, (uint32_t)g.XS * 16);
@@ -244,7 +246,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_tc_kernel(const WgParams 
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
               const int ci = nc * g.Nn + c0 + j;
-              if (ci < p.Cin) atomicAdd(p.dw + ((long long)co * p.Cin + ci) * KK + tap, v[j]);
+              if (ci < p.Cin) atomicAdd(p.dw + ((long long)co * p.Cin + ci) * KK + tap, v[j] * p.out_scale);
             }
           }
         }
@@ -290,9 +292,11 @@ int san_tc_wgrad_supported(int H, int W, int Cin, int Cout, int K) {
 }
 
 int san_tc_wgrad(const void* dys, const void* xs, float* dw, float* dbias, const float* dy, int N, int H, int W, int Cin,
-                 int Cout, int K, void* stream) {
-  SAN_CHECK_ARG(dys && xs && dw && N > 0 && H > 0 && W > 0 && Cin > 0 && Cout > 0, "san_tc_wgrad: bad args");
+                 int Cout, int K, int fmt, void* stream) {
+  SAN_CHECK_ARG(dys && xs && dw && N > 0 && H > 0 && W > 0 && Cin > 0 && Cout > 0 && fmt >= 0 && fmt <= 3, "san_tc_wgrad: bad args");
   WgParams p{};
+  p.fmt = fmt;   // A = staged dY, B = staged X; both were staged as ACTIVATIONS (scale TC_SX when an fp16 pair)
+  p.out_scale = ((fmt & TC_FMT_A_F16) ? 1.f / TC_SX : 1.f) * ((fmt & TC_FMT_B_F16) ? 1.f / TC_SX : 1.f);
   SAN_CHECK_ARG(wg_geometry(H, W, Cin, Cout, K, &p.g), "san_tc_wgrad: unsupported shape H=%d W=%d Cin=%d Cout=%d K=%d", H, W,
                 Cin, Cout, K);
   cudaStream_t st = (cudaStream_t)stream;

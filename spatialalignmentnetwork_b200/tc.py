@@ -11,6 +11,7 @@ gradient is folded in analytically (the InstanceNorm / BatchNorm backward is lin
 gradient, so every consumer adds its own contribution).
 """
 import ctypes
+import os
 
 import torch
 from torch.autograd import Function
@@ -20,6 +21,18 @@ from ._lib import call, lib
 
 MODE_DIRECT, MODE_POOL, MODE_D2S, MODE_UP = 0, 1, 2, 3
 _IN_EPS = 1e-5
+
+# 16-bit pair formats of the staged operands (include/san_b200.h): forward operands (normalised activations, network
+# inputs, weights: O(1) magnitudes) are fp16 pairs = fp32-class products; gradients (dY) are bf16 pairs (unbounded
+# exponent range).  The data- and weight-gradient GEMMs then multiply a bf16-pair operand with an fp16-pair one
+# (tcgen05 kind::f16 takes the two operand formats independently).  SAN_TC_FMT selects the A/B experiments:
+#   f16 (default) | f16nomix (fp16 pairs in the forward only; the backward re-stages X and W as bf16 pairs) |
+#   bf16 (round-1 behaviour: bf16 pairs everywhere).
+FMT_BF16, FMT_F16 = 0, 1
+_FMT_MODE = os.environ.get("SAN_TC_FMT", "f16")
+assert _FMT_MODE in ("f16", "f16nomix", "bf16"), _FMT_MODE
+_FMT_FWD = FMT_BF16 if _FMT_MODE == "bf16" else FMT_F16          # staged X and W of the forward conv
+_FMT_BWD = FMT_F16 if _FMT_MODE == "f16" else FMT_BF16           # staged X / W as the backward GEMMs read them
 
 # Staged operands are as large as the activations they come from.  They are re-created in the backward
 # pass (for the weight gradient) unless HBM is plentiful: while live tensors take less than
@@ -100,8 +113,8 @@ def _staged_act(N, H, W, C, device):
     return torch.empty(lib().san_tc_staged_act_elems(N, H, W, C), dtype=torch.bfloat16, device=device)
 
 
-def _stage(xs, N, H, W, Cpad, terms):
-    """terms: list of (y, mu, a, b, slope, C, mode, accumulate)."""
+def _stage(xs, N, H, W, Cpad, terms, fmt):
+    """terms: list of (y, mu, a, b, slope, C, mode, accumulate); fmt: FMT_BF16 | FMT_F16."""
     arr = (_StageTerm * len(terms))()
     for t, (y, mu, a, b, slope, C, mode, acc) in zip(arr, terms):
         t.y = y.data_ptr()
@@ -109,15 +122,15 @@ def _stage(xs, N, H, W, Cpad, terms):
         t.a = a.data_ptr() if a is not None else None
         t.b = b.data_ptr() if b is not None else None
         t.slope, t.C, t.mode, t.accumulate = slope, C, mode, int(acc)
-    call("tc_stage_terms", xs, N, H, W, Cpad, ctypes.addressof(arr), len(terms))
+    call("tc_stage_terms", xs, N, H, W, Cpad, ctypes.addressof(arr), len(terms), fmt)
 
 
-def _stage_weights(w, dgrad, H, W):
+def _stage_weights(w, dgrad, H, W, fmt):
     Cout, Cin, K, _ = w.shape
     n = lib().san_tc_staged_weight_elems(H, W, Cin if dgrad else Cout, Cout if dgrad else Cin, K)
     assert n > 0, f"tcgen05 conv: unsupported shape H={H} W={W} {tuple(w.shape)}"
     ws = torch.empty(n, dtype=torch.bfloat16, device=w.device)
-    call("tc_stage_weights", w, ws, H, W, Cout, Cin, K, int(dgrad))
+    call("tc_stage_weights", w, ws, H, W, Cout, Cin, K, int(dgrad), fmt)
     return ws
 
 
@@ -166,15 +179,16 @@ class _FusedConv(Function):
                 ctot += C
         assert ctot == Cin, (ctot, Cin)
         xs = _staged_act(N, H, W, Cin, w.device)
-        _stage(xs, N, H, W, _pad16(Cin), terms)
-        ws = _stage_weights(w, False, H, W)
+        _stage(xs, N, H, W, _pad16(Cin), terms, _FMT_FWD)
+        ws = _stage_weights(w, False, H, W, _FMT_FWD)
         out = torch.empty(N, Cout, H, W, dtype=torch.float32, device=w.device)
-        call("tc_conv", xs, ws, bias, out, N, H, W, Cin, Cout, K, 0)
+        call("tc_conv", xs, ws, bias, out, N, H, W, Cin, Cout, K, 0, 3 * _FMT_FWD)
         # The staged operand is kept for the backward only while HBM is plentiful (_keep_staged); otherwise
         # the weight gradient re-stages it from the raw tensors, which autograd holds anyway for the
         # normalisation backward.
         coefs = [m[5] for m in metas if m[5] is not None]
-        keep = _keep_staged(w.device) and (ctx.needs_input_grad[0] or ctx.needs_input_grad[1])
+        keep = (_keep_staged(w.device) and (ctx.needs_input_grad[0] or ctx.needs_input_grad[1])
+                and _FMT_BWD == _FMT_FWD)    # f16nomix: the weight gradient wants bf16 pairs -> re-staged in backward
         ctx.save_for_backward(w, *tensors, *coefs, *([xs] if keep else []))
         ctx.meta = (K, [(m[0], m[1], m[2], m[3], m[4], m[5] is not None, m[6]) for m in metas], (N, H, W),
                     bias is not None, len(tensors), keep)
@@ -209,7 +223,7 @@ class _FusedConv(Function):
             ti += 3 if norm == "bn" else 1
         # dY staged once as BF16 hi/lo: the operand of both the data- and the weight-gradient GEMMs
         gys = _staged_act(N, H, W, Cout, dev)
-        _stage(gys, N, H, W, _pad16(Cout), [(gy, None, None, None, 1.0, Cout, MODE_DIRECT, False)])
+        _stage(gys, N, H, W, _pad16(Cout), [(gy, None, None, None, 1.0, Cout, MODE_DIRECT, False)], FMT_BF16)
         # ---- weight gradient: tcgen05 GEMM over the pixel dimension on the staged dY and the re-staged input
         dw = db = None
         if ctx.needs_input_grad[0] or (has_bias and ctx.needs_input_grad[1]):
@@ -220,21 +234,23 @@ class _FusedConv(Function):
             else:
                 xs = _staged_act(N, H, W, Cin, dev)
                 _stage(xs, N, H, W, _pad16(Cin),
-                       [(t["y"], *_coef_views(t["norm"], t["st"])[:3], t["slope"], t["C"], t["mode"], t["acc"]) for t in terms])
+                       [(t["y"], *_coef_views(t["norm"], t["st"])[:3], t["slope"], t["C"], t["mode"], t["acc"]) for t in terms],
+                       _FMT_BWD)
             if lib().san_tc_wgrad_supported(H, W, Cin, Cout, K):
-                call("tc_wgrad", gys, xs, dw, db, gy if has_bias else None, N, H, W, Cin, Cout, K)
+                # A = dY (bf16 pair), B = X (fp16 pair unless SAN_TC_FMT says otherwise)
+                call("tc_wgrad", gys, xs, dw, db, gy if has_bias else None, N, H, W, Cin, Cout, K, 2 * _FMT_BWD)
             else:   # tiny images (W < 16): fp32 CUDA-core kernel on the un-staged operand
                 x32 = torch.empty(N, Cin, H, W, dtype=torch.float32, device=dev)
-                call("tc_unstage_act", xs, x32, N, Cin, H, W)
+                call("tc_unstage_act", xs, x32, N, Cin, H, W, _FMT_BWD)
                 call("conv2d_wgrad", x32, gy, dw, db, N, Cin, H, W, Cout, K, 0, 0)
                 del x32
             del xs
         # ---- data gradient: the same tcgen05 conv on the staged dY with the flipped filter
         grads = [None] * ntens
         if any(ctx.needs_input_grad[3 + t["ti"]] for t in terms):
-            wsd = _stage_weights(w, True, H, W)
+            wsd = _stage_weights(w, True, H, W, _FMT_BWD)
             dx = torch.empty(N, Cin, H, W, dtype=torch.float32, device=dev)
-            call("tc_conv", gys, wsd, None, dx, N, H, W, Cout, Cin, K, 0)
+            call("tc_conv", gys, wsd, None, dx, N, H, W, Cout, Cin, K, 0, 2 * _FMT_BWD)
             del gys
             for t in terms:
                 if not ctx.needs_input_grad[3 + t["ti"]]:

@@ -213,10 +213,15 @@ def _describe(L, H, W, Cin, Cout, K):
     out = (ctypes.c_int * 16)()
     assert L.san_tc_describe(H, W, Cin, Cout, K, ctypes.addressof(out)) == 0
     keys = ("Cin_pad KG KS nsplit Npad Wp Hp R T S_alloc strips stages acc_stages a_bytes b_bytes smem_bytes").split()
-    return dict(zip(keys, list(out)))
+    g = dict(zip(keys, list(out)))
+    form = (ctypes.c_int * 4)()
+    assert L.san_tc_describe_form(H, W, Cin, Cout, K, ctypes.addressof(form)) == 0
+    g.update(dict(zip("dxn Np wtaps xchg_bytes".split(), list(form))))
+    return g
 
 
-@pytest.mark.parametrize("shape", [(1, 3, 12, 20, 5, 3), (2, 18, 16, 24, 18, 3), (1, 20, 9, 33, 40, 1), (1, 7, 10, 18, 170, 3)])
+@pytest.mark.parametrize("shape", [(1, 3, 12, 20, 5, 3), (2, 18, 16, 24, 18, 3), (1, 20, 9, 33, 40, 1), (1, 7, 10, 18, 170, 3),
+                                   (1, 36, 10, 160, 36, 3), (1, 32, 5, 320, 32, 3), (1, 2, 7, 50, 8, 3)])
 def test_tc_flattened_pixel_formulation_on_cpu(built, shape):
     """CPU model of csrc/conv_tc.cu driven by the library's own geometry (san_tc_describe): the staged layout
     Xs[n][hl][kg][slot][8] with a one-pixel zero border, strips of R rows, 128-row M tiles over the flattened padded
@@ -235,9 +240,15 @@ def test_tc_flattened_pixel_formulation_on_cpu(built, shape):
     assert Npad % 16 == 0 and g["nsplit"] * Npad >= Cout and Npad <= 256
     assert T * Npad * g["acc_stages"] <= 512                                   # TMEM columns
     assert g["S_alloc"] >= 128 * T + 2 * Wp + 2 and g["S_alloc"] >= (R + 2) * Wp  # every tap row of every tile is in the tile
-    assert g["a_bytes"] == 4 * g["S_alloc"] * 16 and g["b_bytes"] == ntaps * 4 * Npad * 16
-    assert g["stages"] >= 2 and 256 + g["stages"] * (g["a_bytes"] + g["b_bytes"]) <= 225 * 1024
+    dxn, Np = g["dxn"], g["Np"]
+    assert dxn == (1 if (K == 3 and Cout <= 40) else 0)              # narrow 3x3 layers: horizontal taps in the MMA N dimension
+    assert g["wtaps"] == (3 if dxn else ntaps)
+    assert g["a_bytes"] == 4 * g["S_alloc"] * 16 and g["b_bytes"] == g["wtaps"] * 4 * Npad * 16
+    assert g["stages"] >= 2 and 256 + g["xchg_bytes"] + g["stages"] * (g["a_bytes"] + g["b_bytes"]) <= 225 * 1024
     assert g["strips"] == -(-H // R) and 128 * T >= R * Wp
+    if dxn:
+        assert Np % 8 == 0 and Np >= Cout and Npad >= 3 * Np and g["nsplit"] == 1
+        assert g["xchg_bytes"] >= T * 4 * 5 * Np * 4                   # [T][quarter][5][Np] floats
     torch.manual_seed(7)
     x = torch.randn(N, Cin, H, W)
     w = torch.randn(Cout, Cin, K, K) / (Cin * ntaps) ** 0.5
@@ -261,6 +272,27 @@ def test_tc_flattened_pixel_formulation_on_cpu(built, shape):
             rows_in = min(R + 2, Hp - y0)
             tile = torch.zeros(2, KG, g["S_alloc"], 8)                         # what the TMA bulk copies deliver
             tile[:, :, :rows_in * Wp] = xs[n][:, :, y0 * Wp:(y0 + rows_in) * Wp]
+            if dxn:
+                # B rows nn = dx * Np + co per filter row dy; ONE A window per dy (offset dy * Wp); the accumulator
+                # holds E_dx[q] in column block dx, and y[q] = E_0[q] + E_1[q + 1] + E_2[q + 2]
+                acc = torch.zeros(128 * T, Npad, dtype=torch.float64)
+                for dy in range(3):
+                    bh = torch.zeros(Npad, g["Cin_pad"], dtype=torch.float64)
+                    bl = torch.zeros(Npad, g["Cin_pad"], dtype=torch.float64)
+                    for dx in range(3):
+                        bh[dx * Np:dx * Np + Cout] = whi[:Cout, :, dy * 3 + dx].double()
+                        bl[dx * Np:dx * Np + Cout] = wlo[:Cout, :, dy * 3 + dx].double()
+                    off = dy * Wp
+                    assert off + 128 * T <= g["S_alloc"]
+                    a_hi = tile[0, :, off:off + 128 * T].permute(1, 0, 2).reshape(128 * T, -1).double()
+                    a_lo = tile[1, :, off:off + 128 * T].permute(1, 0, 2).reshape(128 * T, -1).double()
+                    acc += a_hi @ bh.T + a_lo @ bh.T + a_hi @ bl.T
+                for q in range(R * Wp):
+                    r, xx = divmod(q, Wp)
+                    if xx < W and y0 + r < H:
+                        assert q + 2 < 128 * T          # the neighbouring lanes exist (next quarter / next tile of the unit)
+                        out[n, :, y0 + r, xx] = (acc[q, 0:Cout] + acc[q + 1, Np:Np + Cout]) + acc[q + 2, 2 * Np:2 * Np + Cout]
+                continue
             for ns in range(g["nsplit"]):
                 acc = torch.zeros(128 * T, Npad, dtype=torch.float64)
                 for tap in range(ntaps):
@@ -511,7 +543,9 @@ def test_conv_cycle_model_runs(built):
     for shape, meas in conv_model.MEASURED_MS.items():
         if shape == (18, 2, 320, 1):       # 1x1 head: the model charges halo rows the 1x1 kernel finds in L2
             continue
-        _, m = conv_model.model(L, 64, *shape)
+        g, m = conv_model.model(L, 64, *shape)
+        if g["dxn"] != conv_model.MEASURED_FORM.get(shape, 0):
+            continue                       # measured with the other formulation
         assert 0.95 < meas / m["bound"] < 2.2, (shape, meas, m)
 
 
@@ -553,8 +587,9 @@ def test_abi_argument_validation_without_gpu(built):
         (L.san_filter2d(p, p, p, 1, 8, 8, 4, None), "bad args"),                     # even window
         (L.san_sn_sigma(p, p, p, p, p, 0, 4, 1e-12, 1, None), "bad args"),
         (L.san_adamw_step(p, p, p, p, p, 1, 1e-4, 0.9, 0.999, 1e-8, 0.0, 0, None), "bad args"),     # step counts from 1
-        (L.san_tc_conv(p, p, None, p, 1, 8, 8, 4, 4, 5, 0, None), "unsupported shape"),  # 5x5 filter
-        (L.san_tc_stage_terms(p, 1, 8, 8, 16, p, 7, None), "bad args"),              # more than 6 terms
+        (L.san_tc_conv(p, p, None, p, 1, 8, 8, 4, 4, 5, 0, 3, None), "unsupported shape"),  # 5x5 filter
+        (L.san_tc_conv(p, p, None, p, 1, 8, 8, 4, 4, 3, 0, 4, None), "bad args"),           # unknown pair format
+        (L.san_tc_stage_terms(p, 1, 8, 8, 16, p, 7, 1, None), "bad args"),           # more than 6 terms
     ]
     for rc, msg in cases:
         assert rc == ARG, (rc, msg)

@@ -231,7 +231,7 @@ def test_train_and_eval_entry_points(tmp_path):
     assert out.returncode == 0, out.stderr[-2000:]
     lines = [json.loads(l) for l in out.stdout.splitlines() if l.startswith("{")]
     its = [l for l in lines if "iter" in l]
-    assert len(its) == 6 and all(l["loss_all"] == l["loss_all"] for l in its)        # finite
+    assert len(its) == 6 and all(l["loss_sim"] == l["loss_sim"] and "loss_all" not in l for l in its)   # finite; loss_all is released (model.py:261)
     assert its[-1]["loss_sim"] < its[0]["loss_sim"]                                   # it learns
     ck = [d for d in os.listdir(logdir) if d.endswith("_final.pt")]
     assert len(ck) == 1 and {"config", "net_T", "net_R", "net_mask"} <= set(os.listdir(os.path.join(logdir, ck[0])))

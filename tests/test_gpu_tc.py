@@ -18,28 +18,32 @@ def _lib():
     return _lib
 
 
-def stage(x, Cpad=None):
+BF16, F16 = 0, 1      # 16-bit pair formats of the staged operands (include/san_b200.h)
+
+
+def stage(x, fmt=BF16):
     """fp32 NCHW -> staged hi/lo tensor via san_tc_stage_act (single identity source)."""
     L = _lib()
     N, C, H, W = x.shape
     xs = torch.empty(L.lib().san_tc_staged_act_elems(N, H, W, C), dtype=torch.bfloat16, device=x.device)
     Cpad = (C + 15) // 16 * 16
     L.call("tc_stage_act", xs, N, H, W, Cpad, x, None, None, None, 1.0, C, 0,
-           None, None, None, None, 1.0, 0, 0, None, None, None, None, 1.0, 0, 0)
+           None, None, None, None, 1.0, 0, 0, None, None, None, None, 1.0, 0, 0, fmt)
     return xs
 
 
-def conv_tc(x, w, bias=None, dgrad=False):
+def conv_tc(x, w, bias=None, dgrad=False, fmt_a=BF16, fmt_b=BF16):
+    """fmt_a: pair format of the staged activations / dY, fmt_b: of the staged weights (may differ)."""
     L = _lib()
     N, Cin, H, W = x.shape
     Cout, Cin_w, K, _ = w.shape
-    xs = stage(x)
+    xs = stage(x, fmt_a)
     ws = torch.empty(L.lib().san_tc_staged_weight_elems(H, W, Cin_w if dgrad else Cout, Cout if dgrad else Cin_w, K),
                      dtype=torch.bfloat16, device=x.device)
-    L.call("tc_stage_weights", w, ws, H, W, Cout, Cin_w, K, int(dgrad))
+    L.call("tc_stage_weights", w, ws, H, W, Cout, Cin_w, K, int(dgrad), fmt_b)
     co = Cin_w if dgrad else Cout
     y = torch.empty(N, co, H, W, dtype=torch.float32, device=x.device)
-    L.call("tc_conv", xs, ws, bias, y, N, H, W, Cin, co, K, 0)
+    L.call("tc_conv", xs, ws, bias, y, N, H, W, Cin, co, K, 0, fmt_a + 2 * fmt_b)
     return y
 
 
@@ -64,8 +68,17 @@ def test_tc_conv_fwd_and_dgrad(case):
     xr = x.double().requires_grad_(True)
     yr = F.conv2d(xr, w.double(), b.double() if has_bias else None, padding=K // 2)
     (yr * gy.double()).sum().backward()
+    # forward as the path runs it: fp16 pairs on both operands = fp32-class (the bar is 10x below the bf16-pair one)
+    y = conv_tc(x.cuda(), w.cuda(), b.cuda() if has_bias else None, fmt_a=F16, fmt_b=F16)
+    e16 = rel_l2(y, yr)
+    assert e16 < 2e-6, e16
+    # data gradient as the path runs it: dY as a bf16 pair x weights as an fp16 pair (mixed-format MMA)
+    dx = conv_tc(gy.cuda(), w.cuda(), None, dgrad=True, fmt_a=BF16, fmt_b=F16)
+    assert rel_l2(dx, xr.grad) < 2e-5
+    # bf16 pairs on both operands (SAN_TC_FMT=bf16, the round-1 arithmetic)
     y = conv_tc(x.cuda(), w.cuda(), b.cuda() if has_bias else None)
-    assert rel_l2(y, yr) < 2e-5
+    eb = rel_l2(y, yr)
+    assert eb < 2e-5 and e16 < eb
     dx = conv_tc(gy.cuda(), w.cuda(), None, dgrad=True)
     assert rel_l2(dx, xr.grad) < 2e-5
 
@@ -91,13 +104,14 @@ def test_tc_stage_roundtrip_and_fused_sources():
     cb = [t.float().reshape(-1).cuda().contiguous() for t in (mub, 1 / torch.sqrt(vb + 1e-5))]
     C = 15
     xs = torch.empty(L.lib().san_tc_staged_act_elems(N, H, W, C), dtype=torch.bfloat16, device="cuda")
-    L.call("tc_stage_act", xs, N, H, W, 16,
-           ya.cuda(), ca[0], ca[1], None, 0.2, 5, 2,
-           yb.cuda(), cb[0], cb[1], None, 0.2, 7, 1,
-           yc.cuda(), None, None, None, 1.0, 3, 0)
     out = torch.empty(N, C, H, W, device="cuda")
-    L.call("tc_unstage_act", xs, out, N, C, H, W)
-    assert rel_l2(out, ref) < 2e-5
+    for fmt, bar in ((F16, 5e-7), (BF16, 2e-5)):          # fp16 pairs carry 22 significant bits, bf16 pairs ~17
+        L.call("tc_stage_act", xs, N, H, W, 16,
+               ya.cuda(), ca[0], ca[1], None, 0.2, 5, 2,
+               yb.cuda(), cb[0], cb[1], None, 0.2, 7, 1,
+               yc.cuda(), None, None, None, 1.0, 3, 0, fmt)
+        L.call("tc_unstage_act", xs, out, N, C, H, W, fmt)
+        assert rel_l2(out, ref) < bar, (fmt, rel_l2(out, ref))
     st = xs[8:-256].view(N, 2, 2, H + 2, W + 2, 8).float()      # [lead 8 | planes | trail 256]
     assert xs[:8].float().abs().max() == 0 and xs[-256:].float().abs().max() == 0
     assert st[:, :, :, 0].abs().max() == 0 and st[:, :, :, -1].abs().max() == 0      # zero border rows
@@ -221,13 +235,15 @@ def test_tc_wgrad(case):
     wr = w.double().requires_grad_(True)
     br = b.double().requires_grad_(True) if has_bias else None
     (F.conv2d(x.double(), wr, br, padding=K // 2) * gy.double()).sum().backward()
-    xs, gys = stage(x.cuda()), stage(gy.cuda())
-    dw = torch.empty(Cout, Cin, K, K, device="cuda")
-    db = torch.empty(Cout, device="cuda") if has_bias else None
-    L.call("tc_wgrad", gys, xs, dw, db, gy.cuda() if has_bias else None, N, H, W, Cin, Cout, K)
-    assert rel_l2(dw, wr.grad) < 2e-5
-    if has_bias:
-        assert rel_l2(db, br.grad) < 1e-5
+    gys = stage(gy.cuda())
+    for fmt_x in (F16, BF16):          # the path: dY bf16 pair x X fp16 pair (mixed); round-1 arithmetic: both bf16
+        xs = stage(x.cuda(), fmt_x)
+        dw = torch.empty(Cout, Cin, K, K, device="cuda")
+        db = torch.empty(Cout, device="cuda") if has_bias else None
+        L.call("tc_wgrad", gys, xs, dw, db, gy.cuda() if has_bias else None, N, H, W, Cin, Cout, K, 2 * fmt_x)
+        assert rel_l2(dw, wr.grad) < 2e-5, (fmt_x, rel_l2(dw, wr.grad))
+        if has_bias:
+            assert rel_l2(db, br.grad) < 1e-5
 
 
 def test_fused_conv_batchnorm_sum_up_pool():

@@ -27,16 +27,23 @@ MEASURED_MS = {  # profiles/r1h_conv_tc_microbench.txt (bs 64, CUDA events, kern
 }
 
 
+MEASURED_FORM = {}      # shape -> 1 where MEASURED_MS was taken with the DXN form (round-2 numbers), else the 9-tap form
+
+
 def describe(L, H, W, Cin, Cout, K):
     out = (ctypes.c_int * 16)()
     assert L.san_tc_describe(H, W, Cin, Cout, K, ctypes.addressof(out)) == 0
     keys = "Cin_pad KG KS nsplit Npad Wp Hp R T S_alloc strips stages acc_stages a_bytes b_bytes smem_bytes".split()
-    return dict(zip(keys, list(out)))
+    g = dict(zip(keys, list(out)))
+    form = (ctypes.c_int * 4)()
+    assert L.san_tc_describe_form(H, W, Cin, Cout, K, ctypes.addressof(form)) == 0
+    g.update(dict(zip("dxn Np wtaps xchg_bytes".split(), list(form))))
+    return g
 
 
 def model(L, N, Cin, Cout, HW, K):
     g = describe(L, HW, HW, Cin, Cout, K)
-    taps = K * K
+    taps = g["wtaps"]                               # 9, or 3 in the DXN form (horizontal taps in the MMA N dimension)
     mma_per_unit = g["T"] * taps * 3 * g["KS"]
     smem_clk = 32 + g["Npad"] / 4.0                 # A 4 KB + B Npad*32 B at 128 B/clk
     tens_clk = g["Npad"] / 2.0
@@ -52,6 +59,8 @@ def model(L, N, Cin, Cout, HW, K):
     # epilogue: every accumulator column of every tile goes TMEM -> registers -> global; overlapped only when the
     # accumulators are double-buffered
     epi_clk = g["T"] * g["Npad"] / 8.0 * 40.0 / 4.0      # ~40 clk per 8-column tcgen05.ld + stores, 4 warps per quarter
+    if g["dxn"]:
+        epi_clk = max(epi_clk, g["T"] * g["Npad"] * 8.0)  # TMEM read of the 3 column blocks at 64 B/clk
     epi_ms = waves * epi_clk / (CLK_GHZ * 1e6)
     bound = max(mma_ms, hbm_ms) + (0.0 if g["acc_stages"] == 2 else epi_ms)
     return g, dict(mma=mma_ms, tensor=tens_ms, hbm=hbm_ms, epi=epi_ms, bound=bound, waves=waves,
