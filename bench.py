@@ -459,6 +459,7 @@ def parity_block(args, net, dev, nslices=2):
             "grad_all_params_vs_fp64": float(f"{g['all_concatenated']['vs_fp64']:.3e}"),
             "grad_cpu_fp32_oracle_vs_fp64": float(f"{g['all_concatenated']['fp32_vs_fp64']:.3e}"),
             "grad_cosine_vs_fp64": round(g["all_concatenated"]["cosine_vs_fp64"], 6),
+            "grad_cpu_fp32_oracle_cosine_vs_fp64": round(g["all_concatenated"]["fp32_cosine_vs_fp64"], 6),
             "grad_tensors": g["tensors"], "grad_worst": g["worst"][:3],
             "psnr_rec_vs_reference_rec_db": round(rep["image_metrics"]["psnr_rec_vs_reference_rec_db"], 2),
             "ssim_rec_vs_reference_rec": round(rep["image_metrics"]["ssim_rec_vs_reference_rec"], 7),
@@ -581,7 +582,7 @@ def run_b200(args):
         out = {"metric": METRIC, "value": round(val, 3), "unit": "slices/s", "n_gpus": world, "steps": args.steps,
                "warmup": max(args.warmup, args.min_warmup), "ms_per_step": round(ms_res / args.steps, 3), "higher_is_better": True,
                "scaling": args.scaling, "vs_baseline": None,
-               "dtype": "bf16x3 (convs: BF16 hi/lo split operands, 3 tcgen05 MMAs, fp32 accumulate; fp32 storage and FFT)",
+               "dtype": "f16x3 (convs: fp16 hi/lo pair operands, 3 tcgen05 kind::f16 MMAs per product, fp32 TMEM accumulate = fp32-class products; fp32 storage, norms and FFT)",
                "data": "synthetic", "config": workload_config(args, world, ckpt),
                "e2e": {"value": round(e2e, 3), "unit": "slices/s", "h2d_bytes_per_step": inbytes, "d2h_bytes_per_step": 4,
                        "ms_per_step": round(ms_e2e / args.steps, 3)},

@@ -69,6 +69,9 @@ int san_sens_normalize_bwd(const void* G, const float* s_planar, float* ds_plana
                            float eps, void* stream);
 /* out = a*x + b*y (y may be NULL): residual adds (unet.py:15-24) and gradient accumulation */
 int san_axpby(const float* x, const float* y, float* out, float a, float b, long long n, void* stream);
+/* out[0] = max |x[i]| over finite elements (device scalar): the dynamic scale of fp16-pair GRADIENT operands (dY of the
+ * data- and weight-gradient GEMMs; no reference counterpart: cuDNN computes these in fp32) */
+int san_absmax(const float* x, long long n, float* out, void* stream);
 
 /* ---- convolutions (varnet.py:75-80,139-146,176-179; unet.py:119-140; cross.py:15) ---- */
 /* repack OIHW weights for the kernels: dgrad=0 -> [Cin][K*K][Cout]; dgrad=1 -> flipped,
@@ -94,8 +97,10 @@ int san_space_to_depth2(const float* y, float* x, int N, int Co, int H, int W, v
  *   1  fp16 pair: z = s*v (static power-of-two s: 16 for activations, 256 for weights), hi = fp16(z),
  *      lo = fp16(z - hi): 22 significant bits, fp32-class products, for operands of O(1) magnitude (normalised
  *      activations, network inputs, weights); the kernels undo the scale exactly in their epilogues.
- * For san_tc_conv / san_tc_wgrad `fmt` is a bit mask: bit 0 = the A operand (activations / dY) is an fp16 pair,
- * bit 1 = the B operand (weights / X) is an fp16 pair; the two operands of one MMA may differ in format.
+ *      Gradient operands (dY) have no static magnitude: their fp16 pairs use a DYNAMIC power-of-two scale derived
+ *      on the device from max|dY| (san_absmax); pass that device scalar as `absmax` / `a_absmax` / `dy_absmax`.
+ * For san_tc_conv / san_tc_wgrad `fmt` is 0 (both operands bf16 pairs) or 3 (both fp16 pairs): the two operands of
+ * one tcgen05 kind::f16 MMA must share the format on the B200 (a mixed f16 x bf16 MMA faults).
  * Activations are staged as Xs[n][hl][kg][(H+2)*(W+2)][8] 16-bit (hl = hi/lo halves of the fp32 value,
  * kg = groups of 8 channels, Cin padded to 16, one-pixel zero border); weights as
  * Ws[nsplit][KS][taps][hl][2][Npad][8].  Element counts of the caller-allocated buffers: */
@@ -133,7 +138,7 @@ typedef struct san_stage_term {
   int accumulate;
 } san_stage_term;
 int san_tc_stage_terms(void* xs, int N, int H, int W, int Cpad, const san_stage_term* terms, int nterms, int fmt,
-                       void* stream);
+                       const float* absmax, void* stream);
 /* x[N,C,H,W] = hi + lo of a staged tensor (input of the fp32 weight-gradient kernel) */
 int san_tc_unstage_act(const void* xs, float* x, int N, int C, int H, int W, int fmt, void* stream);
 /* OIHW fp32 -> staged hi/lo for images of H x W (the output-channel split depends on the strip geometry);
@@ -144,7 +149,7 @@ int san_tc_stage_weights(const float* w, void* ws, int H, int W, int Cout, int C
 /* y[N,Cout,H,W] (+ bias) = conv2d(staged x, staged w), stride 1, padding K/2, K in {1,3};
  * Cin/Cout are the channel counts of THIS launch (for dgrad: Cin = original Cout, Cout = original Cin) */
 int san_tc_conv(const void* xs, const void* ws, const float* bias, float* y, int N, int H, int W, int Cin, int Cout,
-                int K, long long y_bs, int fmt, void* stream);
+                int K, long long y_bs, int fmt, const float* a_absmax, void* stream);
 
 /* dW[Cout,Cin,K,K] (and dbias[Cout] from the fp32 dy, both optional-bias) from the staged dY and the staged
  * input of the forward conv: tcgen05 GEMM over the pixel dimension, MN-major operands, BF16x3 */
@@ -153,7 +158,7 @@ int san_tc_wgrad_supported(int H, int W, int Cin, int Cout, int K);
  * nchunks, Wp, PS, range0, range_len (host pointer) */
 int san_tc_wgrad_describe(int H, int W, int Cin, int Cout, int K, int* out);
 int san_tc_wgrad(const void* dys, const void* xs, float* dw, float* dbias, const float* dy, int N, int H, int W, int Cin,
-                 int Cout, int K, int fmt, void* stream);
+                 int Cout, int K, int fmt, const float* dy_absmax, void* stream);
 
 /* ---- normalisation / activation / resampling (varnet.py:98,139-146,235,257-273; unet.py:119-140) ---- */
 /* per-plane mean and centred sum of squares (two-pass) */

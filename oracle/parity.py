@@ -81,11 +81,13 @@ def compare(cand_out, cand_grads, f32, g32, f64, g64, worst=6):
     c, r32, r64 = _cat(cand_grads, names), _cat(g32, names), _cat(g64, names)
     glob_c, glob_32 = ((c - r64).norm() / r64.norm()).item(), ((r32 - r64).norm() / r64.norm()).item()
     cos = (c @ r64 / (c.norm() * r64.norm())).item()
+    cos32 = (r32 @ r64 / (r32.norm() * r64.norm())).item()
     order = sorted(names, key=lambda k: -per[k][0])
     rep["grad"] = {
         "tensors": len(names), "missing": missing,
         "all_concatenated": {"vs_fp64": glob_c, "fp32_vs_fp64": glob_32, "ratio_to_fp32_floor": glob_c / max(glob_32, 1e-30),
-                             "vs_fp32": ((c - r32).norm() / r32.norm()).item(), "cosine_vs_fp64": cos},
+                             "vs_fp32": ((c - r32).norm() / r32.norm()).item(), "cosine_vs_fp64": cos,
+                             "fp32_cosine_vs_fp64": cos32},
         "per_tensor_median": {"vs_fp64": sorted(v[0] for v in per.values())[len(per) // 2],
                               "fp32_vs_fp64": sorted(v[1] for v in per.values())[len(per) // 2]},
         "worst": [{"name": k, "vs_fp64": per[k][0], "fp32_vs_fp64": per[k][1]} for k in order[:worst]],

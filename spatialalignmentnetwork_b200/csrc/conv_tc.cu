@@ -167,6 +167,7 @@ struct ConvTcParams {
   int nunits;
   int fmt;                  // TC_FMT_* bits: which operands are fp16 pairs (else bf16 pairs)
   float out_scale;          // exact inverse of the operands' static scales
+  const float* a_absmax;    // null, or device scalar max|A| when A was staged with the dynamic scale (dY in the data gradient)
   TcGeom g;
 };
 
@@ -297,6 +298,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const ConvTcPara
     // ================================ epilogue ====================================
     const int wq = warp & 3;            // TMEM lane quarter this warp may access
     const int egrp = (warp - 2) >> 2;   // which of the warps sharing that quarter: takes tiles t = egrp, egrp + G, ...
+    const float oscale = p.a_absmax ? p.out_scale / tc_dyn_scale(__ldg(p.a_absmax)) : p.out_scale;
     constexpr int EG = TC_EPI_WARPS / 4;
     int as = 0;
     uint32_t aph = 0;
@@ -338,7 +340,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const ConvTcPara
               else if (lane == 31) xc[4 * Np + c] = e0[j];
               if (valid && c < p.Cout) {
                 const float bv = p.bias ? __ldg(p.bias + c) : 0.f;
-                dst[(long long)c * HW] = fmaf(pe + s2, p.out_scale, bv);
+                dst[(long long)c * HW] = fmaf(pe + s2, oscale, bv);
               }
             }
           }
@@ -363,7 +365,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const ConvTcPara
             if (r < g.R && x < p.W && yy < p.H && c < p.Cout) {
               const float v = l ? (xc[4 * Np + c] + xn[c]) + xn[2 * Np + c] : xc[3 * Np + c] + xn[Np + c];
               const float bv = p.bias ? __ldg(p.bias + c) : 0.f;
-              yn[(long long)c * HW + (long long)yy * p.W + x] = fmaf(v, p.out_scale, bv);
+              yn[(long long)c * HW + (long long)yy * p.W + x] = fmaf(v, oscale, bv);
             }
           }
         }
@@ -386,7 +388,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const ConvTcPara
               const int c = c0 + j;
               if (c < c_cnt) {
                 const float bv = p.bias ? __ldg(p.bias + c_base + c) : 0.f;
-                dst[(long long)(c_base + c) * HW] = fmaf(v[j], p.out_scale, bv);
+                dst[(long long)(c_base + c) * HW] = fmaf(v[j], oscale, bv);
               }
             }
           }
@@ -424,7 +426,8 @@ struct StageArgs {
   int nterms;
   __nv_bfloat16* xs;
   int N, H, W, Wp, PS, KG;
-  int fmt;           // 0: bf16 pairs (gradients), 1: fp16 pairs scaled by TC_SX (forward operands)
+  int fmt;           // 0: bf16 pairs, 1: fp16 pairs scaled by TC_SX (forward operands) or by the dynamic scale below
+  const float* absmax;   // null, or device scalar max|y| of the (single, identity) source: dynamic scale (gradients)
 };
 
 __device__ __forceinline__ float act1(float v, float mu, float a, float b, float slope) {
@@ -464,13 +467,13 @@ __device__ __forceinline__ int pick_off(int mode, const SlotOffs& o) {
   return mode == 0 ? o.off0 : (mode == 2 ? o.offs2 : (mode == 3 ? o.offu : 0));
 }
 __device__ __forceinline__ void store_split(__nv_bfloat16* xs, long long o_hi, long long o_lo, int slot, const float* v,
-                                            bool f16) {
+                                            bool f16, float scale) {
   uint32_t hw[4], lw[4];
 #pragma unroll
   for (int j = 0; j < 4; ++j) {
     unsigned short h0, l0, h1, l1;
-    split16(v[2 * j], f16, TC_SX, h0, l0);
-    split16(v[2 * j + 1], f16, TC_SX, h1, l1);
+    split16(v[2 * j], f16, scale, h0, l0);
+    split16(v[2 * j + 1], f16, scale, h1, l1);
     hw[j] = (uint32_t)h0 | ((uint32_t)h1 << 16);
     lw[j] = (uint32_t)l0 | ((uint32_t)l1 << 16);
   }
@@ -512,6 +515,7 @@ __global__ void __launch_bounds__(256, 3) stage_act_kernel(const StageArgs A) {
   const int kmax = s_kmax;
   const bool pooled = s_pool != 0;
   const bool f16 = A.fmt != 0;
+  const float scale = A.absmax ? tc_dyn_scale(__ldg(A.absmax)) : TC_SX;
   const long long o_hi = ((long long)(n * 2 + 0) * A.KG + kg) * A.PS;
   const long long o_lo = ((long long)(n * 2 + 1) * A.KG + kg) * A.PS;
   const int Wh = A.W / 2, HWq = (A.H / 2) * Wh, W2 = 2 * A.W;
@@ -561,8 +565,8 @@ __global__ void __launch_bounds__(256, 3) stage_act_kernel(const StageArgs A) {
     }
 #pragma unroll
     for (int j = 0; j < 8; ++j) { vA[j] = oA.inb ? vA[j] : 0.f; vB[j] = oB.inb ? vB[j] : 0.f; }
-    store_split(A.xs, o_hi, o_lo, slot, vA, f16);
-    if (slotB < A.PS) store_split(A.xs, o_hi, o_lo, slotB, vB, f16);
+    store_split(A.xs, o_hi, o_lo, slot, vA, f16, scale);
+    if (slotB < A.PS) store_split(A.xs, o_hi, o_lo, slotB, vB, f16, scale);
   }
   // zero lead-in / trailing slack of the buffer (see TC_LEAD / TC_TRAIL)
   if (blockIdx.x == 0 && blockIdx.y == 0) {
@@ -694,9 +698,11 @@ int san_tc_supported(int H, int W, int Cin, int Cout, int K) {
   return tc_geometry(H, W, Cin, Cout, K, &g) ? 1 : 0;
 }
 
-static int launch_stage(StageArgs& A, void* xs, int N, int H, int W, int Cpad, int fmt, cudaStream_t st) {
+static int launch_stage(StageArgs& A, void* xs, int N, int H, int W, int Cpad, int fmt, const float* absmax,
+                        cudaStream_t st) {
   SAN_CHECK_ARG(fmt == 0 || fmt == 1, "san_tc_stage: fmt must be 0 (bf16 pairs) or 1 (fp16 pairs)");
-  A.fmt = fmt;
+  SAN_CHECK_ARG(!absmax || fmt == 1, "san_tc_stage: the dynamic scale applies to fp16 pairs only");
+  A.fmt = fmt; A.absmax = absmax;
   int ctot = 0;
   for (int i = 0; i < A.nterms; ++i) {
     SAN_CHECK_ARG(A.s[i].y && A.s[i].C > 0, "san_tc_stage: term %d has no tensor / channels", i);
@@ -718,7 +724,7 @@ static int launch_stage(StageArgs& A, void* xs, int N, int H, int W, int Cpad, i
 }
 
 int san_tc_stage_terms(void* xs, int N, int H, int W, int Cpad, const san_stage_term* terms, int nterms, int fmt,
-                       void* stream) {
+                       const float* absmax, void* stream) {
   SAN_CHECK_ARG(xs && terms && nterms >= 1 && nterms <= STAGE_MAX_TERMS && N > 0 && H > 0 && W > 0 && Cpad % 16 == 0,
                 "san_tc_stage_terms: bad args");
   StageArgs A{};
@@ -733,7 +739,7 @@ int san_tc_stage_terms(void* xs, int N, int H, int W, int Cpad, const san_stage_
     c_prev = c0;
     if (!t.accumulate) c_next = c0 + t.C;
   }
-  return launch_stage(A, xs, N, H, W, Cpad, fmt, (cudaStream_t)stream);
+  return launch_stage(A, xs, N, H, W, Cpad, fmt, absmax, (cudaStream_t)stream);
 }
 
 int san_tc_stage_act(void* xs, int N, int H, int W, int Cpad,
@@ -747,7 +753,7 @@ int san_tc_stage_act(void* xs, int N, int H, int W, int Cpad,
   A.nterms = 1;
   if (y1) { A.s[1] = StageTerm{y1, mu1, a1, b1, slope1, C1, mode1, C0}; A.nterms = 2; }
   if (y2) { SAN_CHECK_ARG(y1, "san_tc_stage_act: source 2 without source 1"); A.s[2] = StageTerm{y2, mu2, a2, b2, slope2, C2, mode2, C0 + C1}; A.nterms = 3; }
-  return launch_stage(A, xs, N, H, W, Cpad, fmt, (cudaStream_t)stream);
+  return launch_stage(A, xs, N, H, W, Cpad, fmt, nullptr, (cudaStream_t)stream);
 }
 
 int san_tc_unstage_act(const void* xs, float* x, int N, int C, int H, int W, int fmt, void* stream) {
@@ -773,10 +779,13 @@ int san_tc_stage_weights(const float* w, void* ws, int H, int W, int Cout, int C
 }
 
 int san_tc_conv(const void* xs, const void* ws, const float* bias, float* y, int N, int H, int W, int Cin, int Cout,
-                int K, long long y_bs, int fmt, void* stream) {
-  SAN_CHECK_ARG(xs && ws && y && N > 0 && H > 0 && W > 0 && Cin > 0 && Cout > 0 && fmt >= 0 && fmt <= 3, "san_tc_conv: bad args");
+                int K, long long y_bs, int fmt, const float* a_absmax, void* stream) {
+  SAN_CHECK_ARG(xs && ws && y && N > 0 && H > 0 && W > 0 && Cin > 0 && Cout > 0 && (fmt == 0 || fmt == 3),
+                "san_tc_conv: bad args (fmt: 0 = bf16 pairs, 3 = fp16 pairs; the operands of an MMA share the format)");
+  SAN_CHECK_ARG(!a_absmax || fmt == 3, "san_tc_conv: the dynamic scale applies to fp16 pairs only");
   ConvTcParams p{};
-  p.fmt = fmt;
+  p.fmt = fmt; p.a_absmax = a_absmax;
+  if (a_absmax) fmt &= ~TC_FMT_A_F16;   // the static activation scale is replaced by the dynamic one (undone in the epilogue)
   p.out_scale = ((fmt & TC_FMT_A_F16) ? 1.f / TC_SX : 1.f) * ((fmt & TC_FMT_B_F16) ? 1.f / TC_SW : 1.f);
   SAN_CHECK_ARG(tc_geometry(H, W, Cin, Cout, K, &p.g), "san_tc_conv: unsupported shape H=%d W=%d Cin=%d Cout=%d K=%d", H, W,
                 Cin, Cout, K);

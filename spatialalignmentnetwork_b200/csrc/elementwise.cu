@@ -150,6 +150,32 @@ int san_finalize_scalar(const double* acc, float* out, double scale, cudaStream_
   return SAN_OK;
 }
 
+// max |x| of a tensor into a device scalar (the dynamic fp16-pair scale of gradient operands, tc_common.cuh):
+// non-negative floats order like their bit patterns, so one atomicMax on the uint view per block suffices.
+// NaN / inf elements are skipped (they would poison the scale; the values themselves still propagate).
+__global__ void __launch_bounds__(256) absmax_kernel(const float* __restrict__ x, long long n, unsigned int* __restrict__ out) {
+  float m = 0.f;
+  const long long n4 = (((uintptr_t)x & 15) == 0) ? n >> 2 : 0;     // vector path only for 16 B aligned tensors
+  const float4* x4 = (const float4*)x;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+    const float4 v = __ldg(x4 + i);
+    const float a = fmaxf(fmaxf(fabsf(v.x), fabsf(v.y)), fmaxf(fabsf(v.z), fabsf(v.w)));   // fmaxf drops NaN operands
+    m = fmaxf(m, a);
+  }
+  for (long long i = (n4 << 2) + blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    m = fmaxf(m, fabsf(x[i]));
+  if (!(m < 3.0e38f)) m = 0.f;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  __shared__ float red[8];
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = m;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int w = 1; w < 8; ++w) m = fmaxf(m, red[w]);
+    atomicMax(out, __float_as_uint(m));
+  }
+}
+
 extern "C" {
 
 int san_cmul_conj_planar(const void* u, const float* planar, void* out, int N, int C, long long P, float sign,
@@ -205,6 +231,15 @@ int san_sens_normalize_bwd(const void* G, const float* s_planar, float* ds_plana
   const long long NP = (long long)N * P;
   sens_normalize_bwd_kernel<<<ew_grid(NP), 256, 0, (cudaStream_t)stream>>>((const float2*)G, s_planar, ds_planar, C, P,
                                                                            NP, eps);
+  SAN_LAUNCH_CHECK();
+  return SAN_OK;
+}
+
+int san_absmax(const float* x, long long n, float* out, void* stream) {
+  SAN_CHECK_ARG(x && out && n > 0, "san_absmax: bad args");
+  cudaStream_t st = (cudaStream_t)stream;
+  SAN_CUDA(cudaMemsetAsync(out, 0, sizeof(float), st));
+  absmax_kernel<<<ew_grid(n >> 2 > 0 ? n >> 2 : 1), 256, 0, st>>>(x, n, (unsigned int*)out);
   SAN_LAUNCH_CHECK();
   return SAN_OK;
 }

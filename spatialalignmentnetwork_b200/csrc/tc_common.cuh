@@ -106,7 +106,7 @@ __device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo_bytes
          ((uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32) | (1ull << 46);
 }
 // Instruction descriptor (cute::UMMA::InstrDescriptor): D fp32 (bit 4), A / B format (bits 7..9 / 10..12: 0 = f16,
-// 1 = bf16; the two operands may differ), A / B major (bits 15 / 16: 0 = K-major, 1 = MN-major), N>>3 at bit 17,
+// 1 = bf16; on the B200 both operands must use the SAME format - a mixed f16 x bf16 MMA faults), A / B major (bits 15 / 16: 0 = K-major, 1 = MN-major), N>>3 at bit 17,
 // M>>4 at bit 24.  fmt: bit 0 = A is an fp16 pair, bit 1 = B is an fp16 pair (else bf16 pairs), see TC_FMT_*.
 __host__ __device__ inline uint32_t umma_idesc_16(int M, int N, int fmt, int mn_major = 0) {
   return (1u << 4) | ((fmt & 1) ? 0u : (1u << 7)) | ((fmt & 2) ? 0u : (1u << 10)) | ((uint32_t)(mn_major ? 3 : 0) << 15) |
@@ -123,7 +123,10 @@ __host__ __device__ inline uint32_t umma_idesc_bf16(int M, int N, int mn_major =
 //              significant bits (|z - hi - lo| <= max(2^-24 |z|, 2^-25)), i.e. fp32-class products, for operands of
 //              known O(1) magnitude: normalised / activated activations and network inputs (s = TC_SX; the
 //              InstanceNorm bound |x| <= sqrt(H*W) keeps s*x far below the fp16 maximum, values are clamped anyway)
-//              and weights (s = TC_SW).  The kernel epilogue multiplies by the exact inverse scale.
+//              and weights (s = TC_SW); gradients (dY) use a DYNAMIC power-of-two scale from the tensor's largest
+//              magnitude (san_absmax -> tc_dyn_scale).  The kernel epilogue multiplies by the exact inverse scale.
+// The two operands of one MMA must share the format: mixing a bf16 with an f16 operand in kind::f16 raises an
+// illegal-instruction fault on the B200 (measured, round 2), so the backward GEMMs run on fp16 pairs as well.
 // Why: at the headline configuration (12 cascades, 320x320) bf16 pairs put img_rec 4.9e-3 from the fp32 reference on
 // ill-conditioned (fresh-init) weights, 26x the fp32-vs-fp64 floor (profiles/r2b_parity_*.json); fp16 pairs cost
 // the same 3 MMAs and the same bytes.
@@ -131,6 +134,17 @@ constexpr int TC_FMT_A_F16 = 1, TC_FMT_B_F16 = 2;
 constexpr float TC_SX = 16.f;       // activations: typical |x| ~ 0.5 -> 8; fp16 max 65504 -> |x| < 4094
 constexpr float TC_SW = 256.f;      // weights: Kaiming bound 0.02 .. 0.2 -> 5 .. 50; |w| < 255
 constexpr float TC_F16_MAX = 65504.f;
+
+// Dynamic scale of an fp16-pair operand whose magnitude is not known statically (gradients): the power of two that maps
+// the tensor's largest magnitude `amax` (device scalar from san_absmax) into [2^13, 2^14).  Elements down to 2^-28 of
+// the maximum keep full precision; smaller ones are absolutely negligible in a dot product.  amax == 0 -> 1.
+__device__ __forceinline__ float tc_dyn_scale(float amax) {
+  if (!(amax > 0.f) || amax > 3.0e38f) return 1.f;
+  int e = (int)((__float_as_uint(amax) >> 23) & 0xff) - 127;       // floor(log2(amax)) for normal numbers
+  e = 13 - e;
+  e = e < -100 ? -100 : (e > 100 ? 100 : e);
+  return __uint_as_float((uint32_t)(e + 127) << 23);
+}
 
 // (hi, lo) bit patterns of one value in the given pair format
 __device__ __forceinline__ void split16(float v, bool f16, float scale, unsigned short& hi, unsigned short& lo) {

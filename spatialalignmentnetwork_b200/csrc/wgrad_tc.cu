@@ -92,6 +92,7 @@ struct WgParams {
   int ngroups, ctas_per_group;
   int fmt;                    // TC_FMT_* bits: A = dY pair format, B = X pair format
   float out_scale;
+  const float* a_absmax;      // null, or device scalar max|dY| when dY was staged with the dynamic scale
   WgGeom g;
 };
 
@@ -237,6 +238,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_tc_kernel(const WgParams 
       if (stacked && row >= 8 * kga) row = (row < 16 * kga) ? row - 8 * kga : -1;
       const int co = row < 0 ? p.Cout : mb * 128 + row;
       const int KK = p.K * p.K;
+      const float oscale = p.a_absmax ? p.out_scale / tc_dyn_scale(__ldg(p.a_absmax)) : p.out_scale;
       for (int dx = 0; dx < ndx; ++dx) {
         const int tap = (p.K == 3) ? dyi * 3 + dx : 0;
         for (int c0 = 0; c0 < g.Nn; c0 += 8) {
@@ -246,7 +248,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_tc_kernel(const WgParams 
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
               const int ci = nc * g.Nn + c0 + j;
-              if (ci < p.Cin) atomicAdd(p.dw + ((long long)co * p.Cin + ci) * KK + tap, v[j] * p.out_scale);
+              if (ci < p.Cin) atomicAdd(p.dw + ((long long)co * p.Cin + ci) * KK + tap, v[j] * oscale);
             }
           }
         }
@@ -292,11 +294,14 @@ int san_tc_wgrad_supported(int H, int W, int Cin, int Cout, int K) {
 }
 
 int san_tc_wgrad(const void* dys, const void* xs, float* dw, float* dbias, const float* dy, int N, int H, int W, int Cin,
-                 int Cout, int K, int fmt, void* stream) {
-  SAN_CHECK_ARG(dys && xs && dw && N > 0 && H > 0 && W > 0 && Cin > 0 && Cout > 0 && fmt >= 0 && fmt <= 3, "san_tc_wgrad: bad args");
+                 int Cout, int K, int fmt, const float* dy_absmax, void* stream) {
+  SAN_CHECK_ARG(dys && xs && dw && N > 0 && H > 0 && W > 0 && Cin > 0 && Cout > 0 && (fmt == 0 || fmt == 3),
+                "san_tc_wgrad: bad args (fmt: 0 = bf16 pairs, 3 = fp16 pairs; the operands of an MMA share the format)");
+  SAN_CHECK_ARG(!dy_absmax || fmt == 3, "san_tc_wgrad: the dynamic scale applies to fp16 pairs only");
   WgParams p{};
-  p.fmt = fmt;   // A = staged dY, B = staged X; both were staged as ACTIVATIONS (scale TC_SX when an fp16 pair)
-  p.out_scale = ((fmt & TC_FMT_A_F16) ? 1.f / TC_SX : 1.f) * ((fmt & TC_FMT_B_F16) ? 1.f / TC_SX : 1.f);
+  p.fmt = fmt; p.a_absmax = dy_absmax;
+  // A = staged dY, B = staged X; both were staged as ACTIVATIONS: static scale TC_SX, or the dynamic one for dY
+  p.out_scale = ((fmt & TC_FMT_A_F16) && !dy_absmax ? 1.f / TC_SX : 1.f) * ((fmt & TC_FMT_B_F16) ? 1.f / TC_SX : 1.f);
   SAN_CHECK_ARG(wg_geometry(H, W, Cin, Cout, K, &p.g), "san_tc_wgrad: unsupported shape H=%d W=%d Cin=%d Cout=%d K=%d", H, W,
                 Cin, Cout, K);
   cudaStream_t st = (cudaStream_t)stream;

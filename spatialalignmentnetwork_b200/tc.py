@@ -22,17 +22,18 @@ from ._lib import call, lib
 MODE_DIRECT, MODE_POOL, MODE_D2S, MODE_UP = 0, 1, 2, 3
 _IN_EPS = 1e-5
 
-# 16-bit pair formats of the staged operands (include/san_b200.h): forward operands (normalised activations, network
-# inputs, weights: O(1) magnitudes) are fp16 pairs = fp32-class products; gradients (dY) are bf16 pairs (unbounded
-# exponent range).  The data- and weight-gradient GEMMs then multiply a bf16-pair operand with an fp16-pair one
-# (tcgen05 kind::f16 takes the two operand formats independently).  SAN_TC_FMT selects the A/B experiments:
-#   f16 (default) | f16nomix (fp16 pairs in the forward only; the backward re-stages X and W as bf16 pairs) |
-#   bf16 (round-1 behaviour: bf16 pairs everywhere).
+# 16-bit pair formats of the staged operands (include/san_b200.h).  Default: fp16 pairs everywhere = fp32-class
+# products at the cost of the same 3 MMAs: forward operands (normalised activations, network inputs, weights) with
+# static power-of-two scales, gradients (dY) with a dynamic one derived on the device from max|dY| (san_absmax).
+# The operands of one MMA must share the format (a mixed f16 x bf16 tcgen05 MMA faults on the B200).
+# SAN_TC_FMT selects the A/B experiments:
+#   f16 (default) | f16nomix (fp16 pairs in the forward only; the backward re-stages X and stages dY / W as bf16
+#   pairs: no dynamic scale, one more staging pass per conv) | bf16 (round-1 arithmetic: bf16 pairs everywhere).
 FMT_BF16, FMT_F16 = 0, 1
 _FMT_MODE = os.environ.get("SAN_TC_FMT", "f16")
 assert _FMT_MODE in ("f16", "f16nomix", "bf16"), _FMT_MODE
 _FMT_FWD = FMT_BF16 if _FMT_MODE == "bf16" else FMT_F16          # staged X and W of the forward conv
-_FMT_BWD = FMT_F16 if _FMT_MODE == "f16" else FMT_BF16           # staged X / W as the backward GEMMs read them
+_FMT_BWD = FMT_F16 if _FMT_MODE == "f16" else FMT_BF16           # staged dY, X and W of the backward GEMMs
 
 # Staged operands are as large as the activations they come from.  They are re-created in the backward
 # pass (for the weight gradient) unless HBM is plentiful: while live tensors take less than
@@ -113,8 +114,9 @@ def _staged_act(N, H, W, C, device):
     return torch.empty(lib().san_tc_staged_act_elems(N, H, W, C), dtype=torch.bfloat16, device=device)
 
 
-def _stage(xs, N, H, W, Cpad, terms, fmt):
-    """terms: list of (y, mu, a, b, slope, C, mode, accumulate); fmt: FMT_BF16 | FMT_F16."""
+def _stage(xs, N, H, W, Cpad, terms, fmt, absmax=None):
+    """terms: list of (y, mu, a, b, slope, C, mode, accumulate); fmt: FMT_BF16 | FMT_F16; absmax: device scalar
+    max|y| selecting the dynamic fp16-pair scale (gradient operands)."""
     arr = (_StageTerm * len(terms))()
     for t, (y, mu, a, b, slope, C, mode, acc) in zip(arr, terms):
         t.y = y.data_ptr()
@@ -122,7 +124,7 @@ def _stage(xs, N, H, W, Cpad, terms, fmt):
         t.a = a.data_ptr() if a is not None else None
         t.b = b.data_ptr() if b is not None else None
         t.slope, t.C, t.mode, t.accumulate = slope, C, mode, int(acc)
-    call("tc_stage_terms", xs, N, H, W, Cpad, ctypes.addressof(arr), len(terms), fmt)
+    call("tc_stage_terms", xs, N, H, W, Cpad, ctypes.addressof(arr), len(terms), fmt, absmax)
 
 
 def _stage_weights(w, dgrad, H, W, fmt):
@@ -182,7 +184,7 @@ class _FusedConv(Function):
         _stage(xs, N, H, W, _pad16(Cin), terms, _FMT_FWD)
         ws = _stage_weights(w, False, H, W, _FMT_FWD)
         out = torch.empty(N, Cout, H, W, dtype=torch.float32, device=w.device)
-        call("tc_conv", xs, ws, bias, out, N, H, W, Cin, Cout, K, 0, 3 * _FMT_FWD)
+        call("tc_conv", xs, ws, bias, out, N, H, W, Cin, Cout, K, 0, 3 * _FMT_FWD, None)
         # The staged operand is kept for the backward only while HBM is plentiful (_keep_staged); otherwise
         # the weight gradient re-stages it from the raw tensors, which autograd holds anyway for the
         # normalisation backward.
@@ -223,7 +225,11 @@ class _FusedConv(Function):
             ti += 3 if norm == "bn" else 1
         # dY staged once as BF16 hi/lo: the operand of both the data- and the weight-gradient GEMMs
         gys = _staged_act(N, H, W, Cout, dev)
-        _stage(gys, N, H, W, _pad16(Cout), [(gy, None, None, None, 1.0, Cout, MODE_DIRECT, False)], FMT_BF16)
+        amax = None
+        if _FMT_BWD == FMT_F16:          # dynamic power-of-two scale of the gradient operand
+            amax = torch.empty(1, dtype=torch.float32, device=dev)
+            call("absmax", gy, gy.numel(), amax)
+        _stage(gys, N, H, W, _pad16(Cout), [(gy, None, None, None, 1.0, Cout, MODE_DIRECT, False)], _FMT_BWD, amax)
         # ---- weight gradient: tcgen05 GEMM over the pixel dimension on the staged dY and the re-staged input
         dw = db = None
         if ctx.needs_input_grad[0] or (has_bias and ctx.needs_input_grad[1]):
@@ -237,8 +243,7 @@ class _FusedConv(Function):
                        [(t["y"], *_coef_views(t["norm"], t["st"])[:3], t["slope"], t["C"], t["mode"], t["acc"]) for t in terms],
                        _FMT_BWD)
             if lib().san_tc_wgrad_supported(H, W, Cin, Cout, K):
-                # A = dY (bf16 pair), B = X (fp16 pair unless SAN_TC_FMT says otherwise)
-                call("tc_wgrad", gys, xs, dw, db, gy if has_bias else None, N, H, W, Cin, Cout, K, 2 * _FMT_BWD)
+                call("tc_wgrad", gys, xs, dw, db, gy if has_bias else None, N, H, W, Cin, Cout, K, 3 * _FMT_BWD, amax)
             else:   # tiny images (W < 16): fp32 CUDA-core kernel on the un-staged operand
                 x32 = torch.empty(N, Cin, H, W, dtype=torch.float32, device=dev)
                 call("tc_unstage_act", xs, x32, N, Cin, H, W, _FMT_BWD)
@@ -250,7 +255,7 @@ class _FusedConv(Function):
         if any(ctx.needs_input_grad[3 + t["ti"]] for t in terms):
             wsd = _stage_weights(w, True, H, W, _FMT_BWD)
             dx = torch.empty(N, Cin, H, W, dtype=torch.float32, device=dev)
-            call("tc_conv", gys, wsd, None, dx, N, H, W, Cout, Cin, K, 0, 2 * _FMT_BWD)
+            call("tc_conv", gys, wsd, None, dx, N, H, W, Cout, Cin, K, 0, 3 * _FMT_BWD, amax)
             del gys
             for t in terms:
                 if not ctx.needs_input_grad[3 + t["ti"]]:

@@ -60,7 +60,7 @@ def _run(tag, n, coils, H, W, cascades, seed=20221017):
     for k, v in fw.items():
         assert v["vs_fp32"] < 1e-3, (k, v)
     assert gr["vs_fp64"] < max(3.0 * gr["fp32_vs_fp64"], 2e-3), gr
-    assert gr["cosine_vs_fp64"] > 0.999, gr
+    assert gr["cosine_vs_fp64"] > gr["fp32_cosine_vs_fp64"] - 0.01, gr          # same direction as well as the CPU fp32 oracle
     assert im["psnr_rec_vs_reference_rec_db"] > 60.0 and im["ssim_rec_vs_reference_rec"] > 0.9999, im
     return rep
 

@@ -32,18 +32,49 @@ def stage(x, fmt=BF16):
     return xs
 
 
-def conv_tc(x, w, bias=None, dgrad=False, fmt_a=BF16, fmt_b=BF16):
-    """fmt_a: pair format of the staged activations / dY, fmt_b: of the staged weights (may differ)."""
+def absmax(x):
+    L = _lib()
+    out = torch.empty(1, device=x.device)
+    L.call("absmax", x, x.numel(), out)
+    return out
+
+
+def stage_dyn(x):
+    """fp16 pairs with the dynamic power-of-two scale (gradient operands); -> (staged, absmax scalar)."""
+    L = _lib()
+    N, C, H, W = x.shape
+    xs = torch.empty(L.lib().san_tc_staged_act_elems(N, H, W, C), dtype=torch.bfloat16, device=x.device)
+    am = absmax(x)
+    term = tc_mod()._StageTerm(y=x.data_ptr(), mu=None, a=None, b=None, slope=1.0, C=C, mode=0, accumulate=0)
+    arr = (tc_mod()._StageTerm * 1)(term)
+    import ctypes
+    L.call("tc_stage_terms", xs, N, H, W, (C + 15) // 16 * 16, ctypes.addressof(arr), 1, F16, am)
+    return xs, am
+
+
+def tc_mod():
+    from spatialalignmentnetwork_b200 import tc
+    return tc
+
+
+def conv_tc(x, w, bias=None, dgrad=False, fmt=BF16, dyn=False):
+    """fmt: pair format of BOTH staged operands (the operands of an MMA share it); dyn: stage x with the dynamic
+    scale (as the data gradient stages dY)."""
     L = _lib()
     N, Cin, H, W = x.shape
     Cout, Cin_w, K, _ = w.shape
-    xs = stage(x, fmt_a)
+    fmt_a = fmt_b = fmt
+    am = None
+    if dyn:
+        xs, am = stage_dyn(x)
+    else:
+        xs = stage(x, fmt_a)
     ws = torch.empty(L.lib().san_tc_staged_weight_elems(H, W, Cin_w if dgrad else Cout, Cout if dgrad else Cin_w, K),
                      dtype=torch.bfloat16, device=x.device)
     L.call("tc_stage_weights", w, ws, H, W, Cout, Cin_w, K, int(dgrad), fmt_b)
     co = Cin_w if dgrad else Cout
     y = torch.empty(N, co, H, W, dtype=torch.float32, device=x.device)
-    L.call("tc_conv", xs, ws, bias, y, N, H, W, Cin, co, K, 0, fmt_a + 2 * fmt_b)
+    L.call("tc_conv", xs, ws, bias, y, N, H, W, Cin, co, K, 0, fmt_a + 2 * fmt_b, am)
     return y
 
 
@@ -69,12 +100,13 @@ def test_tc_conv_fwd_and_dgrad(case):
     yr = F.conv2d(xr, w.double(), b.double() if has_bias else None, padding=K // 2)
     (yr * gy.double()).sum().backward()
     # forward as the path runs it: fp16 pairs on both operands = fp32-class (the bar is 10x below the bf16-pair one)
-    y = conv_tc(x.cuda(), w.cuda(), b.cuda() if has_bias else None, fmt_a=F16, fmt_b=F16)
+    y = conv_tc(x.cuda(), w.cuda(), b.cuda() if has_bias else None, fmt=F16)
     e16 = rel_l2(y, yr)
     assert e16 < 2e-6, e16
-    # data gradient as the path runs it: dY as a bf16 pair x weights as an fp16 pair (mixed-format MMA)
-    dx = conv_tc(gy.cuda(), w.cuda(), None, dgrad=True, fmt_a=BF16, fmt_b=F16)
-    assert rel_l2(dx, xr.grad) < 2e-5
+    # data gradient as the path runs it: dY as fp16 pairs with the DYNAMIC scale (here gradients of magnitude 1e-7,
+    # far below the fp16 range without it), weights as fp16 pairs
+    dx = conv_tc(gy.cuda() * 1e-7, w.cuda(), None, dgrad=True, fmt=F16, dyn=True)
+    assert rel_l2(dx, xr.grad * 1e-7) < 2e-6
     # bf16 pairs on both operands (SAN_TC_FMT=bf16, the round-1 arithmetic)
     y = conv_tc(x.cuda(), w.cuda(), b.cuda() if has_bias else None)
     eb = rel_l2(y, yr)
@@ -235,13 +267,14 @@ def test_tc_wgrad(case):
     wr = w.double().requires_grad_(True)
     br = b.double().requires_grad_(True) if has_bias else None
     (F.conv2d(x.double(), wr, br, padding=K // 2) * gy.double()).sum().backward()
-    gys = stage(gy.cuda())
-    for fmt_x in (F16, BF16):          # the path: dY bf16 pair x X fp16 pair (mixed); round-1 arithmetic: both bf16
-        xs = stage(x.cuda(), fmt_x)
+    for fmt in (F16, BF16):          # the path: fp16 pairs (dY with the dynamic scale); round-1 arithmetic: bf16 pairs
+        xs = stage(x.cuda(), fmt)
+        gys, am = stage_dyn(gy.cuda()) if fmt == F16 else (stage(gy.cuda()), None)
         dw = torch.empty(Cout, Cin, K, K, device="cuda")
         db = torch.empty(Cout, device="cuda") if has_bias else None
-        L.call("tc_wgrad", gys, xs, dw, db, gy.cuda() if has_bias else None, N, H, W, Cin, Cout, K, 2 * fmt_x)
-        assert rel_l2(dw, wr.grad) < 2e-5, (fmt_x, rel_l2(dw, wr.grad))
+        L.call("tc_wgrad", gys, xs, dw, db, gy.cuda() if has_bias else None, N, H, W, Cin, Cout, K, 3 * fmt, am)
+        bar = 2e-6 if fmt == F16 else 2e-5
+        assert rel_l2(dw, wr.grad) < bar, (fmt, rel_l2(dw, wr.grad))
         if has_bias:
             assert rel_l2(db, br.grad) < 1e-5
 

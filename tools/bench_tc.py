@@ -41,16 +41,16 @@ def main():
         st = lambda: L.call("tc_stage_act", xs, N, HW, HW, Cpad, x, None, None, None, 1.0, Cin, 0,
                             None, None, None, None, 1.0, 0, 0, None, None, None, None, 1.0, 0, 0, 1)
         L.call("tc_stage_weights", w, ws, HW, HW, Cout, Cin, K, 0, 1)
-        cv = lambda: L.call("tc_conv", xs, ws, None, y, N, HW, HW, Cin, Cout, K, 0, 3)      # fp16 pairs, as the forward runs
+        cv = lambda: L.call("tc_conv", xs, ws, None, y, N, HW, HW, Cin, Cout, K, 0, 3, None)  # fp16 pairs, as the forward runs
         wp = ops._pack(w, False)
         y2 = torch.empty_like(y)
         fp = lambda: L.call("conv2d_fwd", x, wp, None, y2, N, Cin, HW, HW, Cout, K, 0, 0)
         gy = torch.randn(N, Cout, HW, HW, device="cuda")
         gys = torch.empty(L.lib().san_tc_staged_act_elems(N, HW, HW, Cout), dtype=torch.bfloat16, device="cuda")
         L.call("tc_stage_act", gys, N, HW, HW, (Cout + 15) // 16 * 16, gy, None, None, None, 1.0, Cout, 0,
-               None, None, None, None, 1.0, 0, 0, None, None, None, None, 1.0, 0, 0, 0)
+               None, None, None, None, 1.0, 0, 0, None, None, None, None, 1.0, 0, 0, 1)
         dw = torch.empty_like(w)
-        wg = lambda: L.call("tc_wgrad", gys, xs, dw, None, None, N, HW, HW, Cin, Cout, K, 2)   # dY bf16 pair x X fp16 pair
+        wg = lambda: L.call("tc_wgrad", gys, xs, dw, None, None, N, HW, HW, Cin, Cout, K, 3, None)   # fp16 pairs (timing only)
         t_wg = timeit(wg)
         t_st, t_cv, t_fp = timeit(st), timeit(cv), timeit(fp)
         fl = 2.0 * N * Cout * HW * HW * Cin * K * K

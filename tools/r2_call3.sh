@@ -10,7 +10,7 @@ done
 timeout 600 python -m pytest tests/test_gpu_models.py tests/test_gpu_ops.py -m gpu -x -q -p no:cacheprovider > gpurun_out/r2c_model_tests.log 2>&1; echo "model tests rc=$?"; tail -4 gpurun_out/r2c_model_tests.log | cut -c1-300
 timeout 600 python -m pytest tests/test_gpu_parity_full.py -m gpu -q -p no:cacheprovider -s > gpurun_out/r2c_parity.log 2>&1; echo "parity rc=$?"; grep -o '"forward": {"img_rec": {[^}]*}' gpurun_out/r2c_parity.log; grep -o '"all_concatenated": {[^}]*}' gpurun_out/r2c_parity.log
 cp gpurun_out/parity_cfg2_n2_320_c12.json gpurun_out/r2c_parity_cfg2_f16.json; cp gpurun_out/parity_cfg4_n1_15c_640x368_c12.json gpurun_out/r2c_parity_cfg4_f16.json
-SAN_TC_FMT=f16nomix timeout 300 python -m pytest tests/test_gpu_parity_full.py -m gpu -q -p no:cacheprovider -s -k cfg2 > gpurun_out/r2c_parity_nomix.log 2>&1; echo "parity nomix rc=$?"; grep -o '"forward": {"img_rec": {[^}]*}' gpurun_out/r2c_parity_nomix.log; grep -o '"all_concatenated": {[^}]*}' gpurun_out/r2c_parity_nomix.log
+SAN_TC_FMT=f16nomix timeout 400 python -m pytest tests/test_gpu_parity_full.py -m gpu -q -p no:cacheprovider -s -k cfg2 > gpurun_out/r2c_parity_nomix.log 2>&1; echo "parity nomix rc=$?"; grep -o '"forward": {"img_rec": {[^}]*}' gpurun_out/r2c_parity_nomix.log; grep -o '"all_concatenated": {[^}]*}' gpurun_out/r2c_parity_nomix.log
 for d in 1 0; do
   SAN_TC_DXN=$d timeout 300 python bench.py --steps 5 --warmup 3 --no-parity --no-cpu-baseline --breakdown gpurun_out/r2c_breakdown_dxn$d.json > gpurun_out/r2c_bench_dxn$d.json 2> gpurun_out/r2c_bench_dxn$d.err
   echo "bench DXN=$d rc=$?"; python -c "import json; d=json.load(open('gpurun_out/r2c_bench_dxn$d.json')); print(d['value'], d['roofline']['frac'], d['roofline']['avg_launch_ms'], d['kernel_time_shares'])"; tail -2 gpurun_out/r2c_bench_dxn$d.err
