@@ -192,9 +192,11 @@ int san_act_bwd_apply(const float* g, const float* y, const float* mu, const flo
 int san_act_bwd_reduce_map(const float* g, int Ctot, int c0, int mode, const float* y, const float* mu, const float* a,
                            const float* b, const float* sa, float slope, float* s1, float* s2, int N, int Cy, int Hy,
                            int Wy, void* stream);
+/* absmax (optional device scalar): receives max |dy| - the producing layer's backward stages dy as an fp16 pair with
+ * the dynamic scale derived from it, so no separate san_absmax pass over dy is needed */
 int san_act_bwd_apply_map(const float* g, int Ctot, int c0, int mode, const float* y, const float* mu, const float* a,
                           const float* b, float slope, const float* p, const float* q, const float* r, float* dy, int N,
-                          int Cy, int Hy, int Wy, void* stream);
+                          int Cy, int Hy, int Wy, float* absmax, void* stream);
 /* y = scale * (2x2 block sum of x): avg_pool2d (scale .25) and the adjoint of nearest up-sampling (scale 1) */
 int san_pool2(const float* x, float* y, long long planes, int H, int W, float scale, void* stream);
 /* y[2h+a,2w+b] = scale * x[h,w]: nearest x2 (scale 1) and the adjoint of avg_pool2d (scale .25) */

@@ -65,8 +65,9 @@ int tc_env_int(const char* name, int dflt) {
   const char* e = getenv(name);
   return e ? atoi(e) : dflt;
 }
-// SAN_TC_DXN = 0 disables the DXN form (A/B runs); SAN_TC_DXN_R = r forces its strip height (tuning runs)
-int tc_dxn_enabled() { static const int v = tc_env_int("SAN_TC_DXN", 1); return v; }
+// SAN_TC_DXN = 1 enables the DXN form (off by default: first measurement 1.34 vs 0.55 ms on 18->18 @320, the per-tile
+// epilogue chain of one warp is the critical path - profiles/r2d_*); SAN_TC_DXN_R = r forces its strip height (tuning runs)
+int tc_dxn_enabled() { static const int v = tc_env_int("SAN_TC_DXN", 0); return v; }
 int tc_dxn_force_r() { static const int v = tc_env_int("SAN_TC_DXN_R", 0); return v; }
 
 // DXN geometry; false if the layer does not qualify.  The strip height minimises a cycle estimate per output row:
@@ -470,13 +471,7 @@ __device__ __forceinline__ void store_split(__nv_bfloat16* xs, long long o_hi, l
                                             bool f16, float scale) {
   uint32_t hw[4], lw[4];
 #pragma unroll
-  for (int j = 0; j < 4; ++j) {
-    unsigned short h0, l0, h1, l1;
-    split16(v[2 * j], f16, scale, h0, l0);
-    split16(v[2 * j + 1], f16, scale, h1, l1);
-    hw[j] = (uint32_t)h0 | ((uint32_t)h1 << 16);
-    lw[j] = (uint32_t)l0 | ((uint32_t)l1 << 16);
-  }
+  for (int j = 0; j < 4; ++j) split16x2(v[2 * j], v[2 * j + 1], f16, scale, hw[j], lw[j]);
   *(uint4*)(xs + (o_hi + slot) * 8) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
   *(uint4*)(xs + (o_lo + slot) * 8) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
 }

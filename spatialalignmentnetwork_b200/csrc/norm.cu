@@ -313,13 +313,15 @@ __global__ void __launch_bounds__(256) act_bwd_apply_map_kernel(const GMap m, co
                                                                 const float* __restrict__ mu, const float* __restrict__ a,
                                                                 const float* __restrict__ b, float slope,
                                                                 const float* __restrict__ p, const float* __restrict__ q,
-                                                                const float* __restrict__ r, float* __restrict__ dy, int P) {
+                                                                const float* __restrict__ r, float* __restrict__ dy, int P,
+                                                                unsigned int* __restrict__ absmax) {
   const long long base = (long long)blockIdx.x * P;
   const float* gp = gmap_plane<MODE>(m, blockIdx.x);
   const float cm = mu ? mu[blockIdx.x] : 0.f;
   const float ca = a[blockIdx.x], cb = b ? b[blockIdx.x] : 0.f;
   const float cp = p[blockIdx.x], cq = q ? q[blockIdx.x] : 0.f, cr = r ? r[blockIdx.x] : 0.f;
   const int stride = gridDim.y * blockDim.x;
+  float am = 0.f;       // max |dy| of this thread (optional output: the dynamic fp16-pair scale of the consumer, tc_common.cuh)
   if (MODE == 0 && (P & 3) == 0) {
     const float4* y4 = (const float4*)(y + base);
     const float4* g4 = (const float4*)gp;
@@ -339,13 +341,12 @@ __global__ void __launch_bounds__(256) act_bwd_apply_map_kernel(const GMap m, co
         float gg = gv[k];
         if (fmaf(ca, yc, cb) <= 0.f) gg *= slope;
         yv[k] = fmaf(cp, gg, fmaf(cq, yc, cr));
+        am = fmaxf(am, fabsf(yv[k]));       // (the duplicated tail values of !has2 are real elements: harmless)
       }
       d4[i] = make_float4(yv[0], yv[1], yv[2], yv[3]);
       if (has2) d4[i2] = make_float4(yv[4], yv[5], yv[6], yv[7]);
     }
-    return;
-  }
-  if (MODE == 1 && (m.Wy & 3) == 0) {
+  } else if (MODE == 1 && (m.Wy & 3) == 0) {
     const float4* y4 = (const float4*)(y + base);
     float4* d4 = (float4*)(dy + base);
     const int n4 = P >> 2, w4 = m.Wy >> 2, wd = m.Wy >> 1;
@@ -361,12 +362,11 @@ __global__ void __launch_bounds__(256) act_bwd_apply_map_kernel(const GMap m, co
         float gg = gv[k];
         if (fmaf(ca, yc, cb) <= 0.f) gg *= slope;
         yv[k] = fmaf(cp, gg, fmaf(cq, yc, cr));
+        am = fmaxf(am, fabsf(yv[k]));
       }
       d4[i] = make_float4(yv[0], yv[1], yv[2], yv[3]);
     }
-    return;
-  }
-  if (MODE == 2 && (m.Wy & 3) == 0) {
+  } else if (MODE == 2 && (m.Wy & 3) == 0) {
     const float4* y4 = (const float4*)(y + base);
     float4* d4 = (float4*)(dy + base);
     const int n4 = P >> 2, w4 = m.Wy >> 2, q4 = m.Hy * w4, wd = 2 * m.Wy;
@@ -384,24 +384,34 @@ __global__ void __launch_bounds__(256) act_bwd_apply_map_kernel(const GMap m, co
         float gg = gv[k];
         if (fmaf(ca, yc, cb) <= 0.f) gg *= slope;
         yv[k] = fmaf(cp, gg, fmaf(cq, yc, cr));
+        am = fmaxf(am, fabsf(yv[k]));
       }
       d4[i] = make_float4(yv[0], yv[1], yv[2], yv[3]);
     }
-    return;
-  }
-  for (int i = blockIdx.y * blockDim.x + threadIdx.x; i < P; i += 2 * stride) {
-    const int i2 = i + stride;
-    const bool has2 = i2 < P;
-    const float ya = __ldg(y + base + i), ga = gmap_load<MODE>(gp, i, m.Hy, m.Wy);
-    const float yb = has2 ? __ldg(y + base + i2) : cm, gb = has2 ? gmap_load<MODE>(gp, i2, m.Hy, m.Wy) : 0.f;
-    float yc = ya - cm, gg = ga;
-    if (fmaf(ca, yc, cb) <= 0.f) gg *= slope;
-    dy[base + i] = fmaf(cp, gg, fmaf(cq, yc, cr));
-    if (has2) {
-      yc = yb - cm; gg = gb;
+  } else {
+    for (int i = blockIdx.y * blockDim.x + threadIdx.x; i < P; i += 2 * stride) {
+      const int i2 = i + stride;
+      const bool has2 = i2 < P;
+      const float ya = __ldg(y + base + i), ga = gmap_load<MODE>(gp, i, m.Hy, m.Wy);
+      const float yb = has2 ? __ldg(y + base + i2) : cm, gb = has2 ? gmap_load<MODE>(gp, i2, m.Hy, m.Wy) : 0.f;
+      float yc = ya - cm, gg = ga;
       if (fmaf(ca, yc, cb) <= 0.f) gg *= slope;
-      dy[base + i2] = fmaf(cp, gg, fmaf(cq, yc, cr));
+      float o = fmaf(cp, gg, fmaf(cq, yc, cr));
+      dy[base + i] = o;
+      am = fmaxf(am, fabsf(o));
+      if (has2) {
+        yc = yb - cm; gg = gb;
+        if (fmaf(ca, yc, cb) <= 0.f) gg *= slope;
+        o = fmaf(cp, gg, fmaf(cq, yc, cr));
+        dy[base + i2] = o;
+        am = fmaxf(am, fabsf(o));
+      }
     }
+  }
+  if (absmax) {      // one atomicMax per warp on the uint view (non-negative floats order like their bit patterns)
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) am = fmaxf(am, __shfl_xor_sync(0xffffffffu, am, o));
+    if ((threadIdx.x & 31) == 0 && am < 3.0e38f) atomicMax(absmax, __float_as_uint(am));
   }
 }
 
@@ -653,7 +663,7 @@ int san_act_bwd_reduce_map(const float* g, int Ctot, int c0, int mode, const flo
 
 int san_act_bwd_apply_map(const float* g, int Ctot, int c0, int mode, const float* y, const float* mu, const float* a,
                           const float* b, float slope, const float* p, const float* q, const float* r, float* dy, int N,
-                          int Cy, int Hy, int Wy, void* stream) {
+                          int Cy, int Hy, int Wy, float* absmax, void* stream) {
   SAN_CHECK_ARG(y && a && p && dy, "san_act_bwd_apply_map: bad args");
   int rc = gmap_check(g, N, Ctot, c0, Cy, Hy, Wy, mode, "san_act_bwd_apply_map");
   if (rc != SAN_OK) return rc;
@@ -661,11 +671,13 @@ int san_act_bwd_apply_map(const float* g, int Ctot, int c0, int mode, const floa
   const int planes = N * Cy, P = (mode == 2 ? 4 : 1) * Hy * Wy;
   dim3 grid(planes, chunks_for(planes, P));
   cudaStream_t st = (cudaStream_t)stream;
+  unsigned int* am = (unsigned int*)absmax;
+  if (am) SAN_CUDA(cudaMemsetAsync(am, 0, sizeof(float), st));
   switch (mode) {
-    case 0: act_bwd_apply_map_kernel<0><<<grid, 256, 0, st>>>(m, y, mu, a, b, slope, p, q, r, dy, P); break;
-    case 1: act_bwd_apply_map_kernel<1><<<grid, 256, 0, st>>>(m, y, mu, a, b, slope, p, q, r, dy, P); break;
-    case 2: act_bwd_apply_map_kernel<2><<<grid, 256, 0, st>>>(m, y, mu, a, b, slope, p, q, r, dy, P); break;
-    default: act_bwd_apply_map_kernel<3><<<grid, 256, 0, st>>>(m, y, mu, a, b, slope, p, q, r, dy, P); break;
+    case 0: act_bwd_apply_map_kernel<0><<<grid, 256, 0, st>>>(m, y, mu, a, b, slope, p, q, r, dy, P, am); break;
+    case 1: act_bwd_apply_map_kernel<1><<<grid, 256, 0, st>>>(m, y, mu, a, b, slope, p, q, r, dy, P, am); break;
+    case 2: act_bwd_apply_map_kernel<2><<<grid, 256, 0, st>>>(m, y, mu, a, b, slope, p, q, r, dy, P, am); break;
+    default: act_bwd_apply_map_kernel<3><<<grid, 256, 0, st>>>(m, y, mu, a, b, slope, p, q, r, dy, P, am); break;
   }
   SAN_LAUNCH_CHECK();
   return SAN_OK;

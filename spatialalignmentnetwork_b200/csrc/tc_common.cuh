@@ -160,6 +160,19 @@ __device__ __forceinline__ void split16(float v, bool f16, float scale, unsigned
     lo = __bfloat16_as_ushort(__float2bfloat16_rn(v - __bfloat162float(h)));
   }
 }
+// two values at once -> packed (hi0 | hi1 << 16), (lo0 | lo1 << 16): one F2FP (packed, saturating) per pair and half
+__device__ __forceinline__ void split16x2(float v0, float v1, bool f16, float scale, uint32_t& hw, uint32_t& lw) {
+  if (f16) {
+    const float z0 = v0 * scale, z1 = v1 * scale;
+    asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(hw) : "f"(z1), "f"(z0));     // saturates, NaN stays NaN
+    const float2 hf = __half22float2(*reinterpret_cast<const __half2*>(&hw));
+    asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(lw) : "f"(z1 - hf.y), "f"(z0 - hf.x));
+  } else {
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(hw) : "f"(v1), "f"(v0));
+    const float h0 = __uint_as_float(hw << 16), h1 = __uint_as_float(hw & 0xffff0000u);
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(lw) : "f"(v1 - h1), "f"(v0 - h0));
+  }
+}
 __device__ __forceinline__ float unsplit16(unsigned short hi, unsigned short lo, bool f16, float inv_scale) {
   if (f16) return (__half2float(__ushort_as_half(hi)) + __half2float(__ushort_as_half(lo))) * inv_scale;
   return __bfloat162float(__ushort_as_bfloat16(hi)) + __bfloat162float(__ushort_as_bfloat16(lo));

@@ -149,6 +149,24 @@ def _coef_views(norm, st):
     return st[2], st[3], st[4], st[5]
 
 
+def _tag_absmax(dy):
+    """Device scalar that the kernel writing ``dy`` fills with max|dy|; it rides on the tensor object to the producing
+    layer's backward (autograd hands the very same tensor over when the gradient has a single consumer).  The tensor
+    version is recorded: an in-place accumulation by the autograd engine invalidates the tag."""
+    if _FMT_BWD != FMT_F16:
+        return None
+    amax = torch.empty(1, dtype=torch.float32, device=dy.device)
+    dy._san_absmax = (amax, dy._version)
+    return amax
+
+
+def _known_absmax(gy):
+    tag = getattr(gy, "_san_absmax", None)
+    if tag is not None and tag[1] == gy._version and gy.is_contiguous():
+        return tag[0]
+    return None
+
+
 class _FusedConv(Function):
     """y = conv2d(concat_k sum_j act(norm(resample(raw_kj))), w) + bias on the tcgen05 kernels.
 
@@ -227,8 +245,10 @@ class _FusedConv(Function):
         gys = _staged_act(N, H, W, Cout, dev)
         amax = None
         if _FMT_BWD == FMT_F16:          # dynamic power-of-two scale of the gradient operand
-            amax = torch.empty(1, dtype=torch.float32, device=dev)
-            call("absmax", gy, gy.numel(), amax)
+            amax = _known_absmax(gy)     # left by the consumer's normalisation backward when it wrote gy
+            if amax is None:
+                amax = torch.empty(1, dtype=torch.float32, device=dev)
+                call("absmax", gy, gy.numel(), amax)
         _stage(gys, N, H, W, _pad16(Cout), [(gy, None, None, None, 1.0, Cout, MODE_DIRECT, False)], _FMT_BWD, amax)
         # ---- weight gradient: tcgen05 GEMM over the pixel dimension on the staged dY and the re-staged input
         dw = db = None
@@ -285,7 +305,7 @@ class _FusedConv(Function):
                     planes = N * C
                     ones = torch.ones(planes, dtype=torch.float32, device=dev)
                     call("act_bwd_apply_map", dx, Cin, c0, mode, y, None, ones, None, slope, ones, None, None, dy,
-                         N, C, Hy, Wy)
+                         N, C, Hy, Wy, _tag_absmax(dy))
                     grads[t["ti"]] = dy
                     continue
                 planes = st.shape[1]
@@ -301,7 +321,8 @@ class _FusedConv(Function):
                     call("bn_finalize_bwd", wk[0], wk[1], gamma, sa, wk[2], wk[3], wk[4], dgamma, dbeta,
                          y.shape[0], y.shape[1], P, int(t["bn_training"]))
                     grads[t["ti"] + 1], grads[t["ti"] + 2] = dgamma, dbeta
-                call("act_bwd_apply_map", dx, Cin, c0, mode, y, mu, a, b, slope, wk[2], wk[3], wk[4], dy, N, C, Hy, Wy)
+                call("act_bwd_apply_map", dx, Cin, c0, mode, y, mu, a, b, slope, wk[2], wk[3], wk[4], dy, N, C, Hy, Wy,
+                     _tag_absmax(dy))
                 grads[t["ti"]] = dy
         return (dw, db, None, *grads)
 
