@@ -197,6 +197,11 @@ int san_act_bwd_reduce_map(const float* g, int Ctot, int c0, int mode, const flo
 int san_act_bwd_apply_map(const float* g, int Ctot, int c0, int mode, const float* y, const float* mu, const float* a,
                           const float* b, float slope, const float* p, const float* q, const float* r, float* dy, int N,
                           int Cy, int Hy, int Wy, float* absmax, void* stream);
+/* InstanceNorm2d + LeakyReLU backward of varnet.py:141-145 in ONE kernel per tensor (the three calls above fused for
+ * per-plane statistics): one CTA per (n, c) plane reduces sum(g'), sum(g' xhat), forms the coefficients and applies
+ * them, re-reading the plane from L2 in reverse order.  mu / a = mean and rstd per plane (the 'in' coefficient table). */
+int san_in_bwd_fused_map(const float* g, int Ctot, int c0, int mode, const float* y, const float* mu, const float* a,
+                         float slope, float* dy, int N, int Cy, int Hy, int Wy, float* absmax, void* stream);
 /* y = scale * (2x2 block sum of x): avg_pool2d (scale .25) and the adjoint of nearest up-sampling (scale 1) */
 int san_pool2(const float* x, float* y, long long planes, int H, int W, float scale, void* stream);
 /* y[2h+a,2w+b] = scale * x[h,w]: nearest x2 (scale 1) and the adjoint of avg_pool2d (scale .25) */

@@ -415,6 +415,116 @@ __global__ void __launch_bounds__(256) act_bwd_apply_map_kernel(const GMap m, co
   }
 }
 
+// ---- InstanceNorm backward of one plane in ONE kernel: reduce -> coefficients -> apply (act_bwd_reduce_map +
+// in_finalize_bwd + act_bwd_apply_map).  One CTA per (n, c) plane.  The second pass walks the plane in REVERSE order,
+// most recently read data first, so that its reads of y and dx are served by the 126 MB L2 wherever the planes of the
+// resident CTAs fit (always below 320x320; partly there): 3 HBM passes (y, dx in; dy out) instead of 5.
+// 4 consecutive y pixels + their gradients through the map (vector paths need Wy % 4 == 0, else scalar fall-back).
+template <int MODE>
+__device__ __forceinline__ void fused_load4(const GMap& m, const float* __restrict__ yb, const float* __restrict__ gp, int i,
+                                            float* yv, float* gv) {
+  const float4 y4 = __ldg((const float4*)yb + i);
+  yv[0] = y4.x; yv[1] = y4.y; yv[2] = y4.z; yv[3] = y4.w;
+  if (MODE == 0) {
+    const float4 g4 = __ldg((const float4*)gp + i);
+    gv[0] = g4.x; gv[1] = g4.y; gv[2] = g4.z; gv[3] = g4.w;
+  } else if (MODE == 1) {
+    const int w4 = m.Wy >> 2, h = i / w4, wq = i - h * w4;
+    const float2 g2 = __ldg((const float2*)(gp + (h >> 1) * (m.Wy >> 1) + 2 * wq));
+    gv[0] = 0.25f * g2.x; gv[1] = gv[0]; gv[2] = 0.25f * g2.y; gv[3] = gv[2];
+  } else if (MODE == 2) {
+    const int w4 = m.Wy >> 2, q4 = m.Hy * w4;
+    const int sub = i / q4, r = i - sub * q4, h = r / w4, wq = r - h * w4;
+    const float4* gq = (const float4*)(gp + (2 * h + (sub >> 1)) * (2 * m.Wy) + 8 * wq);
+    const float4 ga = __ldg(gq), gb = __ldg(gq + 1);
+    gv[0] = (sub & 1) ? ga.y : ga.x; gv[1] = (sub & 1) ? ga.w : ga.z; gv[2] = (sub & 1) ? gb.y : gb.x; gv[3] = (sub & 1) ? gb.w : gb.z;
+  } else {
+#pragma unroll
+    for (int k = 0; k < 4; ++k) gv[k] = gmap_load<3>(gp, 4 * i + k, m.Hy, m.Wy);
+  }
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(1024) in_bwd_fused_map_kernel(const GMap m, const float* __restrict__ y,
+                                                                const float* __restrict__ mu, const float* __restrict__ a,
+                                                                float slope, float* __restrict__ dy, int P,
+                                                                unsigned int* __restrict__ absmax) {
+  __shared__ double red[32];
+  __shared__ float coef[3];
+  const long long base = (long long)blockIdx.x * P;
+  const float* gp = gmap_plane<MODE>(m, blockIdx.x);
+  const float* yb = y + base;
+  const float cm = mu[blockIdx.x], ca = a[blockIdx.x];
+  const bool vec = (P & 3) == 0 && (m.Wy & 3) == 0;
+  const int n4 = P >> 2;
+  float t1 = 0.f, t2 = 0.f;
+  if (vec) {
+    for (int i = threadIdx.x; i < n4; i += blockDim.x) {
+      float yv[4], gv[4];
+      fused_load4<MODE>(m, yb, gp, i, yv, gv);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const float yc = yv[k] - cm;
+        float gg = gv[k];
+        if (ca * yc <= 0.f) gg *= slope;
+        t1 += gg;
+        t2 += gg * (ca * yc);
+      }
+    }
+  } else {
+    for (int i = threadIdx.x; i < P; i += blockDim.x) {
+      const float yc = __ldg(yb + i) - cm;
+      float gg = gmap_load<MODE>(gp, i, m.Hy, m.Wy);
+      if (ca * yc <= 0.f) gg *= slope;
+      t1 += gg;
+      t2 += gg * (ca * yc);
+    }
+  }
+  const double r1 = block_sum_d((double)t1, red);
+  const double r2 = block_sum_d((double)t2, red);
+  if (threadIdx.x == 0) {           // in_finalize_bwd: dy = p g' + q (y - mu) + r
+    const double A = ca, M = P;
+    coef[0] = (float)A;
+    coef[1] = (float)(-A * A * (double)(float)r2 / M);
+    coef[2] = (float)(-A * (double)(float)r1 / M);
+  }
+  __syncthreads();
+  const float cp = coef[0], cq = coef[1], cr = coef[2];
+  float am = 0.f;
+  if (vec) {
+    float4* d4 = (float4*)(dy + base);
+    for (int k0 = threadIdx.x; k0 < n4; k0 += blockDim.x) {
+      const int i = n4 - 1 - k0;      // reverse: what the first pass read last is still in L2
+      float yv[4], gv[4];
+      fused_load4<MODE>(m, yb, gp, i, yv, gv);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const float yc = yv[k] - cm;
+        float gg = gv[k];
+        if (ca * yc <= 0.f) gg *= slope;
+        yv[k] = fmaf(cp, gg, fmaf(cq, yc, cr));
+        am = fmaxf(am, fabsf(yv[k]));
+      }
+      d4[i] = make_float4(yv[0], yv[1], yv[2], yv[3]);
+    }
+  } else {
+    for (int k0 = threadIdx.x; k0 < P; k0 += blockDim.x) {
+      const int i = P - 1 - k0;
+      const float yc = __ldg(yb + i) - cm;
+      float gg = gmap_load<MODE>(gp, i, m.Hy, m.Wy);
+      if (ca * yc <= 0.f) gg *= slope;
+      const float o = fmaf(cp, gg, fmaf(cq, yc, cr));
+      dy[base + i] = o;
+      am = fmaxf(am, fabsf(o));
+    }
+  }
+  if (absmax) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) am = fmaxf(am, __shfl_xor_sync(0xffffffffu, am, o));
+    if ((threadIdx.x & 31) == 0 && am < 3.0e38f) atomicMax(absmax, __float_as_uint(am));
+  }
+}
+
 // dx = rstd * (g' - mean(g') - xhat * mean(g' xhat)), xhat = rstd*(y - mu)  ->  dy = p g' + q (y - mu) + r
 __global__ void in_finalize_bwd_kernel(const float* __restrict__ s1, const float* __restrict__ s2,
                                        const float* __restrict__ a, float* __restrict__ p,
@@ -678,6 +788,30 @@ int san_act_bwd_apply_map(const float* g, int Ctot, int c0, int mode, const floa
     case 1: act_bwd_apply_map_kernel<1><<<grid, 256, 0, st>>>(m, y, mu, a, b, slope, p, q, r, dy, P, am); break;
     case 2: act_bwd_apply_map_kernel<2><<<grid, 256, 0, st>>>(m, y, mu, a, b, slope, p, q, r, dy, P, am); break;
     default: act_bwd_apply_map_kernel<3><<<grid, 256, 0, st>>>(m, y, mu, a, b, slope, p, q, r, dy, P, am); break;
+  }
+  SAN_LAUNCH_CHECK();
+  return SAN_OK;
+}
+
+int san_in_bwd_fused_map(const float* g, int Ctot, int c0, int mode, const float* y, const float* mu, const float* a,
+                         float slope, float* dy, int N, int Cy, int Hy, int Wy, float* absmax, void* stream) {
+  SAN_CHECK_ARG(y && mu && a && dy, "san_in_bwd_fused_map: bad args");
+  int rc = gmap_check(g, N, Ctot, c0, Cy, Hy, Wy, mode, "san_in_bwd_fused_map");
+  if (rc != SAN_OK) return rc;
+  const GMap m = make_gmap(g, Ctot, c0, Cy, Hy, Wy, mode);
+  const int planes = N * Cy, P = (mode == 2 ? 4 : 1) * Hy * Wy;
+  cudaStream_t st = (cudaStream_t)stream;
+  unsigned int* am = (unsigned int*)absmax;
+  if (am) SAN_CUDA(cudaMemsetAsync(am, 0, sizeof(float), st));
+  // threads per plane: a quarter of the float4 groups, 128 .. 1024 (big planes: one 1024-thread CTA per SM keeps the
+  // live planes of all SMs near the L2 capacity)
+  int nt = ((P / 16) + 31) / 32 * 32;
+  nt = nt < 128 ? 128 : (nt > 1024 ? 1024 : nt);
+  switch (mode) {
+    case 0: in_bwd_fused_map_kernel<0><<<planes, nt, 0, st>>>(m, y, mu, a, slope, dy, P, am); break;
+    case 1: in_bwd_fused_map_kernel<1><<<planes, nt, 0, st>>>(m, y, mu, a, slope, dy, P, am); break;
+    case 2: in_bwd_fused_map_kernel<2><<<planes, nt, 0, st>>>(m, y, mu, a, slope, dy, P, am); break;
+    default: in_bwd_fused_map_kernel<3><<<planes, nt, 0, st>>>(m, y, mu, a, slope, dy, P, am); break;
   }
   SAN_LAUNCH_CHECK();
   return SAN_OK;

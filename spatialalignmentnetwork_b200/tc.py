@@ -34,6 +34,8 @@ _FMT_MODE = os.environ.get("SAN_TC_FMT", "f16")
 assert _FMT_MODE in ("f16", "f16nomix", "bf16"), _FMT_MODE
 _FMT_FWD = FMT_BF16 if _FMT_MODE == "bf16" else FMT_F16          # staged X and W of the forward conv
 _FMT_BWD = FMT_F16 if _FMT_MODE == "f16" else FMT_BF16           # staged dY, X and W of the backward GEMMs
+# InstanceNorm backward as one kernel per tensor (san_in_bwd_fused_map); SAN_IN_BWD_FUSED=0: the three-kernel path
+_IN_BWD_FUSED = os.environ.get("SAN_IN_BWD_FUSED", "1") != "0"
 
 # Staged operands are as large as the activations they come from.  They are re-created in the backward
 # pass (for the weight gradient) unless HBM is plentiful: while live tensors take less than
@@ -311,6 +313,11 @@ class _FusedConv(Function):
                 planes = st.shape[1]
                 P = y.numel() // planes
                 mu, a, b, sa = _coef_views(t["norm"], st)
+                if t["norm"] == "in" and _IN_BWD_FUSED:
+                    # per-plane statistics: reduce + coefficients + apply in one kernel, second pass out of L2
+                    call("in_bwd_fused_map", dx, Cin, c0, mode, y, mu, a, slope, dy, N, C, Hy, Wy, _tag_absmax(dy))
+                    grads[t["ti"]] = dy
+                    continue
                 wk = torch.empty(5, planes, dtype=torch.float32, device=dev)
                 call("act_bwd_reduce_map", dx, Cin, c0, mode, y, mu, a, b, sa, slope, wk[0], wk[1], N, C, Hy, Wy)
                 if t["norm"] == "in":

@@ -332,3 +332,43 @@ def test_fused_conv_batchnorm_sum_up_pool():
     assert rel_l2(o2c, o2) < 2e-5
     for a, r in zip(ypc, ypr):
         assert rel_l2(a.grad, r.grad) < 5e-5
+
+
+@pytest.mark.parametrize("mode", [0, 1, 2, 3])
+@pytest.mark.parametrize("hw", [(12, 20), (9, 14)])          # Wy % 4 == 0 (vector paths) and not (scalar fall-back)
+def test_in_bwd_fused_map(mode, hw):
+    """san_in_bwd_fused_map (InstanceNorm + LeakyReLU backward, reduce + coefficients + apply in one kernel, gradient read
+    in place through the adjoint of the consumer's resampling) vs torch fp64 autograd of varnet.py:141-145 followed by
+    avg_pool2d / pixel shuffle / nearest x2, and vs the three-kernel path; the absmax side output = max |dy|."""
+    L = _lib()
+    torch.manual_seed(50 + mode)
+    N, Cy, Ctot, c0, slope = 2, 3, 7, 2, 0.2
+    Hy, Wy = hw
+    if mode == 1 and (Hy % 2 or Wy % 2):
+        Hy, Wy = Hy + Hy % 2, Wy + Wy % 2
+    y = (torch.randn(N, 4 * Cy if mode == 2 else Cy, Hy, Wy) * 1.5 + 0.3)
+    yr = y.double().requires_grad_(True)
+    if mode == 2:
+        z = F.leaky_relu(F.instance_norm(yr.reshape(N, Cy, 4 * Hy, Wy), eps=1e-5), slope).reshape(N, 4 * Cy, Hy, Wy)
+        op = F.pixel_shuffle(z, 2)
+    else:
+        z = F.leaky_relu(F.instance_norm(yr, eps=1e-5), slope)
+        op = z if mode == 0 else F.avg_pool2d(z, 2) if mode == 1 else F.interpolate(z, scale_factor=2, mode="nearest")
+    dx = torch.randn(N, Ctot, op.shape[2], op.shape[3]) * 1e-5          # gradients live far below 1
+    (op * dx[:, c0:c0 + Cy].double()).sum().backward()
+    yy = y.double().reshape(N, Cy, -1)
+    mu = yy.mean(2).reshape(-1).float().cuda()
+    a = (1 / torch.sqrt(yy.var(2, unbiased=False) + 1e-5)).reshape(-1).float().cuda()
+    yc, dxc = y.cuda(), dx.cuda()
+    dy, am = torch.empty_like(yc), torch.empty(1, device="cuda")
+    L.call("in_bwd_fused_map", dxc, Ctot, c0, mode, yc, mu, a, slope, dy, N, Cy, Hy, Wy, am)
+    assert rel_l2(dy, yr.grad) < 2e-5
+    assert abs(am.item() - dy.abs().max().item()) <= 1e-12
+    # the three-kernel path on the same inputs
+    planes = N * Cy
+    wk = torch.empty(5, planes, device="cuda")
+    L.call("act_bwd_reduce_map", dxc, Ctot, c0, mode, yc, mu, a, None, a, slope, wk[0], wk[1], N, Cy, Hy, Wy)
+    L.call("in_finalize_bwd", wk[0], wk[1], a, wk[2], wk[3], wk[4], planes, y.numel() // planes)
+    dy3, am3 = torch.empty_like(yc), torch.empty(1, device="cuda")
+    L.call("act_bwd_apply_map", dxc, Ctot, c0, mode, yc, mu, a, None, slope, wk[2], wk[3], wk[4], dy3, N, Cy, Hy, Wy, am3)
+    assert rel_l2(dy, dy3) < 2e-6 and abs(am3.item() - dy3.abs().max().item()) <= 1e-12
