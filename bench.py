@@ -220,10 +220,11 @@ NCU_TRAFFIC = {
 
 CLASSES = {
     "conv": ("conv2d_fwd", "conv2d_wgrad", "conv_pack_weights", "tc_conv", "tc_wgrad", "tc_stage_weights"),
-    "operand_staging": ("tc_stage_act", "tc_stage_terms", "tc_unstage_act"),
+    "operand_staging": ("tc_stage_act", "tc_stage_terms", "tc_unstage_act", "absmax"),
     "fft_dc": ("fft_expand_dc", "fft_reduce", "fft_rss", "fft2", "dc_bwd", "cmul_conj_planar"),
     "norm_act": ("plane_stats", "in_finalize_fwd", "bn_finalize_fwd", "affine_act_fwd", "act_bwd_reduce",
-                 "in_finalize_bwd", "bn_finalize_bwd", "act_bwd_apply", "act_bwd_reduce_map", "act_bwd_apply_map"),
+                 "in_finalize_bwd", "bn_finalize_bwd", "act_bwd_apply", "act_bwd_reduce_map", "act_bwd_apply_map",
+                 "in_bwd_fused_map"),
     "resample": ("pool2", "up2", "depth_to_space2", "space_to_depth2", "axpby"),
     "align_warp": ("grid_from_offset", "grid_to_nchw", "warp_fwd", "warp_bwd", "grad_loss_fwd", "grad_loss_bwd"),
     "losses": ("ssim_loss_fwd", "ssim_loss_bwd", "lncc_loss_fwd", "lncc_loss_bwd", "mi_hist_fwd", "mi_hist_bwd",
