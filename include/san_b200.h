@@ -157,6 +157,9 @@ int san_tc_wgrad_supported(int H, int W, int Cin, int Cout, int K);
 /* host-only: decomposition of san_tc_wgrad; out[16] = KGo, KGi, nmb, nnc, ndy, Nn, KGn, KC, XS, stages, smem_bytes,
  * nchunks, Wp, PS, range0, range_len (host pointer) */
 int san_tc_wgrad_describe(int H, int W, int Cin, int Cout, int K, int* out);
+/* host-only: out[2] = rown (1 = the three filter rows sit in the MMA N dimension: three row-shifted copies of the X
+ * span per stage, 3x3 layers with <= 48 padded input channels), ncp (X copies per stage) */
+int san_tc_wgrad_describe_form(int H, int W, int Cin, int Cout, int K, int* out);
 int san_tc_wgrad(const void* dys, const void* xs, float* dw, float* dbias, const float* dy, int N, int H, int W, int Cin,
                  int Cout, int K, int fmt, const float* dy_absmax, void* stream);
 

@@ -20,6 +20,12 @@
 // operand [hi; lo]: D = [hi; lo] * X_hi + [hi; lo] * X_lo gives all four partial products in 2 MMAs
 // (rows co and co + Cpad are both added into dW[co]); with <= 32 padded channels the stack is 64 rows
 // and the M = 64 UMMA shape halves the A read again.
+// "Filter rows in N" form (3x3, <= 48 padded input channels: the full- and half-resolution layers): an MMA with
+// N = 32 keeps the tensor pipe busy for 16 clk but needs 24 clk of operand reads, and the three filter rows used to be
+// three CTA groups that each re-loaded the dY chunk.  Here the X span is loaded THREE times, shifted by one image
+// row each ((dy-1)*Wp slots), as separate shared-memory planes [hl][dy][kg]: the channel-group stride of the B
+// operand stays uniform, so ONE MMA covers the three filter rows (N = 3*Nn = 96: tensor-bound), dY is loaded once,
+// and a CTA accumulates all nine taps ([3 dx] x [M x 3 Nn] fp32 in TMEM).
 //   warp 0: TMA producer (bulk copies of the dY chunk and the X span per stage)
 //   warp 1: TMEM allocator + single-thread MMA issuer
 //   warps 2..5: final epilogue (tcgen05.ld -> atomicAdd into dW[Cout][Cin][K][K])
@@ -41,7 +47,15 @@ struct WgGeom {
   int a_bytes, b_bytes, stage_bytes, stages, smem_bytes;
   int nchunks;             // pixel chunks per image
   int Wp, PS, range0, range_len;
+  int rown;                // 1: the three filter rows sit in the MMA N dimension (three row-shifted X copies per stage)
+  int ncp;                 // X copies per stage (3 in that form, else 1)
 };
+
+int wg_env_int(const char* name, int dflt) {
+  const char* e = getenv(name);
+  return e ? atoi(e) : dflt;
+}
+int wg_rown_enabled() { static const int v = wg_env_int("SAN_WG_ROWN", 1); return v; }   // 0: A/B runs against the per-row form
 
 bool wg_geometry(int H, int W, int Cin, int Cout, int K, WgGeom* g) {
   if (K != 1 && K != 3) return false;
@@ -54,7 +68,9 @@ bool wg_geometry(int H, int W, int Cin, int Cout, int K, WgGeom* g) {
     if (cip % k == 0 && (cip / k) % 16 == 0 && cip / k <= 160) { g->nnc = k; break; }
   if (!g->nnc) return false;
   g->Nn = cip / g->nnc; g->KGn = g->Nn / 8;
-  g->ndy = K;
+  g->rown = (K == 3 && 9 * g->Nn <= 512 && wg_rown_enabled()) ? 1 : 0;     // 3 dx accumulators of [M x 3 Nn] in 512 TMEM columns
+  g->ncp = g->rown ? 3 : 1;
+  g->ndy = g->rown ? 1 : K;
   g->Wp = W + 2; g->PS = (H + 2) * g->Wp;
   g->range0 = g->Wp;                                  // first slot of image row 0 (padded row 1)
   g->range_len = (H * g->Wp + 15) / 16 * 16;          // tail runs into the zero border row
@@ -66,7 +82,7 @@ bool wg_geometry(int H, int W, int Cin, int Cout, int K, WgGeom* g) {
   const int reach_groups = (stacked ? 0 : kga) + mg;  // groups spanned from the A start of a stage
   int best = 0, best_slack = 0;
   for (int kc = WG_KC_MAX; kc >= 32; kc -= 16) {
-    const int a = kga * 2 * kc * 16, b = g->KGn * 2 * (kc + 16) * 16;
+    const int a = kga * 2 * kc * 16, b = g->ncp * g->KGn * 2 * (kc + 16) * 16;
     int slack = reach_groups * kc * 16 - (a + b);
     if (slack < 0) slack = 0;
     if (2 * (a + b) + slack + WG_HEADER <= WG_SMEM_MAX) { best = kc; best_slack = slack; break; }
@@ -74,7 +90,7 @@ bool wg_geometry(int H, int W, int Cin, int Cout, int K, WgGeom* g) {
   if (!best) return false;
   g->KC = best; g->XS = best + 16;
   g->a_bytes = kga * 2 * g->KC * 16;
-  g->b_bytes = g->KGn * 2 * g->XS * 16;
+  g->b_bytes = g->ncp * g->KGn * 2 * g->XS * 16;
   g->stage_bytes = g->a_bytes + g->b_bytes;
   g->stages = (WG_SMEM_MAX - WG_HEADER - best_slack) / g->stage_bytes;
   if (g->stages > 4) g->stages = 4;
@@ -148,7 +164,9 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_tc_kernel(const WgParams 
   const int nc = (grp / g.ndy) % g.nnc;
   const int mb = grp / (g.ndy * g.nnc);
   const int kga = min(16, g.KGo - 16 * mb);          // channel groups of dY loaded for this M block
-  const int ndx = g.ndy;                             // 3 taps per filter row (1 for 1x1)
+  const int ndx = p.K;                               // 3 taps per filter row (1 for 1x1)
+  const int ncp = g.ncp;                             // row-shifted X copies per stage (3: filter rows in N)
+  const int Nmma = ncp * g.Nn;                       // MMA N: input channels of the chunk x filter rows
   const int nunits = p.N * g.nchunks;
   const long long plane = (long long)g.PS * 8;
   // slot offset of the X span relative to the dY chunk start: (dy-1)*Wp - 1 for 3x3, 0 for 1x1
@@ -160,7 +178,8 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_tc_kernel(const WgParams 
     // arithmetic was a serial bottleneck)
     int s = 0;
     uint32_t ph = 0;
-    const int ncopy = 2 * (kga + g.KGn);
+    const int per_hl = kga + ncp * g.KGn;
+    const int ncopy = 2 * per_hl;
     for (int u = cta; u < nunits; u += p.ctas_per_group) {
       const int n = u / g.nchunks, ch = u - n * g.nchunks;
       const int p0 = g.range0 + ch * g.KC;
@@ -168,18 +187,20 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_tc_kernel(const WgParams 
       const uint32_t bytesA = (uint32_t)kc * 16, bytesB = (uint32_t)(kc + 2) * 16;   // X span: kc + 2 tap slots
       mbar_wait(bar_empty + 8 * s, ph ^ 1);
       const uint32_t sbase = stage0 + (uint32_t)s * g.stage_bytes;
-      if (lane == 0) mbar_expect_tx(bar_full + 8 * s, 2u * kga * bytesA + 2u * g.KGn * bytesB);
+      if (lane == 0) mbar_expect_tx(bar_full + 8 * s, 2u * kga * bytesA + 2u * ncp * g.KGn * bytesB);
       __syncwarp();
       for (int c = lane; c < ncopy; c += 32) {
-        const int hl = c / (kga + g.KGn), r = c - hl * (kga + g.KGn);
+        const int hl = c / per_hl, r = c - hl * per_hl;
         if (r < kga) {
           const __nv_bfloat16* src = p.dys + ((long long)(n * 2 + hl) * g.KGo + 16 * mb + r) * plane + (long long)p0 * 8;
           bulk_g2s(sbase + (uint32_t)((hl * kga + r) * g.KC) * 16, src, bytesA, bar_full + 8 * s);
         } else {
-          const int kg = r - kga;
+          const int rr = r - kga;
+          const int cp = rr / g.KGn, kg = rr - cp * g.KGn;        // cp: row-shifted copy = filter row (rown form)
+          const int xo = g.rown ? (cp - 1) * g.Wp - 1 : xoff;
           const __nv_bfloat16* src =
-              p.xs + ((long long)(n * 2 + hl) * g.KGi + nc * g.KGn + kg) * plane + (long long)(p0 + xoff) * 8;
-          bulk_g2s(sbase + g.a_bytes + (uint32_t)((hl * g.KGn + kg) * g.XS) * 16, src, bytesB, bar_full + 8 * s);
+              p.xs + ((long long)(n * 2 + hl) * g.KGi + nc * g.KGn + kg) * plane + (long long)(p0 + xo) * 8;
+          bulk_g2s(sbase + g.a_bytes + (uint32_t)(((hl * ncp + cp) * g.KGn + kg) * g.XS) * 16, src, bytesB, bar_full + 8 * s);
         }
       }
       __syncwarp();
@@ -189,14 +210,14 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_tc_kernel(const WgParams 
     // whole warp runs the (warp-uniform) loops; one elected lane issues the tcgen05 instructions
     const bool stacked = 2 * kga <= 16;                // [hi; lo] of dY as one A operand
     const int M = (2 * kga <= 8) ? 64 : 128;
-    const uint32_t idesc = umma_idesc_16(M, g.Nn, p.fmt, /*mn_major=*/1);
+    const uint32_t idesc = umma_idesc_16(M, Nmma, p.fmt, /*mn_major=*/1);
     // MN-major, no swizzle: LBO = 128 B between 8-slot K groups, SBO = one staged plane between channel groups
     const uint64_t a_tmpl = umma_desc(0, 128, (uint32_t)g.KC * 16);
     const uint64_t b_tmpl = umma_desc(0, 128, (uint32_t)g.XS * 16);
     const uint32_t a_hiw = (uint32_t)(a_tmpl >> 32), b_hiw = (uint32_t)(b_tmpl >> 32);
     const uint32_t a_low = (uint32_t)a_tmpl, b_low = (uint32_t)b_tmpl;
     const uint32_t a_losplit = (uint32_t)(kga * g.KC);        // hi -> lo half, 16 B units
-    const uint32_t b_losplit = (uint32_t)(g.KGn * g.XS);
+    const uint32_t b_losplit = (uint32_t)(ncp * g.KGn * g.XS);
     int s = 0;
     uint32_t ph = 0;
     uint32_t started = 0;
@@ -210,11 +231,11 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_tc_kernel(const WgParams 
       if (elect_one_sync()) {
         // the issue loop is specialised on (taps per row, stacked) so that it is branch-free
         if (ndx == 3) {
-          if (stacked) wg_issue<3, true>(a_s, b_s, a_hiw, b_hiw, a_losplit, b_losplit, tmem_base, g.Nn, idesc, kc, started);
-          else wg_issue<3, false>(a_s, b_s, a_hiw, b_hiw, a_losplit, b_losplit, tmem_base, g.Nn, idesc, kc, started);
+          if (stacked) wg_issue<3, true>(a_s, b_s, a_hiw, b_hiw, a_losplit, b_losplit, tmem_base, Nmma, idesc, kc, started);
+          else wg_issue<3, false>(a_s, b_s, a_hiw, b_hiw, a_losplit, b_losplit, tmem_base, Nmma, idesc, kc, started);
         } else {
-          if (stacked) wg_issue<1, true>(a_s, b_s, a_hiw, b_hiw, a_losplit, b_losplit, tmem_base, g.Nn, idesc, kc, started);
-          else wg_issue<1, false>(a_s, b_s, a_hiw, b_hiw, a_losplit, b_losplit, tmem_base, g.Nn, idesc, kc, started);
+          if (stacked) wg_issue<1, true>(a_s, b_s, a_hiw, b_hiw, a_losplit, b_losplit, tmem_base, Nmma, idesc, kc, started);
+          else wg_issue<1, false>(a_s, b_s, a_hiw, b_hiw, a_losplit, b_losplit, tmem_base, Nmma, idesc, kc, started);
         }
         tc_commit(bar_empty + 8 * s);
         if (u + p.ctas_per_group >= nunits) tc_commit(bar_done);
@@ -240,14 +261,16 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_tc_kernel(const WgParams 
       const int KK = p.K * p.K;
       const float oscale = p.a_absmax ? p.out_scale / tc_dyn_scale(__ldg(p.a_absmax)) : p.out_scale;
       for (int dx = 0; dx < ndx; ++dx) {
-        const int tap = (p.K == 3) ? dyi * 3 + dx : 0;
-        for (int c0 = 0; c0 < g.Nn; c0 += 8) {
+        for (int c0 = 0; c0 < Nmma; c0 += 8) {       // column = (filter row, input channel) in the rown form (Nn % 8 == 0)
           float v[8];
-          tc_ld8(tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)(dx * g.Nn + c0), v);
+          tc_ld8(tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)(dx * Nmma + c0), v);
+          const int dye = g.rown ? c0 / g.Nn : dyi;
+          const int tap = (p.K == 3) ? dye * 3 + dx : 0;
+          const int cb = nc * g.Nn + c0 - (g.rown ? dye * g.Nn : 0);
           if (co < p.Cout) {
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
-              const int ci = nc * g.Nn + c0 + j;
+              const int ci = cb + j;
               if (ci < p.Cin) atomicAdd(p.dw + ((long long)co * p.Cin + ci) * KK + tap, v[j] * oscale);
             }
           }
@@ -285,6 +308,14 @@ int san_tc_wgrad_describe(int H, int W, int Cin, int Cout, int K, int* out) {
   const int v[16] = {g.KGo, g.KGi, g.nmb, g.nnc, g.ndy, g.Nn, g.KGn, g.KC, g.XS, g.stages, g.smem_bytes, g.nchunks,
                      g.Wp, g.PS, g.range0, g.range_len};
   for (int i = 0; i < 16; ++i) out[i] = v[i];
+  return SAN_OK;
+}
+
+// Host-only: out[0..1] = rown (1: the three filter rows sit in the MMA N dimension), ncp (row-shifted X copies per stage)
+int san_tc_wgrad_describe_form(int H, int W, int Cin, int Cout, int K, int* out) {
+  WgGeom g;
+  if (!out || !wg_geometry(H, W, Cin, Cout, K, &g)) return SAN_ERR_UNSUPPORTED;
+  out[0] = g.rown; out[1] = g.ncp;
   return SAN_OK;
 }
 

@@ -330,6 +330,7 @@ def test_tc_wgrad_formulation_on_cpu(built, shape):
     g = dict(zip("KGo KGi nmb nnc ndy Nn KGn KC XS stages smem_bytes nchunks Wp PS range0 range_len".split(), list(out)))
     Wp, PS, KC = g["Wp"], g["PS"], g["KC"]
     assert g["nnc"] * g["Nn"] == g["KGi"] * 8 and g["Nn"] % 16 == 0 and g["Nn"] <= 160 and 3 * g["Nn"] <= 512
+    import os
     assert g["nmb"] == -(-g["KGo"] // 16) and KC % 16 == 0 and g["range_len"] % 16 == 0 and g["stages"] >= 2
     assert g["range0"] == Wp and g["range0"] + g["range_len"] <= PS and g["smem_bytes"] <= 225 * 1024
     assert g["nchunks"] == -(-g["range_len"] // KC)
@@ -358,29 +359,41 @@ def test_tc_wgrad_formulation_on_cpu(built, shape):
         assert o >= 0 and o + nslots * 8 <= buf.numel()
         return buf[o:o + nslots * 8].reshape(nslots, 8).double()
 
+    form = (ctypes.c_int * 2)()
+    assert L.san_tc_wgrad_describe_form(H, W, Cin, Cout, K, ctypes.addressof(form)) == 0
+    rown, ncp = form[0], form[1]
+    # "filter rows in N": 3x3 layers with <= 48 padded input channels load three row-shifted copies of the X span
+    # and fold the filter rows into the MMA N dimension (one CTA group accumulates all nine taps)
+    assert rown == (1 if (K == 3 and 9 * g["Nn"] <= 512 and os.environ.get("SAN_WG_ROWN", "1") != "0") else 0)
+    assert ncp == (3 if rown else 1) and g["ndy"] == (1 if rown else K)
+    ndx = K
     dw = torch.zeros(Cout, Cin, K, K, dtype=torch.float64)
     for mb in range(g["nmb"]):
         kga = min(16, KGo - 16 * mb)
         for nc in range(g["nnc"]):
             for dyi in range(g["ndy"]):
-                xoff = (dyi - 1) * Wp - 1 if K == 3 else 0
-                D = [torch.zeros(kga * 8, g["Nn"], dtype=torch.float64) for _ in range(g["ndy"])]
+                rows = list(range(3)) if rown else [dyi]        # filter rows covered by this group's MMAs
+                Nmma = len(rows) * g["Nn"]
+                assert ndx * Nmma <= 512                         # TMEM columns of the dx accumulators
+                D = [torch.zeros(kga * 8, Nmma, dtype=torch.float64) for _ in range(ndx)]
                 for n in range(N):
                     for ch in range(g["nchunks"]):
                         p0 = g["range0"] + ch * KC
                         kc = min(KC, g["range_len"] - ch * KC)
                         A = [torch.cat([span(dys, KGo, n, hl, 16 * mb + k, p0, kc) for k in range(kga)], 1) for hl in (0, 1)]
-                        B = [torch.cat([span(xs, KGi, n, hl, nc * g["KGn"] + k, p0 + xoff, kc + 2) for k in range(g["KGn"])], 1)
-                             for hl in (0, 1)]
-                        for dx in range(g["ndy"]):
+                        # B planes [hl][row copy][kg]: the N index of the MMA is (row copy, channel)
+                        B = [torch.cat([span(xs, KGi, n, hl, nc * g["KGn"] + k, p0 + ((dy - 1) * Wp - 1 if K == 3 else 0), kc + 2)
+                                        for dy in rows for k in range(g["KGn"])], 1) for hl in (0, 1)]
+                        for dx in range(ndx):
                             Bh, Bl = B[0][dx:dx + kc], B[1][dx:dx + kc]
                             D[dx] += A[0].T @ Bh + A[1].T @ Bh + A[0].T @ Bl
-                for dx in range(g["ndy"]):
-                    tap = (dyi, dx) if K == 3 else (0, 0)
-                    co0, ci0 = mb * 128, nc * g["Nn"]
-                    nco, nci = min(kga * 8, Cout - co0), min(g["Nn"], Cin - ci0)
-                    if nco > 0 and nci > 0:
-                        dw[co0:co0 + nco, ci0:ci0 + nci, tap[0], tap[1]] += D[dx][:nco, :nci]
+                for dx in range(ndx):
+                    for ri, dy in enumerate(rows):
+                        tap = (dy, dx) if K == 3 else (0, 0)
+                        co0, ci0 = mb * 128, nc * g["Nn"]
+                        nco, nci = min(kga * 8, Cout - co0), min(g["Nn"], Cin - ci0)
+                        if nco > 0 and nci > 0:
+                            dw[co0:co0 + nco, ci0:ci0 + nci, tap[0], tap[1]] += D[dx][:nco, ri * g["Nn"]:ri * g["Nn"] + nci]
     assert rel_l2(dw, wr.grad) < 2e-5
 
 
