@@ -47,6 +47,8 @@ def parse():
                     help="weak: --batch slices per GPU; strong: --batch is the GLOBAL batch, split over the GPUs")
     ap.add_argument("--no-parity", action="store_true", help="skip the 2-slice parity block (oracle fp32 + fp64 on the host)")
     ap.add_argument("--no-overlap", action="store_true", help="N > 1: blocking flat all-reduce instead of the overlapped buckets")
+    ap.add_argument("--graph", action="store_true",
+                    help="N = 1: capture set_input + update() into ONE CUDA graph and time replays (small batches are launch-bound)")
     ap.add_argument("--cascades", type=int, default=12)
     ap.add_argument("--reg", default="Rec", choices=["Rec", "Mixed"],
                     help="training mode of the step: Rec = the headline cfg2 step; Mixed = BASELINE cfg5 (adds NetG twice, "
@@ -402,7 +404,7 @@ def workload_config(args, world, checkpoint, sample=None):
     cfg = {"workload": what, "reg": args.reg,
            "batch_per_gpu": bpg, "global_batch": bpg * world,
            "shape": args.shape if args.H == args.W else [args.H, args.W], "cascades": args.cascades, "coils": args.coils,
-           "parallelism": f"dp{world}", "checkpoint_cascades": bool(checkpoint),
+           "parallelism": f"dp{world}", "checkpoint_cascades": bool(checkpoint), "cuda_graph": bool(getattr(args, "graph", False)),
            "l2": f"inputs ({step_mb:.0f} MB/step) + activations (GBs) exceed the 126 MB L2; no flush needed"}
     if sample is not None:
         # the reference arm times a BOUNDED SAMPLE of the workload: say what really ran
@@ -536,18 +538,38 @@ def run_b200(args):
 
     for _ in range(max(args.warmup, args.min_warmup)):
         step_resident()
+    gstep = None
+    if args.graph:
+        assert world == 1, "--graph: single GPU (the gradient all-reduce is launched from autograd hooks, not captured)"
+        from spatialalignmentnetwork_b200.graphs import GraphedUpdate
+        gstep = GraphedUpdate(net, full_d, aux_d, warmup=1)
+
+        def step_resident():                    # noqa: F811  (inputs already in the graph's static buffers)
+            gstep.graph.replay()
+
+        def step_e2e():                         # noqa: F811
+            gstep(full_h, aux_h)                # H2D into the static buffers + replay
+            return gstep.loss_sim.item()
+        for _ in range(2):
+            step_resident()
     clocks = ClockSampler(local)
     if rank == 0:
         clocks.start()
     n0 = _lib.launch_count()
     ms_res = timed(step_resident, args.steps)
     launches = _lib.launch_count() - n0
+    if gstep is not None:
+        launches = gstep.launches_per_step * args.steps          # replays launch the captured kernels without host calls
     ms_e2e = timed(step_e2e, args.steps)
     clk = clocks.stop() if rank == 0 else None
     peak_mem = torch.cuda.max_memory_allocated(dev)
 
     roof = roof_fft = breakdown = None
     if not args.no_profile:
+        if gstep is not None:                   # the instrumented step runs eagerly (per-launch CUDA events)
+            def step_resident():                # noqa: F811
+                net.set_input(full_d, aux_d)
+                net.update()
         barrier()
         _lib.profile_begin()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

@@ -276,10 +276,12 @@ int san_mi_metric(const float* x, const float* y, int N, int P, int bins, float 
 
 /* ---- optimiser (model.py:72-81: torch.optim.AdamW, one instance per network) ---- */
 /* One AdamW step (no amsgrad) on `ntensors` fp32 tensors.  params / grads / exp_avg / exp_avg_sq / numel are HOST
- * arrays of device pointers (and element counts); `step` is the 1-based step count of the bias corrections. */
+ * arrays of device pointers (and element counts); `step` is the 1-based step count of the bias corrections.
+ * step_dev / sched_dev (optional, device int / float[2]): the step counter lives on the DEVICE instead - it is incremented
+ * and the bias-correction scalars are formed there (same fp64 arithmetic), which makes the call CUDA-graph capturable. */
 int san_adamw_step(void* const* params, const void* const* grads, void* const* exp_avg, void* const* exp_avg_sq,
                    const long long* numel, int ntensors, double lr, double beta1, double beta2, double eps,
-                   double weight_decay, int step, void* stream);
+                   double weight_decay, int step, int* step_dev, float* sched_dev, void* stream);
 
 #ifdef __cplusplus
 }

@@ -27,8 +27,11 @@ struct AdamTable {
 
 // decay = 1 - lr*wd, omb1 = 1 - beta1, omb2 = 1 - beta2, step = lr / (1 - beta1^t): formed in fp64 on the host and
 // rounded once, as torch does with its python-float hyper-parameters (1.f - 0.999f would be off by 1.3e-5)
+// sched (optional, device): {lr / (1 - beta1^t), sqrt(1 - beta2^t)} written by adamw_sched_kernel from the DEVICE-side
+// step counter - the CUDA-graph-capturable form (a host-side step number would be frozen into the graph)
 __global__ void __launch_bounds__(256) adamw_kernel(const AdamTable t, float decay, float omb1, float b2, float omb2,
-                                                    float eps, float step, float bc2_sqrt) {
+                                                    float eps, float step, float bc2_sqrt, const float* __restrict__ sched) {
+  if (sched) { step = sched[0]; bc2_sqrt = sched[1]; }
   int ti = 0;
   while (ti + 1 < t.nt && (int)blockIdx.x >= t.chunk0[ti + 1]) ++ti;
   const long long base = (long long)((int)blockIdx.x - t.chunk0[ti]) * AD_CHUNK;
@@ -49,16 +52,30 @@ __global__ void __launch_bounds__(256) adamw_kernel(const AdamTable t, float dec
   }
 }
 
+// t += 1 on the device; the two bias-correction scalars in fp64 exactly like the host path
+__global__ void adamw_sched_kernel(int* step, float* sched, double lr, double beta1, double beta2) {
+  const int t = *step + 1;
+  *step = t;
+  sched[0] = (float)(lr / (1.0 - pow(beta1, (double)t)));
+  sched[1] = (float)sqrt(1.0 - pow(beta2, (double)t));
+}
+
 }  // namespace
 
 extern "C" {
 
 int san_adamw_step(void* const* params, const void* const* grads, void* const* exp_avg, void* const* exp_avg_sq,
                    const long long* numel, int ntensors, double lr, double beta1, double beta2, double eps,
-                   double weight_decay, int step, void* stream) {
-  SAN_CHECK_ARG(params && grads && exp_avg && exp_avg_sq && numel && ntensors >= 0 && step >= 1, "san_adamw_step: bad args");
-  const double bc1 = 1.0 - pow(beta1, (double)step);
-  const float bc2_sqrt = (float)sqrt(1.0 - pow(beta2, (double)step));
+                   double weight_decay, int step, int* step_dev, float* sched_dev, void* stream) {
+  SAN_CHECK_ARG(params && grads && exp_avg && exp_avg_sq && numel && ntensors >= 0 && (step >= 1 || (step_dev && sched_dev)),
+                "san_adamw_step: bad args");
+  SAN_CHECK_ARG(!step_dev == !sched_dev, "san_adamw_step: step_dev and sched_dev go together");
+  const double bc1 = step_dev ? 1.0 : 1.0 - pow(beta1, (double)step);
+  const float bc2_sqrt = step_dev ? 1.f : (float)sqrt(1.0 - pow(beta2, (double)step));
+  if (step_dev) {      // device-side step counter (CUDA-graph capture): one increment per call
+    adamw_sched_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(step_dev, sched_dev, lr, beta1, beta2);
+    SAN_LAUNCH_CHECK();
+  }
   for (int t0 = 0; t0 < ntensors; t0 += AD_MAXT) {
     AdamTable tab;
     tab.nt = ntensors - t0 < AD_MAXT ? ntensors - t0 : AD_MAXT;
@@ -77,7 +94,7 @@ int san_adamw_step(void* const* params, const void* const* grads, void* const* e
     tab.chunk0[tab.nt] = blocks;
     adamw_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(tab, (float)(1.0 - lr * weight_decay), (float)(1.0 - beta1),
                                                            (float)beta2, (float)(1.0 - beta2), (float)eps,
-                                                           (float)(lr / bc1), bc2_sqrt);
+                                                           (float)(lr / bc1), bc2_sqrt, sched_dev);
     SAN_LAUNCH_CHECK();
   }
   return SAN_OK;

@@ -600,7 +600,7 @@ def test_abi_argument_validation_without_gpu(built):
         (L.san_warp_reflect(p, p, p, 1, 1, 8, 8, 8, 8, 3, None), "bad args"),
         (L.san_filter2d(p, p, p, 1, 8, 8, 4, None), "bad args"),                     # even window
         (L.san_sn_sigma(p, p, p, p, p, 0, 4, 1e-12, 1, None), "bad args"),
-        (L.san_adamw_step(p, p, p, p, p, 1, 1e-4, 0.9, 0.999, 1e-8, 0.0, 0, None), "bad args"),     # step counts from 1
+        (L.san_adamw_step(p, p, p, p, p, 1, 1e-4, 0.9, 0.999, 1e-8, 0.0, 0, None, None, None), "bad args"),     # step counts from 1
         (L.san_tc_conv(p, p, None, p, 1, 8, 8, 4, 4, 5, 0, 3, None, None), "unsupported shape"),  # 5x5 filter
         (L.san_tc_conv(p, p, None, p, 1, 8, 8, 4, 4, 3, 0, 2, None, None), "bad args"),     # mixed pair formats fault on the B200
         (L.san_tc_conv(p, p, None, p, 1, 8, 8, 4, 4, 3, 0, 0, p, None), "dynamic scale"),  # dynamic scale needs fp16 pairs

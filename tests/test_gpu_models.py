@@ -300,3 +300,46 @@ def test_optional_registration_terms():
     net.set_input(full.to(torch.complex64), aux.to(torch.complex64))
     net.update()
     assert {"loss_lncc", "loss_mi"} <= set(net.get_vis("scalars")["scalars"])
+
+
+def test_graphed_update_matches_eager():
+    """graphs.GraphedUpdate: set_input + update() captured into one CUDA graph; two replays on two batches leave the
+    same weights and the same loss as two eager steps from the same initial state (AdamW step counter on the device)."""
+    import copy
+    import random
+    from spatialalignmentnetwork_b200 import model as M
+    from spatialalignmentnetwork_b200.graphs import GraphedUpdate
+    torch.manual_seed(5)
+    random.seed(5)
+    cfg = M.Config(sparsity=0.25, lr=1e-4, shape=64, coils=1, reg="Rec", mask="equispaced", weight_smooth=1000.0,
+                   weight_sim=1.0, num_cascades=2, gan_layers_G=[4, 8, 8], gan_layers_D=[[4, 4], [8, 8]])
+    net = M.CSModel(cfg).to("cuda")
+    with torch.no_grad():
+        torch.nn.init.normal_(net.net_T.net[-1].weight, 0, 1e-2)
+    sd = {k: copy.deepcopy(getattr(net, k).state_dict()) for k in ("net_T", "net_R")}
+    g = torch.Generator().manual_seed(6)
+    batches = [[torch.complex(torch.rand(2, 1, 64, 64, generator=g), torch.rand(2, 1, 64, 64, generator=g)).cuda()
+                for _ in range(2)] for _ in range(3)]
+    net.train()
+    # eager: warm-up batch (the graph's warm-up does the same step), then two more
+    losses = []
+    for full, aux in batches:
+        net.set_input(full, aux)
+        net.update()
+        losses.append(net.loss_sim.item())
+    eager = {k: v.detach().clone() for k, v in list(net.net_T.state_dict().items()) + list(net.net_R.state_dict().items())}
+    # graphed, from the same initial state with fresh optimisers
+    random.seed(5)
+    net2 = M.CSModel(cfg).to("cuda")
+    for k in sd:
+        getattr(net2, k).load_state_dict(sd[k])
+    net2.train()
+    gs = GraphedUpdate(net2, batches[0][0], batches[0][1], warmup=1)      # warm-up = step 1 on batch 0
+    assert gs.launches_per_step > 100
+    # the capture itself does not execute: steps 2 and 3 are the replays
+    l2 = gs(*batches[1]).item()
+    l3 = gs(*batches[2]).item()
+    assert abs(l2 - losses[1]) < 1e-4 * abs(losses[1]) and abs(l3 - losses[2]) < 1e-4 * abs(losses[2]), (l2, l3, losses)
+    got = dict(list(net2.net_T.state_dict().items()) + list(net2.net_R.state_dict().items()))
+    worst = max(rel_l2(got[k], v) for k, v in eager.items() if v.is_floating_point() and v.numel() > 1)
+    assert worst < 1e-3, worst
