@@ -57,6 +57,7 @@ struct TcGeom {
   int a_bytes, b_bytes, stage_bytes, smem_bytes;
   int dxn, Np;             // DXN form: horizontal taps in the MMA N dimension, Np = Cout padded to 8 (Npad = pad16(3*Np))
   int wtaps;               // weight blocks per K-step: 9 (3x3), 3 (DXN: one per filter row) or 1 (1x1)
+  int hls, Ncol;           // HLS form: [W_hi | W_lo] stacked along the MMA N dimension; Ncol = TMEM columns per tile
   int xchg_bytes;          // DXN: shared-memory exchange area of the epilogue (quarter-boundary lanes)
 };
 
@@ -69,6 +70,43 @@ int tc_env_int(const char* name, int dflt) {
 // epilogue chain of one warp is the critical path - profiles/r2d_*); SAN_TC_DXN_R = r forces its strip height (tuning runs)
 int tc_dxn_enabled() { static const int v = tc_env_int("SAN_TC_DXN", 0); return v; }
 int tc_dxn_force_r() { static const int v = tc_env_int("SAN_TC_DXN_R", 0); return v; }
+// SAN_TC_HLS = 0 disables the hi/lo-stacked form of narrow 3x3 layers (A/B runs); SAN_TC_HLS_R = r forces its strip height
+int tc_hls_enabled() { static const int v = tc_env_int("SAN_TC_HLS", 1); return v; }
+int tc_hls_force_r() { static const int v = tc_env_int("SAN_TC_HLS_R", 0); return v; }
+
+// HLS geometry for narrow 3x3 layers (<= 48 padded output channels): B = [W_hi | W_lo] stacked along N, so that
+// A_hi is read from shared memory ONCE for the two products hi*hi and hi*lo (N = 2*Npad), plus one MMA A_lo x W_hi
+// (N = Npad): 2 reads of the 4 KB A tile per tap instead of 3 (the operand read, not the tensor pipe, bounds these
+// layers); the epilogue adds the two column blocks of a pixel.  Costs 2x the TMEM columns, so strips are one image
+// row at W = 320 to keep the accumulators double-buffered; chosen by the same cycle estimate as above.
+bool tc_geometry_hls(int H, int W, int Cin, int Cout, TcGeom* g) {
+  const int Npad = pad16(Cout);
+  if (Npad > 48) return false;
+  const int Ncol = 2 * Npad, Wp = W + 2, KS = pad16(Cin) / 16;
+  const int b_bytes = 9 * 4 * Npad * 16;
+  const int force = tc_hls_force_r();
+  int bestR = 0;
+  double best = 1e30;
+  for (int R = 1; R <= H; ++R) {
+    const int T = (R * Wp + 127) / 128;
+    if (T * Ncol > 512) break;
+    const int S = ((128 * T + 2 * Wp + 2) + 7) / 8 * 8;
+    if (2 * (4 * S * 16 + b_bytes) + TC_SMEM_HEADER > TC_SMEM_MAX) break;
+    if (force && R != force) continue;
+    const double rd1 = (4096.0 + Ncol * 32.0) / 128.0, rd2 = (4096.0 + Npad * 32.0) / 128.0;
+    const double mma = (double)T * KS * 9.0 * (fmax(rd1, Ncol / 2.0) + fmax(rd2, Npad / 2.0));
+    const double epi = (double)T * Ncol * 8.0 * 2.0;          // TMEM read at 64 B/clk + the per-warp latency chain
+    const bool dbl = 2 * T * Ncol <= 512;
+    const int strips = (H + R - 1) / R;
+    const double per_row = (dbl ? fmax(mma, epi) : mma + epi) * strips / (double)H * (1.0 + 0.1 / R);
+    if (per_row < best - 1e-9) { best = per_row; bestR = R; }
+  }
+  if (!bestR) return false;
+  g->hls = 1; g->nsplit = 1; g->Npad = Npad; g->Ncol = Ncol; g->b_bytes = b_bytes;
+  g->R = bestR;
+  g->T = (g->R * Wp + 127) / 128;
+  return true;
+}
 
 // DXN geometry; false if the layer does not qualify.  The strip height minimises a cycle estimate per output row:
 // MMA phase (9 MMAs per tile and K-step, each max(operand read at 128 B/clk, tensor N/2 clk)) against the epilogue's
@@ -131,8 +169,10 @@ bool tc_geometry(int H, int W, int Cin, int Cout, int K, TcGeom* g) {
   g->Cin_pad = pad16(Cin); g->KG = g->Cin_pad / 8; g->KS = g->Cin_pad / 16;
   g->Wp = W + 2; g->Hp = H + 2; g->PS = g->Hp * g->Wp;
   const int ntaps = K * K;
-  g->dxn = 0; g->Np = 0; g->wtaps = ntaps; g->xchg_bytes = 0;
-  if (!(K == 3 && tc_dxn_enabled() && tc_geometry_dxn(H, W, Cin, Cout, g))) {
+  g->dxn = 0; g->Np = 0; g->wtaps = ntaps; g->xchg_bytes = 0; g->hls = 0;
+  if (K == 3 && tc_dxn_enabled() && tc_geometry_dxn(H, W, Cin, Cout, g)) {
+  } else if (K == 3 && tc_hls_enabled() && tc_geometry_hls(H, W, Cin, Cout, g)) {
+  } else {
     // split the output channels until a strip (A rows + the weight block of one K-step, two stages) fits
     int bestR = 0;
     for (g->nsplit = (pad16(Cout) + TC_NMAX - 1) / TC_NMAX; g->nsplit <= 16; ++g->nsplit) {
@@ -145,6 +185,7 @@ bool tc_geometry(int H, int W, int Cin, int Cout, int K, TcGeom* g) {
     g->R = bestR;
     g->T = (g->R * g->Wp + 127) / 128;
   }
+  if (!g->hls) g->Ncol = g->Npad;
   g->S_alloc = ((128 * g->T + 2 * g->Wp + 2) + 7) / 8 * 8;
   g->a_bytes = 4 * g->S_alloc * 16;
   g->stage_bytes = g->a_bytes + g->b_bytes;
@@ -152,7 +193,7 @@ bool tc_geometry(int H, int W, int Cin, int Cout, int K, TcGeom* g) {
   if (g->stages > 4) g->stages = 4;
   if (g->stages < 2) return false;
   g->strips = (H + g->R - 1) / g->R;
-  g->acc_stages = (2 * g->T * g->Npad <= 512) ? 2 : 1;
+  g->acc_stages = (2 * g->T * g->Ncol <= 512) ? 2 : 1;
   g->smem_bytes = TC_SMEM_HEADER + g->xchg_bytes + g->stages * g->stage_bytes;
   if (g->smem_bytes < 120 * 1024) g->smem_bytes = 120 * 1024;  // one CTA per SM (each allocates all 512 TMEM columns)
   return true;
@@ -178,9 +219,11 @@ __device__ __forceinline__ void mma_issue_loop(const ConvTcParams& p, const TcGe
                                                uint32_t stage0, uint32_t bar_full, uint32_t bar_empty,
                                                uint32_t bar_accf, uint32_t bar_acce) {
   const uint32_t idesc = umma_idesc_16(128, g.Npad, p.fmt);
+  const uint32_t idesc2 = umma_idesc_16(128, 2 * g.Npad, p.fmt);      // HLS form: N = [W_hi | W_lo]
+  const bool hls = g.hls != 0;
   // descriptor templates (address field = 0) and per-tap offsets in 16 B units
   const uint64_t a_tmpl = umma_desc(0, (uint32_t)g.S_alloc * 16, 128);
-  const uint64_t b_tmpl = umma_desc(0, (uint32_t)g.Npad * 16, 128);
+  const uint64_t b_tmpl = umma_desc(0, (uint32_t)(hls ? 2 * g.Npad : g.Npad) * 16, 128);   // LBO = one kk plane of B rows
   const uint32_t a_hi = (uint32_t)(a_tmpl >> 32), b_hi = (uint32_t)(b_tmpl >> 32);
   const uint32_t a_lo0 = (uint32_t)a_tmpl, b_lo0 = (uint32_t)b_tmpl;
   uint32_t tap_off[NTAPS];
@@ -195,7 +238,7 @@ __device__ __forceinline__ void mma_issue_loop(const ConvTcParams& p, const TcGe
   for (int u = blockIdx.x; u < p.nunits; u += gridDim.x) {
     mbar_wait(bar_acce + 8 * as, aph ^ 1);
     tc_fence_after();
-    const uint32_t acc0 = tmem_base + (uint32_t)(as * g.T * g.Npad);
+    const uint32_t acc0 = tmem_base + (uint32_t)(as * g.T * g.Ncol);
     for (int ks = 0; ks < g.KS; ++ks) {
       mbar_wait(bar_full + 8 * s, ph);
       tc_fence_after();
@@ -204,16 +247,31 @@ __device__ __forceinline__ void mma_issue_loop(const ConvTcParams& p, const TcGe
       const uint32_t first = (ks != 0);
       if (elect_one_sync()) {
         uint32_t d = acc0, a_t = a_lo0 + a_s;
-        for (int t = 0; t < g.T; ++t, d += g.Npad, a_t += 128) {
+        if (hls) {
+          // B block of a tap = [kk][2*Npad rows: W_hi then W_lo][8]: A_hi x [W_hi | W_lo] (N = 2*Npad) + A_lo x W_hi (N = Npad)
+          for (int t = 0; t < g.T; ++t, d += g.Ncol, a_t += 128) {
 #pragma unroll
-          for (int tap = 0; tap < NTAPS; ++tap) {
-            const uint32_t al = a_t + tap_off[tap];
-            const uint32_t bl = b_lo0 + b_s + tap * b_tapstride;
-            const uint64_t A_hi = ((uint64_t)a_hi << 32) | al, A_lo = ((uint64_t)a_hi << 32) | (al + a_losplit);
-            const uint64_t B_hi = ((uint64_t)b_hi << 32) | bl, B_lo = ((uint64_t)b_hi << 32) | (bl + b_losplit);
-            tc_mma_bf16(d, A_hi, B_hi, idesc, tap == 0 ? first : 1u);   // hi*hi
-            tc_mma_bf16(d, A_lo, B_hi, idesc, 1u);                      // lo*hi
-            tc_mma_bf16(d, A_hi, B_lo, idesc, 1u);                      // hi*lo
+            for (int tap = 0; tap < NTAPS; ++tap) {
+              const uint32_t al = a_t + tap_off[tap];
+              const uint32_t bl = b_lo0 + b_s + tap * b_tapstride;
+              const uint64_t A_hi = ((uint64_t)a_hi << 32) | al, A_lo = ((uint64_t)a_hi << 32) | (al + a_losplit);
+              const uint64_t B_all = ((uint64_t)b_hi << 32) | bl;
+              tc_mma_bf16(d, A_hi, B_all, idesc2, tap == 0 ? first : 1u);   // hi*hi -> columns [0, Npad), hi*lo -> [Npad, 2 Npad)
+              tc_mma_bf16(d, A_lo, B_all, idesc, 1u);                       // lo*hi -> columns [0, Npad)
+            }
+          }
+        } else {
+          for (int t = 0; t < g.T; ++t, d += g.Npad, a_t += 128) {
+#pragma unroll
+            for (int tap = 0; tap < NTAPS; ++tap) {
+              const uint32_t al = a_t + tap_off[tap];
+              const uint32_t bl = b_lo0 + b_s + tap * b_tapstride;
+              const uint64_t A_hi = ((uint64_t)a_hi << 32) | al, A_lo = ((uint64_t)a_hi << 32) | (al + a_losplit);
+              const uint64_t B_hi = ((uint64_t)b_hi << 32) | bl, B_lo = ((uint64_t)b_hi << 32) | (bl + b_losplit);
+              tc_mma_bf16(d, A_hi, B_hi, idesc, tap == 0 ? first : 1u);   // hi*hi
+              tc_mma_bf16(d, A_lo, B_hi, idesc, 1u);                      // lo*hi
+              tc_mma_bf16(d, A_hi, B_lo, idesc, 1u);                      // hi*lo
+            }
           }
         }
         tc_commit(bar_empty + 8 * s);  // frees the smem stage when these MMAs retire
@@ -325,7 +383,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const ConvTcPara
           const bool valid = (r < g.R) && (x < p.W) && (yy < p.H) && lane < 30;
           float* dst = yn + (long long)yy * p.W + x;
           float* xc = xch + (size_t)((t * 4 + wq) * 5) * Np;
-          const uint32_t trow = tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)(as * g.T * g.Npad + t * g.Npad);
+          const uint32_t trow = tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)(as * g.T * g.Ncol + t * g.Ncol);
           for (int c0 = 0; c0 < Np; c0 += 8) {
             float e0[8], e1[8], e2[8];
             tc_ld8x3(trow + c0, trow + Np + c0, trow + 2 * Np + c0, e0, e1, e2);
@@ -379,10 +437,17 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const ConvTcPara
         const int yy = y0 + r;
         const bool valid = (r < g.R) && (x < p.W) && (yy < p.H);
         float* dst = yn + (long long)yy * p.W + x;
-        const uint32_t trow = tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)(as * g.T * g.Npad + t * g.Npad);
+        const uint32_t trow = tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)(as * g.T * g.Ncol + t * g.Ncol);
         for (int c0 = 0; c0 < c_cnt; c0 += 8) {
           float v[8];
-          tc_ld8(trow + c0, v);
+          if (g.hls) {                 // hi*hi + lo*hi in columns [0, Npad), hi*lo in [Npad, 2 Npad): same pixel, same thread
+            float v2[8];
+            tc_ld8x2(trow + c0, trow + g.Npad + c0, v, v2);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) v[j] += v2[j];
+          } else {
+            tc_ld8(trow + c0, v);
+          }
           if (valid) {
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
@@ -595,7 +660,7 @@ __global__ void __launch_bounds__(256) unstage_act_kernel(const __nv_bfloat16* _
 // dgrad = 1: the transposed, spatially flipped filter (data gradient = the same conv run on dY):
 // "output" channel = original ci, "input" channel = original co.
 __global__ void stage_weights_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ ws, int Cout, int Cin,
-                                     int KK, int dgrad, int nsplit, int KS, int Npad, int fmt, int dxn_np) {
+                                     int KK, int dgrad, int nsplit, int KS, int Npad, int fmt, int dxn_np, int hls) {
   const int Co_k = dgrad ? Cin : Cout;   // kernel-view output channels
   const int Ci_k = dgrad ? Cout : Cin;   // kernel-view input channels
   if (dxn_np) {
@@ -629,9 +694,16 @@ __global__ void stage_weights_kernel(const float* __restrict__ w, __nv_bfloat16*
        i += (long long)gridDim.x * blockDim.x) {
     long long t = i;
     const int j = (int)(t % 8); t /= 8;
-    const int nn = (int)(t % Npad); t /= Npad;
-    const int kk = (int)(t % 2); t /= 2;
-    const int hl = (int)(t % 2); t /= 2;
+    int nn, kk, hl;
+    if (hls) {        // [tap][kk][hl * Npad + nn][8]: W_hi and W_lo stacked along the MMA N dimension
+      nn = (int)(t % Npad); t /= Npad;
+      hl = (int)(t % 2); t /= 2;
+      kk = (int)(t % 2); t /= 2;
+    } else {          // [tap][hl][kk][nn][8]
+      nn = (int)(t % Npad); t /= Npad;
+      kk = (int)(t % 2); t /= 2;
+      hl = (int)(t % 2); t /= 2;
+    }
     const int tap = (int)(t % KK); t /= KK;
     const int ks = (int)(t % KS);
     const int ns = (int)(t / KS);
@@ -679,12 +751,13 @@ int san_tc_describe(int H, int W, int Cin, int Cout, int K, int* out) {
   return SAN_OK;
 }
 
-// Host-only: which formulation the kernel uses.  out[0..3] = dxn (1: horizontal taps in the MMA N dimension), Np (Cout padded
-// to 8 in that form), wtaps (weight blocks per K-step: 9, 3 or 1), xchg_bytes (epilogue exchange area).
+// Host-only: which formulation the kernel uses.  out[0..5] = dxn (1: horizontal taps in the MMA N dimension), Np (Cout padded
+// to 8 in that form), wtaps (weight blocks per K-step: 9, 3 or 1), xchg_bytes (epilogue exchange area), hls (1: W_hi / W_lo
+// stacked along N), Ncol (TMEM columns per 128-pixel tile).
 int san_tc_describe_form(int H, int W, int Cin, int Cout, int K, int* out) {
   TcGeom g;
   if (!out || !tc_geometry(H, W, Cin, Cout, K, &g)) return SAN_ERR_UNSUPPORTED;
-  out[0] = g.dxn; out[1] = g.Np; out[2] = g.wtaps; out[3] = g.xchg_bytes;
+  out[0] = g.dxn; out[1] = g.Np; out[2] = g.wtaps; out[3] = g.xchg_bytes; out[4] = g.hls; out[5] = g.Ncol;
   return SAN_OK;
 }
 
@@ -768,7 +841,7 @@ int san_tc_stage_weights(const float* w, void* ws, int H, int W, int Cout, int C
   SAN_CHECK_ARG(tc_geometry(H, W, Ci_k, Co_k, K, &g), "san_tc_stage_weights: unsupported shape");
   const long long total = (long long)g.nsplit * g.KS * g.wtaps * 4 * g.Npad * 8;
   stage_weights_kernel<<<ew_blocks(total), 256, 0, (cudaStream_t)stream>>>(w, (__nv_bfloat16*)ws, Cout, Cin, K * K, dgrad,
-                                                                           g.nsplit, g.KS, g.Npad, fmt, g.dxn ? g.Np : 0);
+                                                                           g.nsplit, g.KS, g.Npad, fmt, g.dxn ? g.Np : 0, g.hls);
   SAN_LAUNCH_CHECK();
   return SAN_OK;
 }

@@ -81,6 +81,21 @@ __device__ __forceinline__ void tc_ld8(uint32_t taddr, float* v) {
   v[4] = __uint_as_float(r4); v[5] = __uint_as_float(r5); v[6] = __uint_as_float(r6); v[7] = __uint_as_float(r7);
 }
 
+// two 8-column loads in flight before ONE wait (the two column blocks of the HLS accumulator)
+__device__ __forceinline__ void tc_ld8x2(uint32_t t0, uint32_t t1, float* a, float* b) {
+  uint32_t r[16];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%16];\n\t"
+      "tcgen05.ld.sync.aligned.32x32b.x8.b32 {%8, %9, %10, %11, %12, %13, %14, %15}, [%17];\n\t"
+      "tcgen05.wait::ld.sync.aligned;"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(t0), "r"(t1)
+      : "memory");
+#pragma unroll
+  for (int i = 0; i < 8; ++i) { a[i] = __uint_as_float(r[i]); b[i] = __uint_as_float(r[8 + i]); }
+}
+
 // three 8-column loads (the dx blocks of the DXN accumulator) in flight before ONE wait
 __device__ __forceinline__ void tc_ld8x3(uint32_t t0, uint32_t t1, uint32_t t2, float* a, float* b, float* c) {
   uint32_t r[24];

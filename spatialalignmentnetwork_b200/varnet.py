@@ -261,9 +261,11 @@ class SensitivityModel(nn.Module):
 
     def forward(self, masked_kspace: torch.Tensor, num_low_frequencies: int) -> torch.Tensor:
         N, C, H, W = masked_kspace.shape
-        acs = torch.ones(W)
+        # ACS low-pass column mask (reference varnet.py:395-398), built on the device (no host copy: the step stays
+        # capturable into a CUDA graph)
+        acs = torch.ones(W, device=masked_kspace.device)
         acs[num_low_frequencies:] = 0
-        acs = torch.roll(acs, -num_low_frequencies // 2).to(masked_kspace.device)
+        acs = torch.roll(acs, -num_low_frequencies // 2)
         # ifft2(ACS * k) straight into the planar layout; the reference's chunked U-Net
         # (varnet.py:409-414) is a memory workaround with identical per-sample arithmetic
         images = ops.IfftMaskedPlanar.apply(masked_kspace, acs)      # [N*C, 2, H, W]

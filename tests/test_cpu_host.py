@@ -214,9 +214,9 @@ def _describe(L, H, W, Cin, Cout, K):
     assert L.san_tc_describe(H, W, Cin, Cout, K, ctypes.addressof(out)) == 0
     keys = ("Cin_pad KG KS nsplit Npad Wp Hp R T S_alloc strips stages acc_stages a_bytes b_bytes smem_bytes").split()
     g = dict(zip(keys, list(out)))
-    form = (ctypes.c_int * 4)()
+    form = (ctypes.c_int * 6)()
     assert L.san_tc_describe_form(H, W, Cin, Cout, K, ctypes.addressof(form)) == 0
-    g.update(dict(zip("dxn Np wtaps xchg_bytes".split(), list(form))))
+    g.update(dict(zip("dxn Np wtaps xchg_bytes hls Ncol".split(), list(form))))
     return g
 
 
@@ -238,7 +238,10 @@ def test_tc_flattened_pixel_formulation_on_cpu(built, shape):
     # resource bounds
     assert g["Cin_pad"] % 16 == 0 and g["Cin_pad"] >= Cin and KG * 8 == g["Cin_pad"] and g["KS"] * 16 == g["Cin_pad"]
     assert Npad % 16 == 0 and g["nsplit"] * Npad >= Cout and Npad <= 256
-    assert T * Npad * g["acc_stages"] <= 512                                   # TMEM columns
+    assert T * g["Ncol"] * g["acc_stages"] <= 512                              # TMEM columns
+    hls_on = os.environ.get("SAN_TC_HLS", "1") != "0"
+    assert g["hls"] == (1 if (hls_on and not g["dxn"] and K == 3 and Npad <= 48 and g["nsplit"] == 1) else 0)
+    assert g["Ncol"] == (2 * Npad if g["hls"] else Npad)
     assert g["S_alloc"] >= 128 * T + 2 * Wp + 2 and g["S_alloc"] >= (R + 2) * Wp  # every tap row of every tile is in the tile
     dxn, Np = g["dxn"], g["Np"]
     dxn_on = os.environ.get("SAN_TC_DXN", "0") != "0"
@@ -302,7 +305,14 @@ def test_tc_flattened_pixel_formulation_on_cpu(built, shape):
                     a_lo = tile[1, :, off:off + 128 * T].permute(1, 0, 2).reshape(128 * T, -1).double()
                     b_hi = whi[ns * Npad:(ns + 1) * Npad, :, tap].double()
                     b_lo = wlo[ns * Npad:(ns + 1) * Npad, :, tap].double()
-                    acc += a_hi @ b_hi.T + a_lo @ b_hi.T + a_hi @ b_lo.T
+                    if g["hls"]:     # B = [W_hi | W_lo] stacked along N: A_hi x B (2 Npad columns) + A_lo x W_hi (first Npad columns)
+                        acc2 = acc2 if tap else torch.zeros(128 * T, 2 * Npad, dtype=torch.float64)
+                        acc2 += a_hi @ torch.cat([b_hi, b_lo], 0).T
+                        acc2[:, :Npad] += a_lo @ b_hi.T
+                        if tap == ntaps - 1:
+                            acc = acc2[:, :Npad] + acc2[:, Npad:]          # epilogue: the two column blocks of a pixel
+                    else:
+                        acc += a_hi @ b_hi.T + a_lo @ b_hi.T + a_hi @ b_lo.T
                 for q in range(R * Wp):
                     r, xx = divmod(q, Wp)
                     if xx < W and y0 + r < H:
@@ -558,8 +568,8 @@ def test_conv_cycle_model_runs(built):
         if shape == (18, 2, 320, 1):       # 1x1 head: the model charges halo rows the 1x1 kernel finds in L2
             continue
         g, m = conv_model.model(L, 64, *shape)
-        if g["dxn"] != conv_model.MEASURED_FORM.get(shape, 0):
-            continue                       # measured with the other formulation
+        if (g["dxn"], g["hls"]) != conv_model.MEASURED_FORM.get(shape, (0, 0)):
+            continue                       # measured with another formulation
         assert 0.95 < meas / m["bound"] < 2.2, (shape, meas, m)
 
 

@@ -35,9 +35,9 @@ def describe(L, H, W, Cin, Cout, K):
     assert L.san_tc_describe(H, W, Cin, Cout, K, ctypes.addressof(out)) == 0
     keys = "Cin_pad KG KS nsplit Npad Wp Hp R T S_alloc strips stages acc_stages a_bytes b_bytes smem_bytes".split()
     g = dict(zip(keys, list(out)))
-    form = (ctypes.c_int * 4)()
+    form = (ctypes.c_int * 6)()
     assert L.san_tc_describe_form(H, W, Cin, Cout, K, ctypes.addressof(form)) == 0
-    g.update(dict(zip("dxn Np wtaps xchg_bytes".split(), list(form))))
+    g.update(dict(zip("dxn Np wtaps xchg_bytes hls Ncol".split(), list(form))))
     return g
 
 
@@ -47,6 +47,9 @@ def model(L, N, Cin, Cout, HW, K):
     mma_per_unit = g["T"] * taps * 3 * g["KS"]
     smem_clk = 32 + g["Npad"] / 4.0                 # A 4 KB + B Npad*32 B at 128 B/clk
     tens_clk = g["Npad"] / 2.0
+    if g["hls"]:     # 2 MMAs per tap (N = 2 Npad and N = Npad) instead of 3 of N = Npad: express as 3 MMA-equivalents
+        smem_clk = ((32 + g["Npad"] / 2.0) + (32 + g["Npad"] / 4.0)) / 3.0
+        tens_clk = (g["Npad"] + g["Npad"] / 2.0) / 3.0
     units = N * g["strips"] * g["nsplit"]
     waves = -(-units // SMS)
     mma_ms = waves * mma_per_unit * max(smem_clk, tens_clk) / (CLK_GHZ * 1e6)
@@ -61,6 +64,8 @@ def model(L, N, Cin, Cout, HW, K):
     epi_clk = g["T"] * g["Npad"] / 8.0 * 40.0 / 4.0      # ~40 clk per 8-column tcgen05.ld + stores, 4 warps per quarter
     if g["dxn"]:
         epi_clk = max(epi_clk, g["T"] * g["Npad"] * 8.0)  # TMEM read of the 3 column blocks at 64 B/clk
+    if g["hls"]:
+        epi_clk *= 2.0                                    # two column blocks per pixel
     epi_ms = waves * epi_clk / (CLK_GHZ * 1e6)
     bound = max(mma_ms, hbm_ms) + (0.0 if g["acc_stages"] == 2 else epi_ms)
     return g, dict(mma=mma_ms, tensor=tens_ms, hbm=hbm_ms, epi=epi_ms, bound=bound, waves=waves,
