@@ -112,7 +112,7 @@ int san_tc_supported(int H, int W, int Cin, int Cout, int K);
 int san_tc_describe(int H, int W, int Cin, int Cout, int K, int* out);
 /* host-only: out[6] = dxn (1 = "DXN" form, opt-in SAN_TC_DXN=1: the three horizontal taps sit in the MMA N dimension,
  * B row = dx * Np + co, and the epilogue adds the column blocks across neighbouring pixels), Np (Cout padded to 8),
- * wtaps (weight blocks per K-step: 9, 3 or 1), xchg_bytes, hls (1 = narrow 3x3 layers, <= 48 padded output channels:
+ * wtaps (weight blocks per K-step: 9, 3 or 1), xchg_bytes, hls (1 = narrow 3x3 layers, <= 32 padded output channels:
  * [W_hi | W_lo] stacked along the MMA N dimension, 2 instead of 3 reads of the A tile per tap), Ncol (TMEM columns per
  * 128-pixel tile) (host pointer) */
 int san_tc_describe_form(int H, int W, int Cin, int Cout, int K, int* out);

@@ -74,14 +74,14 @@ int tc_dxn_force_r() { static const int v = tc_env_int("SAN_TC_DXN_R", 0); retur
 int tc_hls_enabled() { static const int v = tc_env_int("SAN_TC_HLS", 1); return v; }
 int tc_hls_force_r() { static const int v = tc_env_int("SAN_TC_HLS_R", 0); return v; }
 
-// HLS geometry for narrow 3x3 layers (<= 48 padded output channels): B = [W_hi | W_lo] stacked along N, so that
+// HLS geometry for narrow 3x3 layers (<= 32 padded output channels): B = [W_hi | W_lo] stacked along N, so that
 // A_hi is read from shared memory ONCE for the two products hi*hi and hi*lo (N = 2*Npad), plus one MMA A_lo x W_hi
 // (N = Npad): 2 reads of the 4 KB A tile per tap instead of 3 (the operand read, not the tensor pipe, bounds these
 // layers); the epilogue adds the two column blocks of a pixel.  Costs 2x the TMEM columns, so strips are one image
 // row at W = 320 to keep the accumulators double-buffered; chosen by the same cycle estimate as above.
 bool tc_geometry_hls(int H, int W, int Cin, int Cout, TcGeom* g) {
   const int Npad = pad16(Cout);
-  if (Npad > 48) return false;
+  if (Npad > 32) return false;       // measured: Npad = 48 (N = 96) loses (18->36 @160: 0.156 -> 0.19-0.22 ms), 16 / 32 win
   const int Ncol = 2 * Npad, Wp = W + 2, KS = pad16(Cin) / 16;
   const int b_bytes = 9 * 4 * Npad * 16;
   const int force = tc_hls_force_r();

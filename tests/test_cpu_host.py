@@ -240,7 +240,7 @@ def test_tc_flattened_pixel_formulation_on_cpu(built, shape):
     assert Npad % 16 == 0 and g["nsplit"] * Npad >= Cout and Npad <= 256
     assert T * g["Ncol"] * g["acc_stages"] <= 512                              # TMEM columns
     hls_on = os.environ.get("SAN_TC_HLS", "1") != "0"
-    assert g["hls"] == (1 if (hls_on and not g["dxn"] and K == 3 and Npad <= 48 and g["nsplit"] == 1) else 0)
+    assert g["hls"] == (1 if (hls_on and not g["dxn"] and K == 3 and Npad <= 32 and g["nsplit"] == 1) else 0)
     assert g["Ncol"] == (2 * Npad if g["hls"] else Npad)
     assert g["S_alloc"] >= 128 * T + 2 * Wp + 2 and g["S_alloc"] >= (R + 2) * Wp  # every tap row of every tile is in the tile
     dxn, Np = g["dxn"], g["Np"]

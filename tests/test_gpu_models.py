@@ -341,5 +341,13 @@ def test_graphed_update_matches_eager():
     l3 = gs(*batches[2]).item()
     assert abs(l2 - losses[1]) < 1e-4 * abs(losses[1]) and abs(l3 - losses[2]) < 1e-4 * abs(losses[2]), (l2, l3, losses)
     got = dict(list(net2.net_T.state_dict().items()) + list(net2.net_R.state_dict().items()))
-    worst = max(rel_l2(got[k], v) for k, v in eager.items() if v.is_floating_point() and v.numel() > 1)
-    assert worst < 1e-3, worst
+    # Adam's first steps move every weight by ~lr * sign(g): a parameter whose gradient is at noise level (atomic
+    # summation order) may step the other way, so single tensors (zero-initialised biases) can differ by 2 * lr per
+    # step; the weights as a whole must agree and no element may differ by more than that bound
+    keys = [k for k, v in eager.items() if v.is_floating_point() and "running" not in k]
+    cat = lambda d: torch.cat([d[k].flatten().double() for k in keys])
+    assert rel_l2(cat(got), cat(eager)) < 1e-3
+    assert max((got[k] - eager[k]).abs().max().item() for k in keys) <= 2 * 3 * 1e-4 + 1e-6
+    for k, v in eager.items():          # BatchNorm running statistics took the same three updates
+        if "running" in k:
+            assert rel_l2(got[k], v) < 1e-3, k
