@@ -110,11 +110,12 @@ int san_tc_supported(int H, int W, int Cin, int Cout, int K);
 /* host-only: strip geometry of san_tc_conv for this shape; out[16] = Cin_pad, KG, KS, nsplit, Npad, Wp, Hp, R, T,
  * S_alloc, strips, stages, acc_stages, a_bytes, b_bytes, smem_bytes (host pointer) */
 int san_tc_describe(int H, int W, int Cin, int Cout, int K, int* out);
-/* host-only: out[6] = dxn (1 = "DXN" form, opt-in SAN_TC_DXN=1: the three horizontal taps sit in the MMA N dimension,
+/* host-only: out[7] = dxn (1 = "DXN" form, opt-in SAN_TC_DXN=1: the three horizontal taps sit in the MMA N dimension,
  * B row = dx * Np + co, and the epilogue adds the column blocks across neighbouring pixels), Np (Cout padded to 8),
  * wtaps (weight blocks per K-step: 9, 3 or 1), xchg_bytes, hls (1 = narrow 3x3 layers, <= 32 padded output channels:
  * [W_hi | W_lo] stacked along the MMA N dimension, 2 instead of 3 reads of the A tile per tap), Ncol (TMEM columns per
- * 128-pixel tile) (host pointer) */
+ * 128-pixel tile), pair (1 = odd number of 8-channel input groups: the half-empty last K = 16 step pairs filter taps, 5
+ * MMA steps instead of 9, and never loads the all-zero group) (host pointer) */
 int san_tc_describe_form(int H, int W, int Cin, int Cout, int K, int* out);
 /* Fused operand producer: up to 3 channel-concatenated sources (varnet.py:116 concat order),
  * each out = leaky_relu(a[plane]*(y - mu[plane]) + b[plane], slope) (a NULL = identity), i.e. the

@@ -58,6 +58,7 @@ struct TcGeom {
   int dxn, Np;             // DXN form: horizontal taps in the MMA N dimension, Np = Cout padded to 8 (Npad = pad16(3*Np))
   int wtaps;               // weight blocks per K-step: 9 (3x3), 3 (DXN: one per filter row) or 1 (1x1)
   int hls, Ncol;           // HLS form: [W_hi | W_lo] stacked along the MMA N dimension; Ncol = TMEM columns per tile
+  int pair;                // the last K-step has ONE real channel group: filter taps are paired inside its K = 16 MMAs
   int xchg_bytes;          // DXN: shared-memory exchange area of the epilogue (quarter-boundary lanes)
 };
 
@@ -73,6 +74,8 @@ int tc_dxn_force_r() { static const int v = tc_env_int("SAN_TC_DXN_R", 0); retur
 // SAN_TC_HLS = 0 disables the hi/lo-stacked form of narrow 3x3 layers (A/B runs); SAN_TC_HLS_R = r forces its strip height
 int tc_hls_enabled() { static const int v = tc_env_int("SAN_TC_HLS", 1); return v; }
 int tc_hls_force_r() { static const int v = tc_env_int("SAN_TC_HLS_R", 0); return v; }
+// SAN_TC_PAIR = 0 disables tap pairing in the half-empty last K-step (A/B runs)
+int tc_pair_enabled() { static const int v = tc_env_int("SAN_TC_PAIR", 1); return v; }
 
 // HLS geometry for narrow 3x3 layers (<= 32 padded output channels): B = [W_hi | W_lo] stacked along N, so that
 // A_hi is read from shared memory ONCE for the two products hi*hi and hi*lo (N = 2*Npad), plus one MMA A_lo x W_hi
@@ -186,6 +189,11 @@ bool tc_geometry(int H, int W, int Cin, int Cout, int K, TcGeom* g) {
     g->T = (g->R * g->Wp + 127) / 128;
   }
   if (!g->hls) g->Ncol = g->Npad;
+  // Tap pairing: with an odd number of 8-channel groups (Cin = 18 -> 3 groups, 3 -> 1, 36 -> 5, 72 -> 9) the last K = 16
+  // step would multiply one real group and one all-zero group for each of the 9 taps.  Instead the zero group's slot
+  // of the MMA is pointed (descriptor leading-byte-offset) at the SAME real group shifted by the next tap's offset:
+  // 5 steps (taps 0+1, 2+3, 4+5, 6+7, 8+none) instead of 9, and the zero group is never loaded.
+  g->pair = (K == 3 && !g->dxn && (((Cin + 7) / 8) & 1) && tc_pair_enabled()) ? 1 : 0;
   g->S_alloc = ((128 * g->T + 2 * g->Wp + 2) + 7) / 8 * 8;
   g->a_bytes = 4 * g->S_alloc * 16;
   g->stage_bytes = g->a_bytes + g->b_bytes;
@@ -214,6 +222,34 @@ struct ConvTcParams {
 };
 
 // ---------------------------------------------------------------------------------- MMA issue
+// One K-step of one unit: NSTEP (A window, B block) descriptor pairs per 128-pixel tile.  a_word[i] = low descriptor word
+// of step i without the stage address: window offset (16 B units) | leading-byte-offset << 16.
+template <int NSTEP, bool HLS>
+__device__ __forceinline__ void issue_kstep(const uint32_t (&a_word)[NSTEP], uint32_t a_s, uint32_t a_hi, uint32_t a_losplit,
+                                            uint32_t b_base, uint32_t b_hi, uint32_t b_losplit, uint32_t b_tapstride,
+                                            uint32_t d0, int T, int Ncol, uint32_t idesc, uint32_t idesc2, uint32_t first) {
+  uint32_t d = d0, a_t = a_s;
+  for (int t = 0; t < T; ++t, d += Ncol, a_t += 128) {
+#pragma unroll
+    for (int i = 0; i < NSTEP; ++i) {
+      const uint32_t al = a_t + a_word[i];
+      const uint32_t bl = b_base + i * b_tapstride;
+      const uint64_t A_hi = ((uint64_t)a_hi << 32) | al, A_lo = ((uint64_t)a_hi << 32) | (al + a_losplit);
+      if (HLS) {
+        // B block = [kk][2*Npad rows: W_hi then W_lo][8]: A_hi x [W_hi | W_lo] (N = 2*Npad) + A_lo x W_hi (N = Npad)
+        const uint64_t B_all = ((uint64_t)b_hi << 32) | bl;
+        tc_mma_bf16(d, A_hi, B_all, idesc2, i == 0 ? first : 1u);   // hi*hi -> columns [0, Npad), hi*lo -> [Npad, 2 Npad)
+        tc_mma_bf16(d, A_lo, B_all, idesc, 1u);                     // lo*hi -> columns [0, Npad)
+      } else {
+        const uint64_t B_hi = ((uint64_t)b_hi << 32) | bl, B_lo = ((uint64_t)b_hi << 32) | (bl + b_losplit);
+        tc_mma_bf16(d, A_hi, B_hi, idesc, i == 0 ? first : 1u);     // hi*hi
+        tc_mma_bf16(d, A_lo, B_hi, idesc, 1u);                      // lo*hi
+        tc_mma_bf16(d, A_hi, B_lo, idesc, 1u);                      // hi*lo
+      }
+    }
+  }
+}
+
 template <int NTAPS>
 __device__ __forceinline__ void mma_issue_loop(const ConvTcParams& p, const TcGeom& g, uint32_t tmem_base,
                                                uint32_t stage0, uint32_t bar_full, uint32_t bar_empty,
@@ -226,10 +262,21 @@ __device__ __forceinline__ void mma_issue_loop(const ConvTcParams& p, const TcGe
   const uint64_t b_tmpl = umma_desc(0, (uint32_t)(hls ? 2 * g.Npad : g.Npad) * 16, 128);   // LBO = one kk plane of B rows
   const uint32_t a_hi = (uint32_t)(a_tmpl >> 32), b_hi = (uint32_t)(b_tmpl >> 32);
   const uint32_t a_lo0 = (uint32_t)a_tmpl, b_lo0 = (uint32_t)b_tmpl;
-  uint32_t tap_off[NTAPS];
+  uint32_t tap_off[NTAPS], a_word[NTAPS];
 #pragma unroll
-  for (int tap = 0; tap < NTAPS; ++tap)     // 9: (dy, dx) windows; 3: DXN form, one window per filter row; 1: 1x1 centre
+  for (int tap = 0; tap < NTAPS; ++tap) {   // 9: (dy, dx) windows; 3: DXN form, one window per filter row; 1: 1x1 centre
     tap_off[tap] = (NTAPS == 9) ? (uint32_t)((tap / 3) * g.Wp + (tap % 3)) : (NTAPS == 3) ? (uint32_t)(tap * g.Wp) : (uint32_t)(g.Wp + 1);
+    a_word[tap] = a_lo0 + tap_off[tap];     // K group 1 = the next channel-group plane (LBO = S_alloc slots)
+  }
+  // paired last K-step (g.pair): K group 0 = the real channel group at tap 2i, K group 1 = the SAME plane at tap 2i+1
+  // (LBO = the two taps' window distance); the 9th tap pairs with itself (LBO 0) against zero weights
+  uint32_t p_word[5];
+#pragma unroll
+  for (int i = 0; i < 5; ++i) {
+    const uint32_t o0 = (NTAPS == 9) ? tap_off[(2 * i) % NTAPS] : 0u;
+    const uint32_t o1 = (NTAPS == 9 && i < 4) ? tap_off[(2 * i + 1) % NTAPS] : o0;
+    p_word[i] = ((o1 - o0) << 16) + o0;
+  }
   const uint32_t a_losplit = 2u * g.S_alloc;     // hi -> lo half of A, 16 B units
   const uint32_t b_losplit = 2u * g.Npad;        // hi -> lo half of B
   const uint32_t b_tapstride = 4u * g.Npad;
@@ -245,34 +292,14 @@ __device__ __forceinline__ void mma_issue_loop(const ConvTcParams& p, const TcGe
       const uint32_t a_s = (stage0 + (uint32_t)s * g.stage_bytes) >> 4;   // 16 B units
       const uint32_t b_s = a_s + ((uint32_t)g.a_bytes >> 4);
       const uint32_t first = (ks != 0);
+      const bool paired = NTAPS == 9 && g.pair && ks == g.KS - 1;
       if (elect_one_sync()) {
-        uint32_t d = acc0, a_t = a_lo0 + a_s;
-        if (hls) {
-          // B block of a tap = [kk][2*Npad rows: W_hi then W_lo][8]: A_hi x [W_hi | W_lo] (N = 2*Npad) + A_lo x W_hi (N = Npad)
-          for (int t = 0; t < g.T; ++t, d += g.Ncol, a_t += 128) {
-#pragma unroll
-            for (int tap = 0; tap < NTAPS; ++tap) {
-              const uint32_t al = a_t + tap_off[tap];
-              const uint32_t bl = b_lo0 + b_s + tap * b_tapstride;
-              const uint64_t A_hi = ((uint64_t)a_hi << 32) | al, A_lo = ((uint64_t)a_hi << 32) | (al + a_losplit);
-              const uint64_t B_all = ((uint64_t)b_hi << 32) | bl;
-              tc_mma_bf16(d, A_hi, B_all, idesc2, tap == 0 ? first : 1u);   // hi*hi -> columns [0, Npad), hi*lo -> [Npad, 2 Npad)
-              tc_mma_bf16(d, A_lo, B_all, idesc, 1u);                       // lo*hi -> columns [0, Npad)
-            }
-          }
+        if (paired) {
+          if (hls) issue_kstep<5, true>(p_word, a_s, a_hi, a_losplit, b_lo0 + b_s, b_hi, b_losplit, b_tapstride, acc0, g.T, g.Ncol, idesc, idesc2, first);
+          else issue_kstep<5, false>(p_word, a_s, a_hi, a_losplit, b_lo0 + b_s, b_hi, b_losplit, b_tapstride, acc0, g.T, g.Ncol, idesc, idesc2, first);
         } else {
-          for (int t = 0; t < g.T; ++t, d += g.Npad, a_t += 128) {
-#pragma unroll
-            for (int tap = 0; tap < NTAPS; ++tap) {
-              const uint32_t al = a_t + tap_off[tap];
-              const uint32_t bl = b_lo0 + b_s + tap * b_tapstride;
-              const uint64_t A_hi = ((uint64_t)a_hi << 32) | al, A_lo = ((uint64_t)a_hi << 32) | (al + a_losplit);
-              const uint64_t B_hi = ((uint64_t)b_hi << 32) | bl, B_lo = ((uint64_t)b_hi << 32) | (bl + b_losplit);
-              tc_mma_bf16(d, A_hi, B_hi, idesc, tap == 0 ? first : 1u);   // hi*hi
-              tc_mma_bf16(d, A_lo, B_hi, idesc, 1u);                      // lo*hi
-              tc_mma_bf16(d, A_hi, B_lo, idesc, 1u);                      // hi*lo
-            }
-          }
+          if (hls) issue_kstep<NTAPS, true>(a_word, a_s, a_hi, a_losplit, b_lo0 + b_s, b_hi, b_losplit, b_tapstride, acc0, g.T, g.Ncol, idesc, idesc2, first);
+          else issue_kstep<NTAPS, false>(a_word, a_s, a_hi, a_losplit, b_lo0 + b_s, b_hi, b_losplit, b_tapstride, acc0, g.T, g.Ncol, idesc, idesc2, first);
         }
         tc_commit(bar_empty + 8 * s);  // frees the smem stage when these MMAs retire
         if (ks == g.KS - 1) tc_commit(bar_accf + 8 * as);   // accumulators of this unit complete
@@ -329,11 +356,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const ConvTcPara
         for (int ks = 0; ks < g.KS; ++ks) {
           mbar_wait(bar_empty + 8 * s, ph ^ 1);
           const uint32_t sbase = stage0 + (uint32_t)s * g.stage_bytes;
-          mbar_expect_tx(bar_full + 8 * s, 4 * bytesA + (uint32_t)g.b_bytes);
+          const int nkk = (g.pair && ks == g.KS - 1) ? 1 : 2;     // paired last K-step: the all-zero group is never read
+          mbar_expect_tx(bar_full + 8 * s, 2 * nkk * bytesA + (uint32_t)g.b_bytes);
 #pragma unroll
           for (int hl = 0; hl < 2; ++hl)
-#pragma unroll
-            for (int kk = 0; kk < 2; ++kk) {
+            for (int kk = 0; kk < nkk; ++kk) {
               const __nv_bfloat16* src =
                   p.xs + ((long long)(n * 2 + hl) * g.KG + 2 * ks + kk) * plane_elems + (long long)y0 * g.Wp * 8;
               bulk_g2s(sbase + (uint32_t)(hl * 2 + kk) * g.S_alloc * 16, src, bytesA, bar_full + 8 * s);
@@ -660,7 +687,7 @@ __global__ void __launch_bounds__(256) unstage_act_kernel(const __nv_bfloat16* _
 // dgrad = 1: the transposed, spatially flipped filter (data gradient = the same conv run on dY):
 // "output" channel = original ci, "input" channel = original co.
 __global__ void stage_weights_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ ws, int Cout, int Cin,
-                                     int KK, int dgrad, int nsplit, int KS, int Npad, int fmt, int dxn_np, int hls) {
+                                     int KK, int dgrad, int nsplit, int KS, int Npad, int fmt, int dxn_np, int hls, int pair) {
   const int Co_k = dgrad ? Cin : Cout;   // kernel-view output channels
   const int Ci_k = dgrad ? Cout : Cin;   // kernel-view input channels
   if (dxn_np) {
@@ -704,13 +731,19 @@ __global__ void stage_weights_kernel(const float* __restrict__ w, __nv_bfloat16*
       kk = (int)(t % 2); t /= 2;
       hl = (int)(t % 2); t /= 2;
     }
-    const int tap = (int)(t % KK); t /= KK;
+    int tap = (int)(t % KK); t /= KK;
     const int ks = (int)(t % KS);
     const int ns = (int)(t / KS);
     const int co = ns * Npad + nn;
-    const int ci = ks * 16 + kk * 8 + j;
+    int ci = ks * 16 + kk * 8 + j;
+    bool live = true;
+    if (pair && ks == KS - 1) {       // block i < 5 holds taps 2i (K group 0) and 2i+1 (K group 1) of the ONE real channel group
+      ci = ks * 16 + j;
+      live = tap < 5 && 2 * tap + kk < KK;
+      tap = 2 * tap + kk;
+    }
     float v = 0.f;
-    if (co < Co_k && nn < Npad && ci < Ci_k) {
+    if (live && co < Co_k && nn < Npad && ci < Ci_k) {
       if (!dgrad) v = w[((long long)co * Cin + ci) * KK + tap];
       else v = w[((long long)ci * Cin + co) * KK + (KK - 1 - tap)];
     }
@@ -751,13 +784,13 @@ int san_tc_describe(int H, int W, int Cin, int Cout, int K, int* out) {
   return SAN_OK;
 }
 
-// Host-only: which formulation the kernel uses.  out[0..5] = dxn (1: horizontal taps in the MMA N dimension), Np (Cout padded
+// Host-only: which formulation the kernel uses.  out[0..6] = dxn (1: horizontal taps in the MMA N dimension), Np (Cout padded
 // to 8 in that form), wtaps (weight blocks per K-step: 9, 3 or 1), xchg_bytes (epilogue exchange area), hls (1: W_hi / W_lo
-// stacked along N), Ncol (TMEM columns per 128-pixel tile).
+// stacked along N), Ncol (TMEM columns per 128-pixel tile), pair (1: taps paired in the half-empty last K-step).
 int san_tc_describe_form(int H, int W, int Cin, int Cout, int K, int* out) {
   TcGeom g;
   if (!out || !tc_geometry(H, W, Cin, Cout, K, &g)) return SAN_ERR_UNSUPPORTED;
-  out[0] = g.dxn; out[1] = g.Np; out[2] = g.wtaps; out[3] = g.xchg_bytes; out[4] = g.hls; out[5] = g.Ncol;
+  out[0] = g.dxn; out[1] = g.Np; out[2] = g.wtaps; out[3] = g.xchg_bytes; out[4] = g.hls; out[5] = g.Ncol; out[6] = g.pair;
   return SAN_OK;
 }
 
@@ -841,7 +874,7 @@ int san_tc_stage_weights(const float* w, void* ws, int H, int W, int Cout, int C
   SAN_CHECK_ARG(tc_geometry(H, W, Ci_k, Co_k, K, &g), "san_tc_stage_weights: unsupported shape");
   const long long total = (long long)g.nsplit * g.KS * g.wtaps * 4 * g.Npad * 8;
   stage_weights_kernel<<<ew_blocks(total), 256, 0, (cudaStream_t)stream>>>(w, (__nv_bfloat16*)ws, Cout, Cin, K * K, dgrad,
-                                                                           g.nsplit, g.KS, g.Npad, fmt, g.dxn ? g.Np : 0, g.hls);
+                                                                           g.nsplit, g.KS, g.Npad, fmt, g.dxn ? g.Np : 0, g.hls, g.pair);
   SAN_LAUNCH_CHECK();
   return SAN_OK;
 }
