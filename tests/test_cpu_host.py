@@ -214,14 +214,15 @@ def _describe(L, H, W, Cin, Cout, K):
     assert L.san_tc_describe(H, W, Cin, Cout, K, ctypes.addressof(out)) == 0
     keys = ("Cin_pad KG KS nsplit Npad Wp Hp R T S_alloc strips stages acc_stages a_bytes b_bytes smem_bytes").split()
     g = dict(zip(keys, list(out)))
-    form = (ctypes.c_int * 6)()
+    form = (ctypes.c_int * 7)()
     assert L.san_tc_describe_form(H, W, Cin, Cout, K, ctypes.addressof(form)) == 0
-    g.update(dict(zip("dxn Np wtaps xchg_bytes hls Ncol".split(), list(form))))
+    g.update(dict(zip("dxn Np wtaps xchg_bytes hls Ncol pair".split(), list(form))))
     return g
 
 
 @pytest.mark.parametrize("shape", [(1, 3, 12, 20, 5, 3), (2, 18, 16, 24, 18, 3), (1, 20, 9, 33, 40, 1), (1, 7, 10, 18, 170, 3),
-                                   (1, 36, 10, 160, 36, 3), (1, 32, 5, 320, 32, 3), (1, 2, 7, 50, 8, 3)])
+                                   (1, 36, 10, 160, 36, 3), (1, 32, 5, 320, 32, 3), (1, 2, 7, 50, 8, 3), (1, 72, 6, 40, 36, 3),
+                                   (1, 40, 6, 24, 130, 3)])
 def test_tc_flattened_pixel_formulation_on_cpu(built, shape):
     """CPU model of csrc/conv_tc.cu driven by the library's own geometry (san_tc_describe): the staged layout
     Xs[n][hl][kg][slot][8] with a one-pixel zero border, strips of R rows, 128-row M tiles over the flattened padded
@@ -297,22 +298,46 @@ def test_tc_flattened_pixel_formulation_on_cpu(built, shape):
                         assert q + 2 < 128 * T          # the neighbouring lanes exist (next quarter / next tile of the unit)
                         out[n, :, y0 + r, xx] = (acc[q, 0:Cout] + acc[q + 1, Np:Np + Cout]) + acc[q + 2, 2 * Np:2 * Np + Cout]
                 continue
+            pair_on = os.environ.get("SAN_TC_PAIR", "1") != "0"
+            assert g["pair"] == (1 if (pair_on and K == 3 and not dxn and (-(-Cin // 8)) % 2 == 1) else 0)
             for ns in range(g["nsplit"]):
                 acc = torch.zeros(128 * T, Npad, dtype=torch.float64)
-                for tap in range(ntaps):
-                    off = (tap // 3) * Wp + (tap % 3) if ntaps == 9 else Wp + 1
-                    a_hi = tile[0, :, off:off + 128 * T].permute(1, 0, 2).reshape(128 * T, -1).double()   # [rows, Cin_pad]
-                    a_lo = tile[1, :, off:off + 128 * T].permute(1, 0, 2).reshape(128 * T, -1).double()
-                    b_hi = whi[ns * Npad:(ns + 1) * Npad, :, tap].double()
-                    b_lo = wlo[ns * Npad:(ns + 1) * Npad, :, tap].double()
+                acc2 = torch.zeros(128 * T, 2 * Npad, dtype=torch.float64)
+                offs = [(tap // 3) * Wp + (tap % 3) if ntaps == 9 else Wp + 1 for tap in range(ntaps)]
+
+                def mma(a_h, a_l, b_h, b_l):            # one MMA step of K = 16 (operands [rows, 16] / [Npad, 16])
+                    nonlocal acc, acc2
                     if g["hls"]:     # B = [W_hi | W_lo] stacked along N: A_hi x B (2 Npad columns) + A_lo x W_hi (first Npad columns)
-                        acc2 = acc2 if tap else torch.zeros(128 * T, 2 * Npad, dtype=torch.float64)
-                        acc2 += a_hi @ torch.cat([b_hi, b_lo], 0).T
-                        acc2[:, :Npad] += a_lo @ b_hi.T
-                        if tap == ntaps - 1:
-                            acc = acc2[:, :Npad] + acc2[:, Npad:]          # epilogue: the two column blocks of a pixel
+                        acc2 += a_h @ torch.cat([b_h, b_l], 0).T
+                        acc2[:, :Npad] += a_l @ b_h.T
                     else:
-                        acc += a_hi @ b_hi.T + a_lo @ b_hi.T + a_hi @ b_lo.T
+                        acc += a_h @ b_h.T + a_l @ b_h.T + a_h @ b_l.T
+
+                def window(hl, kg, off):                 # [128 T, 8]: what the descriptor reads for one K group
+                    assert off + 128 * T <= g["S_alloc"]
+                    return tile[hl, kg, off:off + 128 * T].double()
+
+                for ks in range(g["KS"]):
+                    wsl = lambda t_, lo: (wlo if lo else whi)[ns * Npad:(ns + 1) * Npad, ks * 16:ks * 16 + 16, t_].double()
+                    if g["pair"] and ks == g["KS"] - 1:
+                        # one real channel group (2 ks): K group 0 = its window at tap 2i, K group 1 = the SAME plane at
+                        # tap 2i + 1 (descriptor LBO = window distance); tap 8 pairs with itself against zero weights.
+                        # The all-zero group 2 ks + 1 is never read.
+                        for i in range(5):
+                            t0, t1 = 2 * i, min(2 * i + 1, 8)
+                            lbo = offs[t1] - offs[t0] if i < 4 else 0
+                            assert 0 <= lbo < 16384
+                            a = [torch.cat([window(hl, 2 * ks, offs[t0]), window(hl, 2 * ks, offs[t0] + lbo)], 1) for hl in (0, 1)]
+                            z = torch.zeros(Npad, 8, dtype=torch.float64)
+                            b = [torch.cat([wsl(t0, lo)[:, :8], wsl(t1, lo)[:, :8] if i < 4 else z], 1) for lo in (0, 1)]
+                            assert float(wsl(t0, 0)[:, 8:].abs().max()) == 0      # the skipped group really is all zero
+                            mma(a[0], a[1], b[0], b[1])
+                    else:
+                        for tap in range(ntaps):
+                            a = [torch.cat([window(hl, 2 * ks, offs[tap]), window(hl, 2 * ks + 1, offs[tap])], 1) for hl in (0, 1)]
+                            mma(a[0], a[1], wsl(tap, 0), wsl(tap, 1))
+                if g["hls"]:
+                    acc = acc2[:, :Npad] + acc2[:, Npad:]          # epilogue: the two column blocks of a pixel
                 for q in range(R * Wp):
                     r, xx = divmod(q, Wp)
                     if xx < W and y0 + r < H:
