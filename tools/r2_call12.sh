@@ -13,3 +13,6 @@ for pr in 1 0; do
   SAN_TC_PAIR=$pr timeout 400 python bench.py --steps 8 --warmup 3 --no-parity --no-cpu-baseline --breakdown gpurun_out/r2l_breakdown_pair$pr.json > gpurun_out/r2l_bench_pair$pr.json 2> gpurun_out/r2l_bench_pair$pr.err
   echo "bench PAIR=$pr rc=$?"; python -c "import json; d=json.load(open('gpurun_out/r2l_bench_pair$pr.json')); print(d['value'], d['e2e']['value'], d['roofline']['frac'], d['roofline']['avg_launch_ms'], d['kernel_time_shares'])" || tail -3 gpurun_out/r2l_bench_pair$pr.err
 done
+SAN_STAGE_SIMPLE=0 timeout 400 python bench.py --steps 8 --warmup 3 --no-parity --no-cpu-baseline --breakdown gpurun_out/r2l_breakdown_stage_general.json > gpurun_out/r2l_bench_stage_general.json 2> gpurun_out/r2l_bench_stage_general.err
+echo "bench SAN_STAGE_SIMPLE=0 rc=$?"; python -c "import json; d=json.load(open('gpurun_out/r2l_bench_stage_general.json')); print(d['value'], d['kernel_time_shares'])"
+SAN_STAGE_SIMPLE=0 timeout 100 python tools/bench_tc.py 64 "18,18,320,3;36,36,160,3" 2>&1 | cut -c1-40
