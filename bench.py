@@ -208,12 +208,13 @@ def algorithmic(name, a):
 # out) and the staged operand read back by the GEMM, so both kernels are counted.
 NCU_TRAFFIC = {
     "tc_conv": {"launch": "3x3 18->18 @320x320 bs64 (stage_act_kernel + conv_tc_kernel)",
-                "dram_bytes": (472.1e6 + 794.1e6) + (849.5e6 + 436.5e6),
+                "dram_bytes": (471.9e6 + 794.3e6) + (850.8e6 + 441.6e6),
                 "algorithmic_bytes": 4.0 * 64 * 320 * 320 * (18 + 18),
-                "source": "profiles/r1d_tc_ncu_summary.txt"},
+                "source": "profiles/r2i_ncu_summary_stage_wgrad_norm.txt + profiles/r2j_conv_hls_ncu_summary.txt"},
     "tc_wgrad": {"launch": "3x3 18->18 @320x320 bs64 (wgrad_tc_kernel on the two staged operands)",
-                 "dram_bytes": 1693.6e6 + 4.1e6,
-                 "algorithmic_bytes": 4.0 * 64 * 320 * 320 * (18 + 18), "source": "profiles/r1d_tc_ncu_summary.txt"},
+                 "dram_bytes": 1693.6e6 + 6.6e6,
+                 "algorithmic_bytes": 4.0 * 64 * 320 * 320 * (18 + 18),
+                 "source": "profiles/r2i_ncu_summary_stage_wgrad_norm.txt"},
     # fft_rows_v2_kernel + fft_cols_v2_kernel of one fft_expand_dc call, bs 64, 320x320, 1 coil: (32C+8)*P algorithmic
     "fft_expand_dc": {"launch": "fft_expand_dc bs64 320x320 C=1 (fft_rows_v2_kernel + fft_cols_v2_kernel)",
                       "dram_bytes": (104.9e6 + 21.4e6) + (157.3e6 + 34.6e6), "algorithmic_bytes": 40.0 * 64 * 320 * 320,
@@ -256,8 +257,8 @@ def summarise_profile(records, step_ms, peaks):
                           for k, v in sorted(per.items(), key=lambda kv: -kv[1]["ms"])})
     # dominant kernel = the U-Net convolution kernel with the largest share of the step
     roof = None
-    labels = {"tc_conv": "conv_tc_kernel (tcgen05 BF16x3 implicit-GEMM conv, fwd + dgrad)",
-              "tc_wgrad": "wgrad_tc_kernel (tcgen05 BF16x3 weight gradient)",
+    labels = {"tc_conv": "conv_tc_kernel (tcgen05 implicit-GEMM conv on fp16-pair operands, 3 MMAs per product; fwd + dgrad)",
+              "tc_wgrad": "wgrad_tc_kernel (tcgen05 weight gradient on fp16-pair operands)",
               "conv2d_fwd": "conv_fwd_kernel (fp32 CUDA-core conv, fwd + dgrad)",
               "conv2d_wgrad": "conv_wgrad_kernel (fp32 CUDA-core weight gradient)"}
     cands = [(per[k]["ms"], k) for k in labels if k in per and per[k]["ms"] > 0]

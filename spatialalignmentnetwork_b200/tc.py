@@ -4,7 +4,7 @@ The unit of the U-Nets is not "conv, then norm, then LeakyReLU" but
 ``conv(concat_k sum_j act(norm(raw_kj)))``: the normalisation + activation (+ 2x2 average pooling, pixel
 shuffle of the transposed conv, nearest up-sampling, channel concat of the skip connection, residual
 add; reference varnet.py:98,116,139-146,176-181, unet.py:6-24,119-140) of the *producing* layers is
-applied while the operand of the *consuming* convolution is staged as BF16 hi/lo tiles, so normalised /
+applied while the operand of the *consuming* convolution is staged as 16-bit (hi, lo) pair tiles, so normalised /
 activated / concatenated / pooled / summed tensors are never written to HBM.  What crosses an autograd
 edge is always a raw fp32 conv output; its per-plane statistics ride along in a ``Raw`` handle and their
 gradient is folded in analytically (the InstanceNorm / BatchNorm backward is linear in the incoming
@@ -243,7 +243,7 @@ class _FusedConv(Function):
             terms.append(dict(y=y, gamma=gamma, norm=norm, slope=slope, d2s=d2s, mode=mode, acc=acc, st=st, C=C, c0=c0,
                               ti=ti, bn_training=bn_training))
             ti += 3 if norm == "bn" else 1
-        # dY staged once as BF16 hi/lo: the operand of both the data- and the weight-gradient GEMMs
+        # dY staged once as a (hi, lo) pair: the operand of both the data- and the weight-gradient GEMMs
         gys = _staged_act(N, H, W, Cout, dev)
         amax = None
         if _FMT_BWD == FMT_F16:          # dynamic power-of-two scale of the gradient operand
