@@ -102,7 +102,7 @@ int san_space_to_depth2(const float* y, float* x, int N, int Co, int H, int W, v
  * For san_tc_conv / san_tc_wgrad `fmt` is 0 (both operands bf16 pairs) or 3 (both fp16 pairs): the two operands of
  * one tcgen05 kind::f16 MMA must share the format on the B200 (a mixed f16 x bf16 MMA faults).
  * Activations are staged as Xs[n][hl][kg][(H+2)*(W+2)][8] 16-bit (hl = hi/lo halves of the fp32 value,
- * kg = groups of 8 channels, Cin padded to 16, one-pixel zero border); weights as
+ * kg = ceil(C/8) groups of 8 channels - `Cpad` of the staging calls is C padded to 8 -, one-pixel zero border); weights as
  * Ws[nsplit][KS][taps][hl][2][Npad][8].  Element counts of the caller-allocated buffers: */
 long long san_tc_staged_act_elems(int N, int H, int W, int C);
 long long san_tc_staged_weight_elems(int H, int W, int Cout, int Cin, int K);   /* Cout/Cin of the LAUNCH */

@@ -10,7 +10,8 @@
 //
 // Formulation ("flattened padded pixels"): activations are STAGED by san_tc_stage_act as
 //     Xs[n][hl][kg][slot][8]  bf16,   slot = (h+1)*Wp + (w+1),  Wp = W+2, Hp = H+2, zero border,
-//     hl = 0 (hi) / 1 (lo), kg = channel group of 8 (Cin padded to a multiple of 16 with zeros).
+//     hl = 0 (hi) / 1 (lo), kg = channel group of 8, ceil(Cin / 8) groups (the last one zero-padded; there is NO all-zero
+//     group: with an odd group count the last K = 16 step has one real group, see tap pairing below).
 // For one (hl, kg) a span of image rows is ONE contiguous byte range, so the producer warp moves it
 // with a single TMA bulk copy (cp.async.bulk, UBLKCP), and in shared memory it is exactly the
 // canonical no-swizzle K-major UMMA operand: 8 channels = 16 B per pixel row, uniform 16 B row
@@ -49,7 +50,7 @@ constexpr int TC_SMEM_MAX = 225 * 1024;
 constexpr int TC_NMAX = 160;          // largest UMMA N used per unit
 
 struct TcGeom {
-  int Cin_pad, KG, KS;     // input channels padded to 16; groups of 8; K-steps of 16
+  int Cin_pad, KG, KS;     // input channels padded to 16; REAL groups of 8 = staged planes per (image, half); K-steps of 16
   int nsplit, Npad;        // output channels split into nsplit units of Npad (multiple of 16)
   int Wp, Hp, PS;          // padded width/height, pixel slots per image
   int R, T, S_alloc;       // rows per strip, 128-pixel M-tiles per strip, smem slots per (hl, kk)
@@ -169,7 +170,7 @@ static int tc_pick_rows(int H, int W, int K, int Npad, int b_bytes) {
 
 bool tc_geometry(int H, int W, int Cin, int Cout, int K, TcGeom* g) {
   if (K != 1 && K != 3) return false;
-  g->Cin_pad = pad16(Cin); g->KG = g->Cin_pad / 8; g->KS = g->Cin_pad / 16;
+  g->Cin_pad = pad16(Cin); g->KG = (Cin + 7) / 8; g->KS = g->Cin_pad / 16;
   g->Wp = W + 2; g->Hp = H + 2; g->PS = g->Hp * g->Wp;
   const int ntaps = K * K;
   g->dxn = 0; g->Np = 0; g->wtaps = ntaps; g->xchg_bytes = 0; g->hls = 0;
@@ -333,6 +334,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const ConvTcPara
                  : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
+  if ((g.KG & 1) && !g.pair) {
+    // A planes that no bulk copy ever fills (see the producer) must hold finite values: zero the stage area once
+    uint4* z = (uint4*)(smem + TC_SMEM_HEADER + g.xchg_bytes);
+    const int n16 = g.stages * g.stage_bytes / 16;
+    for (int i = threadIdx.x; i < n16; i += blockDim.x) z[i] = make_uint4(0, 0, 0, 0);
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // generic-proxy stores before async-proxy (TMA / UMMA) accesses
+  }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -356,7 +364,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const ConvTcPara
         for (int ks = 0; ks < g.KS; ++ks) {
           mbar_wait(bar_empty + 8 * s, ph ^ 1);
           const uint32_t sbase = stage0 + (uint32_t)s * g.stage_bytes;
-          const int nkk = (g.pair && ks == g.KS - 1) ? 1 : 2;     // paired last K-step: the all-zero group is never read
+          // an odd number of 8-channel groups: the staged tensor has no plane for the padding group of the last
+          // K-step.  With tap pairing it is never read; otherwise the MMA reads that (zero-initialised, later stale
+          // but finite) shared-memory plane against all-zero weight rows.
+          const int nkk = (2 * ks + 1 < g.KG) ? 2 : 1;
           mbar_expect_tx(bar_full + 8 * s, 2 * nkk * bytesA + (uint32_t)g.b_bytes);
 #pragma unroll
           for (int hl = 0; hl < 2; ++hl)
@@ -827,7 +838,7 @@ inline int ew_blocks(long long total) {
 extern "C" {
 
 long long san_tc_staged_act_elems(int N, int H, int W, int C) {
-  return (long long)N * 2 * (pad16(C) / 8) * (long long)(H + 2) * (W + 2) * 8 + TC_LEAD + TC_TRAIL;
+  return (long long)N * 2 * ((C + 7) / 8) * (long long)(H + 2) * (W + 2) * 8 + TC_LEAD + TC_TRAIL;
 }
 
 long long san_tc_staged_weight_elems(int H, int W, int Cout, int Cin, int K) {
@@ -874,7 +885,8 @@ static int launch_stage(StageArgs& A, void* xs, int N, int H, int W, int Cpad, i
     if (A.s[i].mode >= 2) SAN_CHECK_ARG(H % 2 == 0 && W % 2 == 0, "san_tc_stage: odd size with up-sampling source");
     if (A.s[i].c0 + A.s[i].C > ctot) ctot = A.s[i].c0 + A.s[i].C;
   }
-  SAN_CHECK_ARG(ctot <= Cpad, "san_tc_stage: %d channels exceed Cpad %d", ctot, Cpad);
+  SAN_CHECK_ARG(ctot <= Cpad && Cpad - ctot < 8, "san_tc_stage: Cpad %d must be the %d channels padded to 8 (the staged tensor holds"
+                " ceil(C/8) channel groups, no all-zero groups)", Cpad, ctot);
   A.xs = (__nv_bfloat16*)xs + TC_LEAD;
   A.N = N; A.H = H; A.W = W; A.Wp = W + 2; A.PS = (H + 2) * (W + 2); A.KG = Cpad / 8;
   SAN_CHECK_ARG((long long)N * A.KG <= 65535, "san_tc_stage: N*KG too large for grid.y");
@@ -896,7 +908,7 @@ static int launch_stage(StageArgs& A, void* xs, int N, int H, int W, int Cpad, i
 
 int san_tc_stage_terms(void* xs, int N, int H, int W, int Cpad, const san_stage_term* terms, int nterms, int fmt,
                        const float* absmax, void* stream) {
-  SAN_CHECK_ARG(xs && terms && nterms >= 1 && nterms <= STAGE_MAX_TERMS && N > 0 && H > 0 && W > 0 && Cpad % 16 == 0,
+  SAN_CHECK_ARG(xs && terms && nterms >= 1 && nterms <= STAGE_MAX_TERMS && N > 0 && H > 0 && W > 0 && Cpad % 8 == 0,
                 "san_tc_stage_terms: bad args");
   StageArgs A{};
   A.nterms = nterms;
@@ -918,7 +930,7 @@ int san_tc_stage_act(void* xs, int N, int H, int W, int Cpad,
                      const float* y1, const float* mu1, const float* a1, const float* b1, float slope1, int C1, int mode1,
                      const float* y2, const float* mu2, const float* a2, const float* b2, float slope2, int C2, int mode2,
                      int fmt, void* stream) {
-  SAN_CHECK_ARG(xs && y0 && N > 0 && H > 0 && W > 0 && Cpad % 16 == 0 && C0 > 0, "san_tc_stage_act: bad args");
+  SAN_CHECK_ARG(xs && y0 && N > 0 && H > 0 && W > 0 && Cpad % 8 == 0 && C0 > 0, "san_tc_stage_act: bad args");
   StageArgs A{};
   A.s[0] = StageTerm{y0, mu0, a0, b0, slope0, C0, mode0, 0};
   A.nterms = 1;
@@ -931,7 +943,7 @@ int san_tc_unstage_act(const void* xs, float* x, int N, int C, int H, int W, int
   SAN_CHECK_ARG(xs && x && N > 0 && C > 0 && H > 0 && W > 0, "san_tc_unstage_act: bad args");
   const long long total = (long long)N * C * H * W;
   unstage_act_kernel<<<ew_blocks(total), 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)xs + TC_LEAD, x, N, C, H, W,
-                                                                         pad16(C) / 8, fmt);
+                                                                         (C + 7) / 8, fmt);
   SAN_LAUNCH_CHECK();
   return SAN_OK;
 }

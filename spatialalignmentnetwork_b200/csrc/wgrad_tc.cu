@@ -60,7 +60,7 @@ int wg_rown_enabled() { static const int v = wg_env_int("SAN_WG_ROWN", 1); retur
 bool wg_geometry(int H, int W, int Cin, int Cout, int K, WgGeom* g) {
   if (K != 1 && K != 3) return false;
   if (W + 2 < 18) return false;   // the 16-slot tail padding must stay inside the zero border row
-  g->KGo = pad16(Cout) / 8; g->KGi = pad16(Cin) / 8;
+  g->KGo = (Cout + 7) / 8; g->KGi = (Cin + 7) / 8;   // REAL channel groups = planes of the staged tensors (no all-zero groups)
   g->nmb = (g->KGo + 15) / 16;
   const int cip = pad16(Cin);
   g->nnc = 0;
@@ -68,6 +68,9 @@ bool wg_geometry(int H, int W, int Cin, int Cout, int K, WgGeom* g) {
     if (cip % k == 0 && (cip / k) % 16 == 0 && cip / k <= 160) { g->nnc = k; break; }
   if (!g->nnc) return false;
   g->Nn = cip / g->nnc; g->KGn = g->Nn / 8;
+  // narrow layers (one chunk, M = 64 shape: N may be any multiple of 8): the MMA N covers the real groups only
+  // (18 input channels: N = 24 per filter row instead of 32)
+  if (g->nnc == 1 && g->nmb == 1 && 2 * g->KGo <= 8) { g->KGn = g->KGi; g->Nn = 8 * g->KGi; }
   g->rown = (K == 3 && 9 * g->Nn <= 512 && wg_rown_enabled()) ? 1 : 0;     // 3 dx accumulators of [M x 3 Nn] in 512 TMEM columns
   g->ncp = g->rown ? 3 : 1;
   g->ndy = g->rown ? 1 : K;
@@ -180,6 +183,8 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_tc_kernel(const WgParams 
     uint32_t ph = 0;
     const int per_hl = kga + ncp * g.KGn;
     const int ncopy = 2 * per_hl;
+    const int kgl = min(g.KGn, g.KGi - nc * g.KGn);      // real groups of this chunk (a padding group has no staged plane:
+                                                         // its shared-memory plane keeps stale data, its dW columns are dropped)
     for (int u = cta; u < nunits; u += p.ctas_per_group) {
       const int n = u / g.nchunks, ch = u - n * g.nchunks;
       const int p0 = g.range0 + ch * g.KC;
@@ -187,7 +192,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_tc_kernel(const WgParams 
       const uint32_t bytesA = (uint32_t)kc * 16, bytesB = (uint32_t)(kc + 2) * 16;   // X span: kc + 2 tap slots
       mbar_wait(bar_empty + 8 * s, ph ^ 1);
       const uint32_t sbase = stage0 + (uint32_t)s * g.stage_bytes;
-      if (lane == 0) mbar_expect_tx(bar_full + 8 * s, 2u * kga * bytesA + 2u * ncp * g.KGn * bytesB);
+      if (lane == 0) mbar_expect_tx(bar_full + 8 * s, 2u * kga * bytesA + 2u * ncp * kgl * bytesB);
       __syncwarp();
       for (int c = lane; c < ncopy; c += 32) {
         const int hl = c / per_hl, r = c - hl * per_hl;
@@ -197,6 +202,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_tc_kernel(const WgParams 
         } else {
           const int rr = r - kga;
           const int cp = rr / g.KGn, kg = rr - cp * g.KGn;        // cp: row-shifted copy = filter row (rown form)
+          if (kg >= kgl) continue;
           const int xo = g.rown ? (cp - 1) * g.Wp - 1 : xoff;
           const __nv_bfloat16* src =
               p.xs + ((long long)(n * 2 + hl) * g.KGi + nc * g.KGn + kg) * plane + (long long)(p0 + xo) * 8;

@@ -10,8 +10,9 @@ all-reduce asynchronously the moment its last gradient is written - cascade 11's
 travel while cascades 10..0 are still being differentiated.  ``CSModel.update`` brackets each backward with
 ``arm(nets)`` / ``sync(nets)``; ``sync`` only waits for the handles.
 
-BatchNorm in ``net_T`` / ``net_G`` uses per-rank batch statistics (standard DDP semantics) unless ``cfg.sync_bn`` asks
-for global-batch statistics (``SyncStats``); identical masks are obtained by seeding python ``random`` identically."""
+BatchNorm in ``net_T`` / ``net_G`` uses per-rank batch statistics (standard DDP semantics) unless
+``attach(..., sync_bn=True)`` asks for global-batch statistics (the per-plane sums of all ranks are all-gathered before
+the finalise kernels, ``tc.SYNC_BN_GROUP``); identical masks are obtained by seeding python ``random`` identically."""
 import torch
 import torch.distributed as dist
 
@@ -177,13 +178,17 @@ def average_buffers(model, group=None):
             o += b.numel()
 
 
-def attach(model, group=None, overlap=True):
+def attach(model, group=None, overlap=True, sync_bn=False):
     """Install the gradient exchange into a ``CSModel`` (after ``model.to(device)``) and synchronise its initial
-    state.  ``overlap=False`` keeps the blocking single-bucket all-reduce after the backward."""
+    state.  ``overlap=False`` keeps the blocking single-bucket all-reduce after the backward; ``sync_bn=True`` makes
+    every BatchNorm layer (``net_T``, ``net_G``, ``net_D``) use the statistics of the GLOBAL batch (tc.SYNC_BN_GROUP)."""
     nets = [getattr(model, k) for k in _NETS if hasattr(model, k)]
     broadcast_state(nets, group=group)
     if not _active(group):
         return model
+    if sync_bn:
+        from . import tc
+        tc.SYNC_BN_GROUP = group if group is not None else dist.group.WORLD
     if overlap:
         model.grad_buckets = GradBuckets(model, group=group)
     model.grad_sync = lambda params: allreduce_mean_grads(params, group=group)

@@ -45,6 +45,22 @@ KEEP_STAGED_BELOW = 0.55
 _total_mem = {}
 
 
+# BatchNorm batch statistics under data parallelism: None = per-rank statistics (standard DDP semantics); a
+# torch.distributed process group (set by parallel.attach(..., sync_bn=True)) = statistics of the GLOBAL batch: the
+# per-plane sums of every rank are all-gathered (a few hundred floats per layer) before the finalise kernels, so a
+# sharded step equals the single-process reference at the global batch size (reference unet.py:119-140 runs one process).
+SYNC_BN_GROUP = None
+
+
+def _gather_planes(t):
+    """[planes] per-(n, c) statistics of this rank -> [world * planes] of the global batch (rank-major = sample-major)."""
+    import torch.distributed as dist
+    w = dist.get_world_size(SYNC_BN_GROUP)
+    out = torch.empty(w * t.numel(), dtype=t.dtype, device=t.device)
+    dist.all_gather_into_tensor(out, t.contiguous(), group=SYNC_BN_GROUP)
+    return out, w
+
+
 def _keep_staged(device):
     idx = device.index if device.index is not None else torch.cuda.current_device()
     if idx not in _total_mem:
@@ -106,8 +122,16 @@ class Raw:
                         bn.num_batches_tracked.add_(1)
                     if self.up:
                         st[1].mul_(4.0)      # m2 of the up-sampled map
-                call("bn_finalize_fwd", st[0], st[1], bn.weight, bn.bias, bn.running_mean, bn.running_var,
-                     st[2], st[3], st[4], st[5], N, C, P * (4 if self.up else 1), bn.eps, bn.momentum, int(training))
+                if training and SYNC_BN_GROUP is not None:
+                    g0, w = _gather_planes(st[0])
+                    g1, _ = _gather_planes(st[1])
+                    out = torch.empty(4, w * planes, dtype=torch.float32, device=yd.device)
+                    call("bn_finalize_fwd", g0, g1, bn.weight, bn.bias, bn.running_mean, bn.running_var,
+                         out[0], out[1], out[2], out[3], N * w, C, P * (4 if self.up else 1), bn.eps, bn.momentum, 1)
+                    st[2:6].copy_(out[:, :planes])          # the coefficients are per channel: identical for every sample
+                else:
+                    call("bn_finalize_fwd", st[0], st[1], bn.weight, bn.bias, bn.running_mean, bn.running_var,
+                         st[2], st[3], st[4], st[5], N, C, P * (4 if self.up else 1), bn.eps, bn.momentum, int(training))
             self._coef = st
         return self._coef
 
@@ -138,8 +162,9 @@ def _stage_weights(w, dgrad, H, W, fmt):
     return ws
 
 
-def _pad16(c):
-    return (c + 15) // 16 * 16
+def _pad8(c):
+    """Channels of a staged tensor: ceil(C / 8) groups of 8 (no all-zero groups)."""
+    return (c + 7) // 8 * 8
 
 
 def _coef_views(norm, st):
@@ -201,7 +226,7 @@ class _FusedConv(Function):
                 ctot += C
         assert ctot == Cin, (ctot, Cin)
         xs = _staged_act(N, H, W, Cin, w.device)
-        _stage(xs, N, H, W, _pad16(Cin), terms, _FMT_FWD)
+        _stage(xs, N, H, W, _pad8(Cin), terms, _FMT_FWD)
         ws = _stage_weights(w, False, H, W, _FMT_FWD)
         out = torch.empty(N, Cout, H, W, dtype=torch.float32, device=w.device)
         call("tc_conv", xs, ws, bias, out, N, H, W, Cin, Cout, K, 0, 3 * _FMT_FWD, None)
@@ -251,7 +276,7 @@ class _FusedConv(Function):
             if amax is None:
                 amax = torch.empty(1, dtype=torch.float32, device=dev)
                 call("absmax", gy, gy.numel(), amax)
-        _stage(gys, N, H, W, _pad16(Cout), [(gy, None, None, None, 1.0, Cout, MODE_DIRECT, False)], _FMT_BWD, amax)
+        _stage(gys, N, H, W, _pad8(Cout), [(gy, None, None, None, 1.0, Cout, MODE_DIRECT, False)], _FMT_BWD, amax)
         # ---- weight gradient: tcgen05 GEMM over the pixel dimension on the staged dY and the re-staged input
         dw = db = None
         if ctx.needs_input_grad[0] or (has_bias and ctx.needs_input_grad[1]):
@@ -261,7 +286,7 @@ class _FusedConv(Function):
                 xs = xs_kept
             else:
                 xs = _staged_act(N, H, W, Cin, dev)
-                _stage(xs, N, H, W, _pad16(Cin),
+                _stage(xs, N, H, W, _pad8(Cin),
                        [(t["y"], *_coef_views(t["norm"], t["st"])[:3], t["slope"], t["C"], t["mode"], t["acc"]) for t in terms],
                        _FMT_BWD)
             if lib().san_tc_wgrad_supported(H, W, Cin, Cout, K):
@@ -325,8 +350,20 @@ class _FusedConv(Function):
                 else:
                     gamma = t["gamma"]
                     dgamma, dbeta = torch.empty_like(gamma), torch.empty_like(gamma)
-                    call("bn_finalize_bwd", wk[0], wk[1], gamma, sa, wk[2], wk[3], wk[4], dgamma, dbeta,
-                         y.shape[0], y.shape[1], P, int(t["bn_training"]))
+                    if t["bn_training"] and SYNC_BN_GROUP is not None:
+                        # global-batch statistics: the mean terms of dx use the sums of ALL ranks; dgamma / dbeta stay the
+                        # local sums (the gradient all-reduce averages them like every other parameter gradient)
+                        g0, w = _gather_planes(wk[0])
+                        g1, _ = _gather_planes(wk[1])
+                        out = torch.empty(3, w * planes, dtype=torch.float32, device=dev)
+                        call("bn_finalize_bwd", g0, g1, gamma, sa, out[0], out[1], out[2], dgamma, dbeta,
+                             y.shape[0] * w, y.shape[1], P, 1)
+                        wk[2:5].copy_(out[:, :planes])
+                        dbeta = wk[0].view(y.shape[0], -1).sum(0)
+                        dgamma = wk[1].view(y.shape[0], -1).sum(0)
+                    else:
+                        call("bn_finalize_bwd", wk[0], wk[1], gamma, sa, wk[2], wk[3], wk[4], dgamma, dbeta,
+                             y.shape[0], y.shape[1], P, int(t["bn_training"]))
                     grads[t["ti"] + 1], grads[t["ti"] + 2] = dgamma, dbeta
                 call("act_bwd_apply_map", dx, Cin, c0, mode, y, mu, a, b, slope, wk[2], wk[3], wk[4], dy, N, C, Hy, Wy,
                      _tag_absmax(dy))

@@ -204,8 +204,8 @@ def test_tc_geometry_covers_every_layer_shape(built):
                 assert L.san_tc_staged_weight_elems(h, w, cout, cin, k) > 0
                 if w >= 16:
                     assert L.san_tc_wgrad_supported(h, w, cin, cout, k) == 1, ("wgrad", h, w, cin, cout, k)
-    # staged activation buffer: [lead 8][N][2][Cpad/8][(H+2)(W+2)][8][trail 256]
-    assert L.san_tc_staged_act_elems(2, 4, 6, 18) == 2 * 2 * 4 * 6 * 8 * 8 + 8 + 256
+    # staged activation buffer: [lead 8][N][2][ceil(C/8)][(H+2)(W+2)][8][trail 256]: 18 channels = 3 groups
+    assert L.san_tc_staged_act_elems(2, 4, 6, 18) == 2 * 2 * 3 * 6 * 8 * 8 + 8 + 256
 
 
 def _describe(L, H, W, Cin, Cout, K):
@@ -237,7 +237,7 @@ def test_tc_flattened_pixel_formulation_on_cpu(built, shape):
     Wp, Hp, R, T, Npad, KG = g["Wp"], g["Hp"], g["R"], g["T"], g["Npad"], g["KG"]
     ntaps = K * K
     # resource bounds
-    assert g["Cin_pad"] % 16 == 0 and g["Cin_pad"] >= Cin and KG * 8 == g["Cin_pad"] and g["KS"] * 16 == g["Cin_pad"]
+    assert g["Cin_pad"] % 16 == 0 and g["Cin_pad"] >= Cin and KG == -(-Cin // 8) and g["KS"] * 16 == g["Cin_pad"]
     assert Npad % 16 == 0 and g["nsplit"] * Npad >= Cout and Npad <= 256
     assert T * g["Ncol"] * g["acc_stages"] <= 512                              # TMEM columns
     hls_on = os.environ.get("SAN_TC_HLS", "1") != "0"
@@ -263,10 +263,14 @@ def test_tc_flattened_pixel_formulation_on_cpu(built, shape):
         hi = t.to(torch.bfloat16).float()
         return hi, (t - hi).to(torch.bfloat16).float()
 
-    # staged activations [N][hl][KG][Hp*Wp][8] (zero border, zero pad channels)
+    # staged activations [N][hl][KG][Hp*Wp][8] (zero border, zero pad channels; KG = ceil(Cin / 8) REAL groups: with an
+    # odd count the padding group of the last K-step has no staged plane - modelled as a zero plane in the tile below,
+    # standing for "never read" (tap pairing) or "finite stale shared memory x zero weight rows" (otherwise)
+    KGp = g["Cin_pad"] // 8
     xp = torch.zeros(N, g["Cin_pad"], Hp, Wp)
     xp[:, :Cin, 1:H + 1, 1:W + 1] = x
-    xs = torch.stack(split(xp), 1).reshape(N, 2, KG, 8, Hp * Wp).permute(0, 1, 2, 4, 3)     # [N,hl,KG,slot,8]
+    xs = torch.stack(split(xp), 1).reshape(N, 2, KGp, 8, Hp * Wp).permute(0, 1, 2, 4, 3)     # [N,hl,KGp,slot,8]
+    assert float(xs[:, :, KG:].abs().max() if KGp > KG else 0.0) == 0.0                      # what is not staged is all zero
     wp_ = torch.zeros(g["nsplit"] * Npad, g["Cin_pad"], ntaps)
     wp_[:Cout, :Cin] = w.reshape(Cout, Cin, ntaps)
     whi, wlo = split(wp_)
@@ -275,7 +279,7 @@ def test_tc_flattened_pixel_formulation_on_cpu(built, shape):
         for st in range(g["strips"]):
             y0 = st * R
             rows_in = min(R + 2, Hp - y0)
-            tile = torch.zeros(2, KG, g["S_alloc"], 8)                         # what the TMA bulk copies deliver
+            tile = torch.zeros(2, KGp, g["S_alloc"], 8)                        # what the TMA bulk copies deliver
             tile[:, :, :rows_in * Wp] = xs[n][:, :, y0 * Wp:(y0 + rows_in) * Wp]
             if dxn:
                 # B rows nn = dx * Np + co per filter row dy; ONE A window per dy (offset dy * Wp); the accumulator
@@ -364,8 +368,11 @@ def test_tc_wgrad_formulation_on_cpu(built, shape):
     assert L.san_tc_wgrad_describe(H, W, Cin, Cout, K, ctypes.addressof(out)) == 0
     g = dict(zip("KGo KGi nmb nnc ndy Nn KGn KC XS stages smem_bytes nchunks Wp PS range0 range_len".split(), list(out)))
     Wp, PS, KC = g["Wp"], g["PS"], g["KC"]
-    assert g["nnc"] * g["Nn"] == g["KGi"] * 8 and g["Nn"] % 16 == 0 and g["Nn"] <= 160 and 3 * g["Nn"] <= 512
     import os
+    assert g["KGo"] == -(-Cout // 8) and g["KGi"] == -(-Cin // 8)            # real channel groups = staged planes
+    narrow = g["nnc"] == 1 and g["nmb"] == 1 and 2 * g["KGo"] <= 8           # M = 64 shape: N = the real groups only
+    assert g["Nn"] == (8 * g["KGi"] if narrow else (-(-Cin // 16) * 16) // g["nnc"]) and g["KGn"] * 8 == g["Nn"]
+    assert g["Nn"] % (8 if narrow else 16) == 0 and g["Nn"] <= 160 and 3 * g["Nn"] <= 512
     assert g["nmb"] == -(-g["KGo"] // 16) and KC % 16 == 0 and g["range_len"] % 16 == 0 and g["stages"] >= 2
     assert g["range0"] == Wp and g["range0"] + g["range_len"] <= PS and g["smem_bytes"] <= 225 * 1024
     assert g["nchunks"] == -(-g["range_len"] // KC)
@@ -376,8 +383,8 @@ def test_tc_wgrad_formulation_on_cpu(built, shape):
     (F.conv2d(x.double(), wr, padding=K // 2) * gy.double()).sum().backward()
     LEAD, TRAIL = 8, 256
 
-    def staged(t, C):       # flat buffer [lead][N][hl][KG][PS][8][trail] of BF16 hi/lo values (as float)
-        Cp = (C + 15) // 16 * 16
+    def staged(t, C):       # flat buffer [lead][N][hl][KG][PS][8][trail] of hi/lo values (as float), KG = ceil(C / 8)
+        Cp = (C + 7) // 8 * 8
         tp = torch.zeros(N, Cp, H + 2, W + 2)
         tp[:, :C, 1:H + 1, 1:W + 1] = t
         hi = tp.to(torch.bfloat16).float()
@@ -417,8 +424,10 @@ def test_tc_wgrad_formulation_on_cpu(built, shape):
                         kc = min(KC, g["range_len"] - ch * KC)
                         A = [torch.cat([span(dys, KGo, n, hl, 16 * mb + k, p0, kc) for k in range(kga)], 1) for hl in (0, 1)]
                         # B planes [hl][row copy][kg]: the N index of the MMA is (row copy, channel)
+                        kgl = min(g["KGn"], KGi - nc * g["KGn"])        # real groups of this chunk; a padding group is never
+                        zpl = torch.zeros(kc + 2, 8, dtype=torch.float64)   # loaded (stale plane, dW columns dropped): zeros here
                         B = [torch.cat([span(xs, KGi, n, hl, nc * g["KGn"] + k, p0 + ((dy - 1) * Wp - 1 if K == 3 else 0), kc + 2)
-                                        for dy in rows for k in range(g["KGn"])], 1) for hl in (0, 1)]
+                                        if k < kgl else zpl for dy in rows for k in range(g["KGn"])], 1) for hl in (0, 1)]
                         for dx in range(ndx):
                             Bh, Bl = B[0][dx:dx + kc], B[1][dx:dx + kc]
                             D[dx] += A[0].T @ Bh + A[1].T @ Bh + A[0].T @ Bl

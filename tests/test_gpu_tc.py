@@ -26,7 +26,7 @@ def stage(x, fmt=BF16):
     L = _lib()
     N, C, H, W = x.shape
     xs = torch.empty(L.lib().san_tc_staged_act_elems(N, H, W, C), dtype=torch.bfloat16, device=x.device)
-    Cpad = (C + 15) // 16 * 16
+    Cpad = (C + 7) // 8 * 8          # ceil(C / 8) channel groups
     L.call("tc_stage_act", xs, N, H, W, Cpad, x, None, None, None, 1.0, C, 0,
            None, None, None, None, 1.0, 0, 0, None, None, None, None, 1.0, 0, 0, fmt)
     return xs
@@ -48,7 +48,7 @@ def stage_dyn(x):
     term = tc_mod()._StageTerm(y=x.data_ptr(), mu=None, a=None, b=None, slope=1.0, C=C, mode=0, accumulate=0)
     arr = (tc_mod()._StageTerm * 1)(term)
     import ctypes
-    L.call("tc_stage_terms", xs, N, H, W, (C + 15) // 16 * 16, ctypes.addressof(arr), 1, F16, am)
+    L.call("tc_stage_terms", xs, N, H, W, (C + 7) // 8 * 8, ctypes.addressof(arr), 1, F16, am)
     return xs, am
 
 

@@ -37,7 +37,7 @@ def main():
         xs = torch.empty(L.lib().san_tc_staged_act_elems(N, HW, HW, Cin), dtype=torch.bfloat16, device="cuda")
         ws = torch.empty(L.lib().san_tc_staged_weight_elems(HW, HW, Cout, Cin, K), dtype=torch.bfloat16, device="cuda")
         y = torch.empty(N, Cout, HW, HW, device="cuda")
-        Cpad = (Cin + 15) // 16 * 16
+        Cpad = (Cin + 7) // 8 * 8
         st = lambda: L.call("tc_stage_act", xs, N, HW, HW, Cpad, x, None, None, None, 1.0, Cin, 0,
                             None, None, None, None, 1.0, 0, 0, None, None, None, None, 1.0, 0, 0, 1)
         L.call("tc_stage_weights", w, ws, HW, HW, Cout, Cin, K, 0, 1)
@@ -47,7 +47,7 @@ def main():
         fp = lambda: L.call("conv2d_fwd", x, wp, None, y2, N, Cin, HW, HW, Cout, K, 0, 0)
         gy = torch.randn(N, Cout, HW, HW, device="cuda")
         gys = torch.empty(L.lib().san_tc_staged_act_elems(N, HW, HW, Cout), dtype=torch.bfloat16, device="cuda")
-        L.call("tc_stage_act", gys, N, HW, HW, (Cout + 15) // 16 * 16, gy, None, None, None, 1.0, Cout, 0,
+        L.call("tc_stage_act", gys, N, HW, HW, (Cout + 7) // 8 * 8, gy, None, None, None, 1.0, Cout, 0,
                None, None, None, None, 1.0, 0, 0, None, None, None, None, 1.0, 0, 0, 1)
         dw = torch.empty_like(w)
         wg = lambda: L.call("tc_wgrad", gys, xs, dw, None, None, N, HW, HW, Cin, Cout, K, 3, None)   # fp16 pairs (timing only)
