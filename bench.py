@@ -47,6 +47,7 @@ def parse():
                     help="weak: --batch slices per GPU; strong: --batch is the GLOBAL batch, split over the GPUs")
     ap.add_argument("--no-parity", action="store_true", help="skip the 2-slice parity block (oracle fp32 + fp64 on the host)")
     ap.add_argument("--no-overlap", action="store_true", help="N > 1: blocking flat all-reduce instead of the overlapped buckets")
+    ap.add_argument("--sync-bn", action="store_true", help="N > 1: global-batch BatchNorm statistics (parallel.attach(sync_bn=True))")
     ap.add_argument("--graph", action="store_true",
                     help="N = 1: capture set_input + update() into ONE CUDA graph and time replays (small batches are launch-bound)")
     ap.add_argument("--cascades", type=int, default=12)
@@ -225,7 +226,7 @@ CLASSES = {
     "conv": ("conv2d_fwd", "conv2d_wgrad", "conv_pack_weights", "tc_conv", "tc_wgrad", "tc_stage_weights"),
     "operand_staging": ("tc_stage_act", "tc_stage_terms", "tc_unstage_act", "absmax"),
     "fft_dc": ("fft_expand_dc", "fft_reduce", "fft_rss", "fft2", "dc_bwd", "cmul_conj_planar"),
-    "norm_act": ("plane_stats", "in_finalize_fwd", "bn_finalize_fwd", "affine_act_fwd", "act_bwd_reduce",
+    "norm_act": ("plane_stats", "plane_stats_in", "in_finalize_fwd", "bn_finalize_fwd", "affine_act_fwd", "act_bwd_reduce",
                  "in_finalize_bwd", "bn_finalize_bwd", "act_bwd_apply", "act_bwd_reduce_map", "act_bwd_apply_map",
                  "in_bwd_fused_map"),
     "resample": ("pool2", "up2", "depth_to_space2", "space_to_depth2", "axpby"),
@@ -498,7 +499,7 @@ def run_b200(args):
     net.net_R.checkpoint_cascades = ckpt
     net.to(dev).train()
     if world > 1:
-        parallel.attach(net, overlap=not args.no_overlap)
+        parallel.attach(net, overlap=not args.no_overlap, sync_bn=args.sync_bn)
 
     # per-rank shard of the global batch (weak: args.batch slices per GPU; strong: args.batch / world)
     full_h, aux_h = make_inputs(bpg, args, pin=True)

@@ -169,6 +169,10 @@ int san_tc_wgrad(const void* dys, const void* xs, float* dw, float* dbias, const
 /* ---- normalisation / activation / resampling (varnet.py:98,139-146,235,257-273; unet.py:119-140) ---- */
 /* per-plane mean and centred sum of squares (two-pass) */
 int san_plane_stats(const float* x, float* mean, float* m2, int planes, int P, void* stream);
+/* the same + the InstanceNorm2d coefficients (a = rstd = 1/sqrt(m2/P + eps), b = 0; varnet.py:141, biased variance) in
+ * one launch: san_plane_stats followed by san_in_finalize_fwd */
+int san_plane_stats_in(const float* x, float* mean, float* m2, float* a, float* b, int planes, int P, float eps,
+                       void* stream);
 /* InstanceNorm coefficients: a = rstd, b = 0 (the centre mu is the `mean` array itself) */
 int san_in_finalize_fwd(const float* mean, const float* m2, float* a, float* b, int planes, int P, float eps,
                         void* stream);

@@ -16,8 +16,11 @@
 namespace {
 
 // ---- statistics -------------------------------------------------------------
+// in_a / in_b (optional): the InstanceNorm coefficients of in_finalize_fwd_kernel written by the same thread (one launch
+// instead of two per normalised tensor); same float arithmetic on the same rounded m2.
 __global__ void __launch_bounds__(256) plane_stats_kernel(const float* __restrict__ x, float* __restrict__ mean,
-                                                          float* __restrict__ m2, int P) {
+                                                          float* __restrict__ m2, int P, float* __restrict__ in_a,
+                                                          float* __restrict__ in_b, float eps) {
   // ONE pass: shifted-data sums in fp64 (pivot = first element of the plane, so the subtraction
   // Q - S^2/P cancels at most a few bits): mean = K + S/P, m2 = sum (x - mean)^2 = Q - S^2/P.
   __shared__ double red[32];
@@ -52,6 +55,10 @@ __global__ void __launch_bounds__(256) plane_stats_kernel(const float* __restric
     if (v < 0.0) v = 0.0;
     mean[blockIdx.x] = (float)(K + S / (double)P);
     m2[blockIdx.x] = (float)v;
+    if (in_a) {
+      in_a[blockIdx.x] = 1.f / sqrtf((float)v / (float)P + eps);
+      in_b[blockIdx.x] = 0.f;
+    }
   }
 }
 
@@ -672,7 +679,15 @@ extern "C" {
 
 int san_plane_stats(const float* x, float* mean, float* m2, int planes, int P, void* stream) {
   SAN_CHECK_ARG(x && mean && m2 && planes > 0 && P > 0, "san_plane_stats: bad args");
-  plane_stats_kernel<<<planes, 256, 0, (cudaStream_t)stream>>>(x, mean, m2, P);
+  plane_stats_kernel<<<planes, 256, 0, (cudaStream_t)stream>>>(x, mean, m2, P, nullptr, nullptr, 0.f);
+  SAN_LAUNCH_CHECK();
+  return SAN_OK;
+}
+
+int san_plane_stats_in(const float* x, float* mean, float* m2, float* a, float* b, int planes, int P, float eps,
+                       void* stream) {
+  SAN_CHECK_ARG(x && mean && m2 && a && b && planes > 0 && P > 0, "san_plane_stats_in: bad args");
+  plane_stats_kernel<<<planes, 256, 0, (cudaStream_t)stream>>>(x, mean, m2, P, a, b, eps);
   SAN_LAUNCH_CHECK();
   return SAN_OK;
 }

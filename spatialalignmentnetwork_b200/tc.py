@@ -109,8 +109,7 @@ class Raw:
             yd = self.y.detach()
             if self.norm == "in":
                 st = torch.empty(4, planes, dtype=torch.float32, device=yd.device)
-                call("plane_stats", yd, st[0], st[1], planes, P)
-                call("in_finalize_fwd", st[0], st[1], st[2], st[3], planes, P, _IN_EPS)
+                call("plane_stats_in", yd, st[0], st[1], st[2], st[3], planes, P, _IN_EPS)
             else:
                 bn = self.bn
                 N, C = yd.shape[0], yd.shape[1]

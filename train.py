@@ -78,7 +78,7 @@ def main(args):
         net = CSModel(cfg)
     net.to(device)
     if world > 1:
-        parallel.attach(net)
+        parallel.attach(net, sync_bn=args.sync_bn)
     assert args.train.startswith("synthetic") and args.val.startswith("synthetic"), \
         "offline build: use --train synthetic[:N] --val synthetic[:N] (h5 volumes are not available)"
     n_train = int(args.train.split(":")[1]) if ":" in args.train else 64
@@ -176,6 +176,9 @@ if __name__ == "__main__":
     p.add_argument("--mi_weight", type=float, default=0.0, help="extra registration term ms_mi_loss(full, warped) (BASELINE cfg5)")
     p.add_argument("--gan_layers_G", type=str, default="", help="e.g. 8,16,16 (default: the reference's 64,128,256,512,512)")
     p.add_argument("--gan_layers_D", type=str, default="", help="e.g. '8,8;16,16' (default: the reference's widths)")
+    p.add_argument("--sync_bn", action="store_true",
+                   help="torchrun only: BatchNorm statistics of the GLOBAL batch (the sharded step then equals the "
+                        "single-process reference at --batch_size); default: per-rank statistics")
     p.add_argument("--log_every", type=int, default=50)
     p.add_argument("--ckpt_every", type=int, default=1000)
     main(p.parse_args())
