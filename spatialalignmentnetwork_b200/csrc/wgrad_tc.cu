@@ -36,7 +36,7 @@ namespace {
 
 constexpr int WG_THREADS = 192;
 constexpr int WG_HEADER = 256;
-constexpr int WG_SMEM_MAX = 225 * 1024;
+constexpr int WG_SMEM_LIMIT = 225 * 1024;
 constexpr int WG_KC_MAX = 512;   // pixel slots per stage (measured: fewer, larger stages win; per-stage TMA issue + barrier cost)
 
 struct WgGeom {
@@ -55,10 +55,20 @@ int wg_env_int(const char* name, int dflt) {
   const char* e = getenv(name);
   return e ? atoi(e) : dflt;
 }
+// Shared memory the kernel may take per CTA (SAN_WG_SMEM_KB: tuning runs).  The weight gradient runs next to the
+// element-wise backward kernels of the same layer (tc.py: side stream), whose CTAs need ~2 KB of shared memory each on the
+// same SM; measured (profiles/r2o_*): leaving 16 or 48 KB free does not help (385.1 ms/step at 225 KB, 387.2 at 209,
+// 393.2 at 177) - the geometries that carry the step do not fill 225 KB anyway.
+int wg_smem_max() {
+  static const int v = wg_env_int("SAN_WG_SMEM_KB", 225);
+  const int b = v * 1024;
+  return b > WG_SMEM_LIMIT ? WG_SMEM_LIMIT : (b < 64 * 1024 ? 64 * 1024 : b);
+}
 int wg_rown_enabled() { static const int v = wg_env_int("SAN_WG_ROWN", 1); return v; }   // 0: A/B runs against the per-row form
 
 bool wg_geometry(int H, int W, int Cin, int Cout, int K, WgGeom* g) {
   if (K != 1 && K != 3) return false;
+  const int WG_SMEM_MAX = wg_smem_max();
   if (W + 2 < 18) return false;   // the 16-slot tail padding must stay inside the zero border row
   g->KGo = (Cout + 7) / 8; g->KGi = (Cin + 7) / 8;   // REAL channel groups = planes of the staged tensors (no all-zero groups)
   g->nmb = (g->KGo + 15) / 16;
@@ -353,7 +363,7 @@ int san_tc_wgrad(const void* dys, const void* xs, float* dw, float* dbias, const
   SAN_CUDA(cudaMemsetAsync(dw, 0, sizeof(float) * (size_t)Cout * Cin * K * K, st));
   static bool attr_set = false;
   if (!attr_set) {
-    SAN_CUDA(cudaFuncSetAttribute(wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, WG_SMEM_MAX));
+    SAN_CUDA(cudaFuncSetAttribute(wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, WG_SMEM_LIMIT));
     attr_set = true;
   }
   wgrad_tc_kernel<<<p.ngroups * cpg, WG_THREADS, p.g.smem_bytes, st>>>(p);

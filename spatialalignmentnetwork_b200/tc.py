@@ -37,6 +37,23 @@ _FMT_BWD = FMT_F16 if _FMT_MODE == "f16" else FMT_BF16           # staged dY, X 
 # InstanceNorm backward as one kernel per tensor (san_in_bwd_fused_map); SAN_IN_BWD_FUSED=0: the three-kernel path
 _IN_BWD_FUSED = os.environ.get("SAN_IN_BWD_FUSED", "1") != "0"
 
+# Weight-gradient GEMM on a side stream, overlapped with the HBM-bound element-wise backward of the same layer
+# (normalisation backward of the conv's inputs + staging of their gradient for the producing layer): the GEMM is
+# tensor / shared-memory bound and its persistent CTA (192 threads) leaves room on every SM for those kernels' CTAs.
+# Two tcgen05 kernels never co-reside (each CTA allocates all 512 TMEM columns), so the fork happens AFTER the data
+# gradient of the layer and the join BEFORE its backward returns (autograd accumulates dW on the main stream, and the
+# next tcgen05 launch is the producing layer's data gradient).  SAN_WG_OVERLAP=0: everything on one stream.
+_WG_OVERLAP = os.environ.get("SAN_WG_OVERLAP", "1") != "0"
+_side = {}
+
+
+def _side_stream(device):
+    idx = device.index if device.index is not None else torch.cuda.current_device()
+    if idx not in _side:
+        _side[idx] = torch.cuda.Stream(device=idx)
+    return _side[idx]
+
+
 # Staged operands are as large as the activations they come from.  They are re-created in the backward
 # pass (for the weight gradient) unless HBM is plentiful: while live tensors take less than
 # this fraction of the device memory, the forward keeps them (a B200 has 180 GB; the benchmark step
@@ -193,6 +210,28 @@ def _known_absmax(gy):
     return None
 
 
+def _prestage(dy, t):
+    """``dy`` = the gradient this layer's backward just wrote for a conv output with a single consumer: it IS the ``gy`` of
+    the producing conv's backward, so it is staged here - inside the window in which this layer's weight-gradient GEMM runs
+    on the side stream - and rides on the tensor object like the absmax tag."""
+    if not (_WG_OVERLAP and t["prestage"] and _FMT_BWD == FMT_F16):
+        return
+    tag = getattr(dy, "_san_absmax", None)
+    if tag is None:
+        return
+    N, C, H, W = dy.shape
+    gys = _staged_act(N, H, W, C, dy.device)
+    _stage(gys, N, H, W, _pad8(C), [(dy, None, None, None, 1.0, C, MODE_DIRECT, False)], _FMT_BWD, tag[0])
+    dy._san_staged = (gys, tag[0], dy._version)
+
+
+def _known_staged(gy):
+    tag = getattr(gy, "_san_staged", None)
+    if tag is not None and tag[2] == gy._version and gy.is_contiguous():
+        return tag[0], tag[1]
+    return None, None
+
+
 class _FusedConv(Function):
     """y = conv2d(concat_k sum_j act(norm(resample(raw_kj))), w) + bias on the tcgen05 kernels.
 
@@ -217,7 +256,7 @@ class _FusedConv(Function):
         else:
             H, W = y0.shape[2], y0.shape[3]
         terms, ctot = [], 0
-        for y, (norm, slope, d2s, mode, acc, coef, _) in zip(ys, metas):
+        for y, (norm, slope, d2s, mode, acc, coef, _, _) in zip(ys, metas):
             C = y.shape[1] // 4 if d2s else y.shape[1]
             mu, a, b, _sa = _coef_views(norm, coef)
             terms.append((y, mu, a, b, slope, C, mode, acc))
@@ -236,7 +275,7 @@ class _FusedConv(Function):
         keep = (_keep_staged(w.device) and (ctx.needs_input_grad[0] or ctx.needs_input_grad[1])
                 and _FMT_BWD == _FMT_FWD)    # f16nomix: the weight gradient wants bf16 pairs -> re-staged in backward
         ctx.save_for_backward(w, *tensors, *coefs, *([xs] if keep else []))
-        ctx.meta = (K, [(m[0], m[1], m[2], m[3], m[4], m[5] is not None, m[6]) for m in metas], (N, H, W),
+        ctx.meta = (K, [(m[0], m[1], m[2], m[3], m[4], m[5] is not None, m[6], m[7]) for m in metas], (N, H, W),
                     bias is not None, len(tensors), keep)
         return out
 
@@ -250,11 +289,12 @@ class _FusedConv(Function):
         coef_list = list(saved[1 + ntens:len(saved) - (1 if kept else 0)])
         xs_kept = saved[-1] if kept else None
         Cout, Cin = w.shape[0], w.shape[1]
+        gy_in = gy
         gy = gy if gy.is_contiguous() else gy.contiguous()
         dev = w.device
         # unpack terms
         terms, ti, ci, c_next, c_prev = [], 0, 0, 0, 0
-        for (norm, slope, d2s, mode, acc, has_coef, bn_training) in metas:
+        for (norm, slope, d2s, mode, acc, has_coef, bn_training, prod) in metas:
             y = tensors[ti]
             gamma = tensors[ti + 1] if norm == "bn" else None
             C = y.shape[1] // 4 if d2s else y.shape[1]
@@ -265,22 +305,40 @@ class _FusedConv(Function):
             if not acc:
                 c_next = c0 + C
             terms.append(dict(y=y, gamma=gamma, norm=norm, slope=slope, d2s=d2s, mode=mode, acc=acc, st=st, C=C, c0=c0,
-                              ti=ti, bn_training=bn_training))
+                              ti=ti, bn_training=bn_training, prestage=prod[0] and prod[1][0] == 1))
             ti += 3 if norm == "bn" else 1
-        # dY staged once as a (hi, lo) pair: the operand of both the data- and the weight-gradient GEMMs
-        gys = _staged_act(N, H, W, Cout, dev)
-        amax = None
-        if _FMT_BWD == FMT_F16:          # dynamic power-of-two scale of the gradient operand
-            amax = _known_absmax(gy)     # left by the consumer's normalisation backward when it wrote gy
-            if amax is None:
-                amax = torch.empty(1, dtype=torch.float32, device=dev)
-                call("absmax", gy, gy.numel(), amax)
-        _stage(gys, N, H, W, _pad8(Cout), [(gy, None, None, None, 1.0, Cout, MODE_DIRECT, False)], _FMT_BWD, amax)
-        # ---- weight gradient: tcgen05 GEMM over the pixel dimension on the staged dY and the re-staged input
+        # dY staged once as a (hi, lo) pair: the operand of both the data- and the weight-gradient GEMMs (already done by
+        # the consuming layer's backward when this conv output had a single consumer: _prestage)
+        gys, amax = _known_staged(gy_in)
+        if gys is None:
+            gys = _staged_act(N, H, W, Cout, dev)
+            amax = None
+            if _FMT_BWD == FMT_F16:          # dynamic power-of-two scale of the gradient operand
+                amax = _known_absmax(gy_in)  # left by the consumer's normalisation backward when it wrote gy
+                if amax is None:
+                    amax = torch.empty(1, dtype=torch.float32, device=dev)
+                    call("absmax", gy, gy.numel(), amax)
+            _stage(gys, N, H, W, _pad8(Cout), [(gy, None, None, None, 1.0, Cout, MODE_DIRECT, False)], _FMT_BWD, amax)
+        need_dgrad = any(ctx.needs_input_grad[3 + t["ti"]] for t in terms)
+        need_wgrad = ctx.needs_input_grad[0] or (has_bias and ctx.needs_input_grad[1])
+        overlap = _WG_OVERLAP and need_dgrad and need_wgrad
+
+        # ---- weight gradient: tcgen05 GEMM over the pixel dimension on the staged dY and the (kept or re-staged) input
         dw = db = None
-        if ctx.needs_input_grad[0] or (has_bias and ctx.needs_input_grad[1]):
-            dw = torch.empty_like(w)
-            db = torch.empty(Cout, dtype=torch.float32, device=dev) if has_bias else None
+        wg_done = None
+
+        use_tc_wgrad = bool(lib().san_tc_wgrad_supported(H, W, Cin, Cout, K))
+        x32 = None
+
+        def weight_gradient():      # launches only: every buffer is allocated on the main stream beforehand
+            if use_tc_wgrad:
+                call("tc_wgrad", gys, xs, dw, db, gy if has_bias else None, N, H, W, Cin, Cout, K, 3 * _FMT_BWD, amax)
+            else:   # tiny images (W < 16): fp32 CUDA-core kernel on the un-staged operand
+                call("tc_unstage_act", xs, x32, N, Cin, H, W, _FMT_BWD)
+                call("conv2d_wgrad", x32, gy, dw, db, N, Cin, H, W, Cout, K, 0, 0)
+
+        xs = None
+        if need_wgrad:
             if xs_kept is not None:
                 xs = xs_kept
             else:
@@ -288,21 +346,27 @@ class _FusedConv(Function):
                 _stage(xs, N, H, W, _pad8(Cin),
                        [(t["y"], *_coef_views(t["norm"], t["st"])[:3], t["slope"], t["C"], t["mode"], t["acc"]) for t in terms],
                        _FMT_BWD)
-            if lib().san_tc_wgrad_supported(H, W, Cin, Cout, K):
-                call("tc_wgrad", gys, xs, dw, db, gy if has_bias else None, N, H, W, Cin, Cout, K, 3 * _FMT_BWD, amax)
-            else:   # tiny images (W < 16): fp32 CUDA-core kernel on the un-staged operand
+            dw = torch.empty_like(w)
+            db = torch.empty(Cout, dtype=torch.float32, device=dev) if has_bias else None
+            if not use_tc_wgrad:
                 x32 = torch.empty(N, Cin, H, W, dtype=torch.float32, device=dev)
-                call("tc_unstage_act", xs, x32, N, Cin, H, W, _FMT_BWD)
-                call("conv2d_wgrad", x32, gy, dw, db, N, Cin, H, W, Cout, K, 0, 0)
-                del x32
-            del xs
+            if not overlap:
+                weight_gradient()
         # ---- data gradient: the same tcgen05 conv on the staged dY with the flipped filter
         grads = [None] * ntens
-        if any(ctx.needs_input_grad[3 + t["ti"]] for t in terms):
+        if need_dgrad:
             wsd = _stage_weights(w, True, H, W, _FMT_BWD)
             dx = torch.empty(N, Cin, H, W, dtype=torch.float32, device=dev)
             call("tc_conv", gys, wsd, None, dx, N, H, W, Cout, Cin, K, 0, 3 * _FMT_BWD, amax)
-            del gys
+            if overlap:
+                # fork: the weight gradient starts when the data gradient has finished and runs next to the element-wise
+                # kernels below; every tensor it touches stays referenced until the join at the end of this function
+                main, side = torch.cuda.current_stream(), _side_stream(dev)
+                side.wait_stream(main)
+                with torch.cuda.stream(side):
+                    weight_gradient()
+                    wg_done = torch.cuda.Event()
+                    wg_done.record(side)
             for t in terms:
                 if not ctx.needs_input_grad[3 + t["ti"]]:
                     continue
@@ -332,6 +396,7 @@ class _FusedConv(Function):
                     ones = torch.ones(planes, dtype=torch.float32, device=dev)
                     call("act_bwd_apply_map", dx, Cin, c0, mode, y, None, ones, None, slope, ones, None, None, dy,
                          N, C, Hy, Wy, _tag_absmax(dy))
+                    _prestage(dy, t)
                     grads[t["ti"]] = dy
                     continue
                 planes = st.shape[1]
@@ -340,6 +405,7 @@ class _FusedConv(Function):
                 if t["norm"] == "in" and _IN_BWD_FUSED:
                     # per-plane statistics: reduce + coefficients + apply in one kernel, second pass out of L2
                     call("in_bwd_fused_map", dx, Cin, c0, mode, y, mu, a, slope, dy, N, C, Hy, Wy, _tag_absmax(dy))
+                    _prestage(dy, t)
                     grads[t["ti"]] = dy
                     continue
                 wk = torch.empty(5, planes, dtype=torch.float32, device=dev)
@@ -366,7 +432,10 @@ class _FusedConv(Function):
                     grads[t["ti"] + 1], grads[t["ti"] + 2] = dgamma, dbeta
                 call("act_bwd_apply_map", dx, Cin, c0, mode, y, mu, a, b, slope, wk[2], wk[3], wk[4], dy, N, C, Hy, Wy,
                      _tag_absmax(dy))
+                _prestage(dy, t)
                 grads[t["ti"]] = dy
+        if wg_done is not None:
+            torch.cuda.current_stream().wait_event(wg_done)     # join: dW is accumulated by autograd on the main stream
         return (dw, db, None, *grads)
 
 
@@ -380,9 +449,19 @@ def fused_conv(sources, weight, bias=None, modes=None):
         for j, r in enumerate(group):
             mode = modes[i] if modes is not None else (MODE_D2S if r.d2s else MODE_UP if r.up else MODE_DIRECT)
             bn_training = bool(r.bn.training or not r.bn.track_running_stats) if r.norm == "bn" else False
-            metas.append((r.norm, r.slope, r.d2s, mode, j > 0, r.coef(), bn_training))
+            # consumer count of the raw tensor (shared, final by the time the backward runs) and whether a fused conv
+            # produced it: a single-consumer conv output gets its gradient staged by THIS layer's backward
+            uses = getattr(r.y, "_san_uses", None)
+            if uses is None:
+                uses = [0]
+                r.y._san_uses = uses
+            uses[0] += 1
+            metas.append((r.norm, r.slope, r.d2s, mode, j > 0, r.coef(), bn_training,
+                          (bool(getattr(r.y, "_san_conv_out", False)), uses)))
             tensors.append(r.y)
             if r.norm == "bn":
                 tensors += [r.bn.weight, r.bn.bias]
     K = weight.shape[-1]
-    return _FusedConv.apply(weight, bias, (K, metas), *tensors)
+    out = _FusedConv.apply(weight, bias, (K, metas), *tensors)
+    out._san_conv_out = True
+    return out
