@@ -153,6 +153,17 @@ int san_tc_stage_weights(const float* w, void* ws, int H, int W, int Cout, int C
  * Cin/Cout are the channel counts of THIS launch (for dgrad: Cin = original Cout, Cout = original Cin) */
 int san_tc_conv(const void* xs, const void* ws, const float* bias, float* y, int N, int H, int W, int Cin, int Cout,
                 int K, long long y_bs, int fmt, const float* a_absmax, void* stream);
+/* The same convolution with a STATISTICS EPILOGUE: sums[N][Cout][2] (fp64, zeroed by the call) receives the per-plane sum
+ * and sum of squares of y, accumulated by the epilogue warps while they store y (per-warp partials in shared memory,
+ * flushed with fp64 atomicAdd when a CTA moves to another image: reproducible) - what the reference's InstanceNorm2d (varnet.py:141) would
+ * otherwise re-read the whole tensor for.  san_in_stats_from_sums turns them into the coefficient table of
+ * san_plane_stats_in (mean, m2, a = rstd, b = 0); group = 4 for the pixel-shuffled ConvTranspose2d output (four
+ * sub-planes of a channel normalise together, varnet.py:176-181), P = elements per sub-plane. */
+int san_tc_conv_stats_supported(int H, int W, int Cin, int Cout, int K);
+int san_tc_conv_stats(const void* xs, const void* ws, const float* bias, float* y, int N, int H, int W, int Cin, int Cout,
+                      int K, long long y_bs, int fmt, const float* a_absmax, double* sums, void* stream);
+int san_in_stats_from_sums(const double* sums, float* mean, float* m2, float* a, float* b, int planes, int group, int P,
+                           float eps, void* stream);
 
 /* dW[Cout,Cin,K,K] (and dbias[Cout] from the fp32 dy, both optional-bias) from the staged dY and the staged
  * input of the forward conv: tcgen05 GEMM over the pixel dimension, MN-major operands, BF16x3 */

@@ -219,8 +219,50 @@ struct ConvTcParams {
   int fmt;                  // TC_FMT_* bits: which operands are fp16 pairs (else bf16 pairs)
   float out_scale;          // exact inverse of the operands' static scales
   const float* a_absmax;    // null, or device scalar max|A| when A was staged with the dynamic scale (dY in the data gradient)
+  double* sums;             // null, or [N][Cout][2] fp64, pre-zeroed: per-plane sum / sum of squares of y, accumulated by the epilogue
+  int contig;               // 1: a CTA walks a CONTIGUOUS range of units (consecutive strips of one image) instead of a strided one
+  int stat_off;             // byte offset of the epilogue's per-warp statistics accumulators in shared memory
   TcGeom g;
 };
+
+// Units of this CTA: [u0, u1) with step us.  Strided (u = blockIdx.x + k * gridDim.x): neighbouring CTAs work on neighbouring
+// strips at the same time; contiguous: one CTA walks consecutive strips of the same image (the statistics epilogue then
+// flushes its accumulators only a few times per launch).
+__device__ __forceinline__ void tc_unit_range(const ConvTcParams& p, int& u0, int& u1, int& us) {
+  if (p.contig) {
+    u0 = (int)((long long)blockIdx.x * p.nunits / gridDim.x);
+    u1 = (int)((long long)(blockIdx.x + 1) * p.nunits / gridDim.x);
+    us = 1;
+  } else {
+    u0 = blockIdx.x; u1 = p.nunits; us = gridDim.x;
+  }
+}
+
+// Sum over the 32 lanes of 16 per-lane values w[0..15] (a transposing butterfly: 16 shuffles instead of 80): on return
+// every lane holds the total of value index (lane >> 1) & 15 (both lanes of a pair hold the same one).
+__device__ __forceinline__ float warp_sum16(const float (&w)[16], int lane) {
+  float r[8], q[4], t[2];
+  const bool b4 = lane & 16, b3 = lane & 8, b2 = lane & 4, b1 = lane & 2;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const float send = b4 ? w[i] : w[8 + i], keep = b4 ? w[8 + i] : w[i];
+    r[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float send = b3 ? r[i] : r[4 + i], keep = b3 ? r[4 + i] : r[i];
+    q[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+  }
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    const float send = b2 ? q[i] : q[2 + i], keep = b2 ? q[2 + i] : q[i];
+    t[i] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+  }
+  const float send = b1 ? t[0] : t[1], keep = b1 ? t[1] : t[0];
+  float u = keep + __shfl_xor_sync(0xffffffffu, send, 2);
+  u += __shfl_xor_sync(0xffffffffu, u, 1);
+  return u;
+}
 
 // ---------------------------------------------------------------------------------- MMA issue
 // One K-step of one unit: NSTEP (A window, B block) descriptor pairs per 128-pixel tile.  a_word[i] = low descriptor word
@@ -283,7 +325,9 @@ __device__ __forceinline__ void mma_issue_loop(const ConvTcParams& p, const TcGe
   const uint32_t b_tapstride = 4u * g.Npad;
   int s = 0, as = 0;
   uint32_t ph = 0, aph = 0;
-  for (int u = blockIdx.x; u < p.nunits; u += gridDim.x) {
+  int u0, u1, us;
+  tc_unit_range(p, u0, u1, us);
+  for (int u = u0; u < u1; u += us) {
     mbar_wait(bar_acce + 8 * as, aph ^ 1);
     tc_fence_after();
     const uint32_t acc0 = tmem_base + (uint32_t)(as * g.T * g.Ncol);
@@ -310,6 +354,23 @@ __device__ __forceinline__ void mma_issue_loop(const ConvTcParams& p, const TcGe
     }
     if (++as == g.acc_stages) { as = 0; aph ^= 1; }
   }
+}
+
+// add this warp's accumulators of segment seg = n * nsplit + ns to sums[n][c_base + c][q] and clear them
+__device__ __forceinline__ void tc_flush_stats(const ConvTcParams& p, const TcGeom& g, float* sacc, int seg, int lane) {
+  __syncwarp();
+  const int n = seg / g.nsplit, ns = seg - n * g.nsplit;
+  const int c_base = ns * g.Npad;
+  const int c_cnt = min(g.Npad, p.Cout - c_base);
+  // fp64 atomics: a warp's partial is a deterministic fp32 sum (fixed unit order); the few partials per plane are added in
+  // fp64, where the order of the atomics no longer shows after the final rounding - the statistics are reproducible
+  double* dst = p.sums + ((long long)n * p.Cout + c_base) * 2;
+  for (int i = lane; i < 2 * c_cnt; i += 32) {
+    const float v = sacc[i];
+    if (v != 0.f) atomicAdd(dst + i, (double)v);
+    sacc[i] = 0.f;
+  }
+  __syncwarp();
 }
 
 // ---------------------------------------------------------------------------------- main kernel
@@ -354,7 +415,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const ConvTcPara
     if (lane == 0) {
       int s = 0;
       uint32_t ph = 0;
-      for (int u = blockIdx.x; u < p.nunits; u += gridDim.x) {
+      int u0, u1, us;
+      tc_unit_range(p, u0, u1, us);
+      for (int u = u0; u < u1; u += us) {
         const int n = u / units_per_image;
         const int rem = u - n * units_per_image;
         const int ns = rem / g.strips, st = rem - ns * g.strips;
@@ -400,13 +463,25 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const ConvTcPara
     int as = 0;
     uint32_t aph = 0;
     const long long HW = (long long)p.H * p.W;
-    for (int u = blockIdx.x; u < p.nunits; u += gridDim.x) {
+    // statistics epilogue (p.sums): per-warp accumulators [Npad][2] in shared memory (sum, sum of squares of the values this
+    // warp stored for the current (image, channel split) segment), flushed with atomicAdd when the segment changes
+    float* sacc = (float*)(smem + p.stat_off) + (size_t)(warp - 2) * (2 * g.Npad);
+    int seg = -1;
+    if (p.sums)
+      for (int i = lane; i < 2 * g.Npad; i += 32) sacc[i] = 0.f;
+    int u0, u1, us;
+    tc_unit_range(p, u0, u1, us);
+    for (int u = u0; u < u1; u += us) {
       const int n = u / units_per_image;
       const int rem = u - n * units_per_image;
       const int ns = rem / g.strips, st = rem - ns * g.strips;
       const int y0 = st * g.R;
       const int c_base = ns * g.Npad;
       const int c_cnt = min(g.Npad, p.Cout - c_base);
+      if (p.sums && seg != u / g.strips) {
+        if (seg >= 0) tc_flush_stats(p, g, sacc, seg, lane);
+        seg = u / g.strips;
+      }
       mbar_wait(bar_accf + 8 * as, aph);
       tc_fence_after();
       float* yn = p.y + (long long)n * p.y_bs;
@@ -486,15 +561,23 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const ConvTcPara
           } else {
             tc_ld8(trow + c0, v);
           }
-          if (valid) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const int c = c0 + j;
+            const float bv = (p.bias && c < c_cnt) ? __ldg(p.bias + c_base + c) : 0.f;
+            v[j] = fmaf(v[j], oscale, bv);
+            if (valid && c < c_cnt) dst[(long long)(c_base + c) * HW] = v[j];
+          }
+          if (p.sums) {
+            float w16[16];
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
-              const int c = c0 + j;
-              if (c < c_cnt) {
-                const float bv = p.bias ? __ldg(p.bias + c_base + c) : 0.f;
-                dst[(long long)(c_base + c) * HW] = fmaf(v[j], oscale, bv);
-              }
+              const float x = valid ? v[j] : 0.f;
+              w16[j] = x; w16[8 + j] = x * x;
             }
+            const float tot = warp_sum16(w16, lane);
+            const int vi = (lane >> 1) & 15, c = c0 + (vi & 7);
+            if (!(lane & 1) && c < c_cnt) sacc[2 * c + (vi >> 3)] += tot;
           }
         }
       }
@@ -503,6 +586,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const ConvTcPara
       if (lane == 0) mbar_arrive(bar_acce + 8 * as);
       if (++as == g.acc_stages) { as = 0; aph ^= 1; }
     }
+    if (p.sums && seg >= 0) tc_flush_stats(p, g, sacc, seg, lane);
   }
   tc_fence_before();
   __syncthreads();
@@ -961,8 +1045,25 @@ int san_tc_stage_weights(const float* w, void* ws, int H, int W, int Cout, int C
   return SAN_OK;
 }
 
-int san_tc_conv(const void* xs, const void* ws, const float* bias, float* y, int N, int H, int W, int Cin, int Cout,
-                int K, long long y_bs, int fmt, const float* a_absmax, void* stream) {
+// shared-memory bytes of the statistics epilogue's accumulators: one [Npad][2] fp32 table per epilogue warp
+static int tc_stat_bytes(const TcGeom& g) { return TC_EPI_WARPS * 2 * g.Npad * (int)sizeof(float); }
+
+// The accumulators go behind the pipeline stages; where the stages fill the shared memory, one of them (of more than two)
+// is given up.  Returns the number of stages to run with, 0 = no room.
+static int tc_stat_stages(const TcGeom& g) {
+  for (int stages = g.stages; stages >= 2 && stages >= g.stages - 1; --stages)
+    if (TC_SMEM_HEADER + g.xchg_bytes + stages * g.stage_bytes + tc_stat_bytes(g) <= TC_SMEM_MAX) return stages;
+  return 0;
+}
+
+int san_tc_conv_stats_supported(int H, int W, int Cin, int Cout, int K) {
+  TcGeom g;
+  if (!tc_geometry(H, W, Cin, Cout, K, &g) || g.dxn) return 0;
+  return tc_stat_stages(g) ? 1 : 0;
+}
+
+int san_tc_conv_stats(const void* xs, const void* ws, const float* bias, float* y, int N, int H, int W, int Cin, int Cout,
+                      int K, long long y_bs, int fmt, const float* a_absmax, double* sums, void* stream) {
   SAN_CHECK_ARG(xs && ws && y && N > 0 && H > 0 && W > 0 && Cin > 0 && Cout > 0 && (fmt == 0 || fmt == 3),
                 "san_tc_conv: bad args (fmt: 0 = bf16 pairs, 3 = fp16 pairs; the operands of an MMA share the format)");
   SAN_CHECK_ARG(!a_absmax || fmt == 3, "san_tc_conv: the dynamic scale applies to fp16 pairs only");
@@ -976,15 +1077,33 @@ int san_tc_conv(const void* xs, const void* ws, const float* bias, float* y, int
   p.y_bs = y_bs > 0 ? y_bs : (long long)Cout * H * W;
   p.N = N; p.H = H; p.W = W; p.Cout = Cout; p.ntaps = K * K;
   p.nunits = N * p.g.strips * p.g.nsplit;
+  cudaStream_t st = (cudaStream_t)stream;
+  int smem_bytes = p.g.smem_bytes;
+  p.sums = sums;
+  static const int contig_env = tc_env_int("SAN_TC_CONTIG", -1);     // -1: contiguous unit ranges with the statistics epilogue only
+  p.contig = contig_env < 0 ? (sums ? 1 : 0) : (contig_env ? 1 : 0);
+  if (sums) {
+    const int stages = p.g.dxn ? 0 : tc_stat_stages(p.g);
+    SAN_CHECK_ARG(stages, "san_tc_conv_stats: no statistics epilogue for this shape");
+    p.g.stages = stages;
+    p.stat_off = TC_SMEM_HEADER + p.g.xchg_bytes + p.g.stages * p.g.stage_bytes;
+    if (p.stat_off + tc_stat_bytes(p.g) > smem_bytes) smem_bytes = p.stat_off + tc_stat_bytes(p.g);
+    SAN_CUDA(cudaMemsetAsync(sums, 0, sizeof(double) * 2 * (size_t)N * Cout, st));
+  }
   static bool attr_set = false;
   if (!attr_set) {
     SAN_CUDA(cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_MAX));
     attr_set = true;
   }
   const int grid = p.nunits < san_num_sms() ? p.nunits : san_num_sms();
-  conv_tc_kernel<<<grid, TC_THREADS, p.g.smem_bytes, (cudaStream_t)stream>>>(p);
+  conv_tc_kernel<<<grid, TC_THREADS, smem_bytes, st>>>(p);
   SAN_LAUNCH_CHECK();
   return SAN_OK;
+}
+
+int san_tc_conv(const void* xs, const void* ws, const float* bias, float* y, int N, int H, int W, int Cin, int Cout,
+                int K, long long y_bs, int fmt, const float* a_absmax, void* stream) {
+  return san_tc_conv_stats(xs, ws, bias, y, N, H, W, Cin, Cout, K, y_bs, fmt, a_absmax, nullptr, stream);
 }
 
 }  // extern "C"

@@ -16,7 +16,10 @@
 #include <mutex>
 #include <vector>
 
+#include <cuda.h>      // CUtensorMap + enums only: cuTensorMapEncodeTiled is resolved through cudaGetDriverEntryPoint
+
 #include "san_common.cuh"
+#include "tc_common.cuh"
 #include "fft_v2.cuh"
 #include "../../include/san_b200.h"
 
@@ -323,6 +326,179 @@ __global__ void __launch_bounds__(256) fft_cols_kernel(const FftArgs a) {
   }
 }
 
+
+// ------------------------------------------------------------------------------------------------------------
+// Column pass with TMA-staged epilogue operands (H = 320, 8 columns per CTA, one coil per launch unit).
+// The soft-DC store reads k and k0 next to the transform, the coil-reducing store reads the sensitivity map: 20 to 40
+// dependent HBM loads per thread AFTER the FFT in fft_cols_v2_kernel (batched there, at 124 registers and 3 CTAs per SM).
+// Here ONE thread requests the CTA's [320 x 8] tiles of those operands as 2-D TMA tensor copies (cp.async.bulk.tensor,
+// SASS UTMALDG) into shared memory before the column loads are even issued: they arrive while the transform runs, cost
+// no registers, and the epilogue reads them from shared memory (a warp reads 4 rows x 64 B = 256 contiguous bytes).
+struct alignas(64) FftTmaArgs {
+  CUtensorMap m0;      // k (soft DC) or sens (coil reduce): [B][H][W] of 8-byte elements
+  CUtensorMap m1;      // k0 (soft DC)
+  FftArgs a;
+};
+constexpr int TMA_LINES = 8;
+constexpr int TMA_BOX_H = 160;                                   // box height (<= 256): two boxes per tile
+constexpr int TMA_TILE_BYTES = V2_N * TMA_LINES * 8;             // 20480
+constexpr int tma_smem_bytes(int tiles) { return tiles * TMA_TILE_BYTES + TMA_LINES * V2Ex::SIZE * 8 + V2_N * 8 + 16; }
+
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, int c0, int c1, int c2, uint32_t bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+      ::"r"(dst), "l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(bar)
+      : "memory");
+}
+
+template <bool INV, int STORE>
+__global__ void __launch_bounds__(TMA_LINES * V2_N2) fft_cols_tma_kernel(const __grid_constant__ FftTmaArgs ta) {
+  static_assert(STORE == ST_DC || STORE == ST_REDUCE, "TMA-staged epilogue: soft DC and coil reduce");
+  extern __shared__ __align__(128) uint8_t smraw[];
+  const FftArgs& a = ta.a;
+  constexpr int LINES = TMA_LINES, H = V2_N;
+  constexpr int TILES = (STORE == ST_DC) ? 2 : 1;                 // k + k0 | sens
+  float2* e0s = (float2*)smraw;                                   // [H][LINES]
+  float2* e1s = (float2*)(smraw + (TILES - 1) * TMA_TILE_BYTES);  // (aliases e0s when there is no second operand)
+  float2* z = (float2*)(smraw + TILES * TMA_TILE_BYTES);
+  float2* tws = z + LINES * V2Ex::SIZE;
+  const uint32_t bar = smem_u32(tws + V2_N);
+  const int W = a.W;
+  const int w0 = blockIdx.x * LINES;
+  const int ncol = (W - w0) < LINES ? (W - w0) : LINES;
+  const long long HW = (long long)H * W;
+  const long long b = blockIdx.y;
+  const float2* src = a.tmp + b * HW;
+  if (threadIdx.x == 0) {
+    mbar_init(bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    bool second = false;
+    if (STORE == ST_DC) {                            // k0 is only read in sampled columns
+      if (ncol == LINES && ((uintptr_t)(a.dcmask + w0) & 7) == 0) second = *(const unsigned long long*)(a.dcmask + w0) != 0ull;
+      else for (int c = 0; c < ncol; ++c) second |= a.dcmask[w0 + c] != 0;
+    }
+    mbar_expect_tx(bar, (second ? 2u : 1u) * TMA_TILE_BYTES);
+    tma_load_3d(smem_u32(e0s), &ta.m0, w0, 0, (int)b, bar);
+    tma_load_3d(smem_u32(e0s) + TMA_BOX_H * LINES * 8, &ta.m0, w0, TMA_BOX_H, (int)b, bar);
+    if (second) {
+      tma_load_3d(smem_u32(e1s), &ta.m1, w0, 0, (int)b, bar);
+      tma_load_3d(smem_u32(e1s) + TMA_BOX_H * LINES * 8, &ta.m1, w0, TMA_BOX_H, (int)b, bar);
+    }
+  }
+  {
+    const int l = threadIdx.x / LINES, col = threadIdx.x - l * LINES;
+    float2 v[V2_N1];
+    if (col < ncol) {
+#pragma unroll
+      for (int j = 0; j < V2_N1; ++j) v[j] = src[(long long)(V2_N2 * j + l) * W + w0 + col];
+    }
+    load_twiddles(tws, a.twH, V2_N);
+    __syncthreads();                                 // twiddles + the initialised barrier visible
+    if (col < ncol) {
+      fft_small::phase1<INV, V2_N1, V2_N2>(v, l, tws);
+#pragma unroll
+      for (int k1 = 0; k1 < V2_N1; ++k1) z[col * V2Ex::SIZE + V2Ex::at(k1, l)] = v[k1];
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x < LINES * V2_N1) {
+    const int k1 = threadIdx.x / LINES, col = threadIdx.x - k1 * LINES;
+    float2 v[V2_N2];
+    if (col < ncol) {
+#pragma unroll
+      for (int l = 0; l < V2_N2; ++l) v[l] = z[col * V2Ex::SIZE + V2Ex::at(k1, l)];
+      fft_small::phase2<INV, V2_N1, V2_N2>(v);
+    }
+    mbar_wait(bar, 0);                               // the operand tiles have landed
+    if (col < ncol) {
+      const int w = w0 + col;
+      const bool dc_on = (STORE == ST_DC) ? (a.dcmask[w] != 0) : false;
+      const float wgt = (STORE == ST_DC) ? __ldg(a.dcw) : 0.f;
+#pragma unroll
+      for (int k2 = 0; k2 < V2_N2; ++k2) {
+        const int h = k1 + V2_N1 * k2;
+        const long long hw = (long long)h * W + w;
+        const long long off = b * HW + hw;
+        const float2 o = make_float2(v[k2].x * a.scale, v[k2].y * a.scale);
+        const float2 e0 = e0s[h * LINES + col];
+        if (STORE == ST_DC) {
+          float2 d = e0;
+          if (dc_on) {
+            const float2 k0 = e1s[h * LINES + col];
+            d.x = e0.x - (e0.x - k0.x) * wgt;
+            d.y = e0.y - (e0.y - k0.y) * wgt;
+          }
+          a.out_c[off] = make_float2(d.x - o.x, d.y - o.y);
+        } else {
+          if (a.out_u) a.out_u[off] = o;
+          const float2 t = cmulc2(o, e0);
+          a.out_p[(b * 2) * HW + hw] = t.x;
+          a.out_p[(b * 2 + 1) * HW + hw] = t.y;
+        }
+      }
+    }
+  }
+}
+
+typedef CUresult (*TmapEncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                 const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                 CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+TmapEncodeFn tmap_encoder() {
+  static TmapEncodeFn fn = [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess ||
+        q != cudaDriverEntryPointSuccess)
+      p = nullptr;
+    return (TmapEncodeFn)p;
+  }();
+  return fn;
+}
+// [B][H][W] array of 8-byte elements, box = [1][TMA_BOX_H][TMA_LINES]
+bool make_tile_map(CUtensorMap* m, const void* base, int B, int H, int W) {
+  TmapEncodeFn enc = tmap_encoder();
+  if (!enc || ((uintptr_t)base & 15) || (W & 1)) return false;
+  const cuuint64_t gdim[3] = {(cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
+  const cuuint64_t gstr[2] = {(cuuint64_t)W * 8, (cuuint64_t)H * W * 8};
+  const cuuint32_t box[3] = {TMA_LINES, TMA_BOX_H, 1};
+  const cuuint32_t estr[3] = {1, 1, 1};
+  return enc(m, CU_TENSOR_MAP_DATA_TYPE_UINT64, 3, const_cast<void*>(base), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+             CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+// SAN_FFT_TMA = 0: the register-batched epilogue loads of fft_cols_v2_kernel (A/B runs)
+bool fft_tma_enabled() {
+  static const bool on = [] { const char* e = getenv("SAN_FFT_TMA"); return e ? atoi(e) != 0 : true; }();
+  return on;
+}
+
+template <bool INV, int STORE>
+int launch_cols_tma(const FftArgs& a, cudaStream_t st, bool* done) {
+  *done = false;
+  if (!(STORE == ST_DC || STORE == ST_REDUCE)) return SAN_OK;
+  if (!fft_tma_enabled() || a.H != V2_N || a.C != 1 || a.W % TMA_LINES != 0 || 2 * TMA_BOX_H != V2_N) return SAN_OK;
+  FftTmaArgs ta;
+  ta.a = a;
+  const void* p0 = (STORE == ST_DC) ? (const void*)a.k : (const void*)a.sens;
+  if (!make_tile_map(&ta.m0, p0, a.B, a.H, a.W)) return SAN_OK;
+  if (STORE == ST_DC) {
+    if (!make_tile_map(&ta.m1, a.k0, a.B, a.H, a.W)) return SAN_OK;
+  } else {
+    ta.m1 = ta.m0;
+  }
+  constexpr int kStore = (STORE == ST_DC || STORE == ST_REDUCE) ? STORE : ST_DC;     // (other stores never get here)
+  auto kern = fft_cols_tma_kernel<INV, kStore>;
+  constexpr int smem = tma_smem_bytes(kStore == ST_DC ? 2 : 1);
+  static bool attr_set = false;                      // (one static per template instantiation)
+  if (!attr_set) {
+    SAN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    attr_set = true;
+  }
+  kern<<<dim3(a.W / TMA_LINES, a.B), TMA_LINES * V2_N2, smem, st>>>(ta);
+  SAN_LAUNCH_CHECK();
+  *done = true;
+  return SAN_OK;
+}
+
 // SAN_FFT_V2: 1 / unset = register FFT for 320-point lines, 8 columns per column-pass CTA (default since round 2:
 // fft_expand_dc 0.147 -> 0.111 ms at bs 64, profiles/r2a_fft_v2_ab.txt); 2 = 16 columns per CTA; 0 = Stockham kernels only
 int fft_v2_mode() {
@@ -352,6 +528,11 @@ int launch_rows(const FftArgs& a, cudaStream_t st) {
 template <bool INV, int STORE>
 int launch_cols(const FftArgs& a, cudaStream_t st) {
   const bool reducing = (STORE == ST_REDUCE || STORE == ST_RSS);
+  if (fft_v2_enabled() && a.H == V2_N && fft_v2_mode() != 2) {
+    bool done = false;
+    const int rc = launch_cols_tma<INV, STORE>(a, st, &done);
+    if (rc != SAN_OK || done) return rc;
+  }
   if (fft_v2_enabled() && a.H == V2_N) {
     const int lines = fft_v2_mode() == 2 ? 16 : 8;
     dim3 grid2(san_cdiv(a.W, lines), reducing ? a.B / a.C : a.B);

@@ -86,36 +86,45 @@ template <bool INV, int LOAD>
 SAN_GLOBAL void SAN_LAUNCH_BOUNDS(V2_THREADS) fft_rows_v2_kernel(const FftArgs a) {
   SAN_SHARED float2 z[V2_LINES * V2Ex::SIZE];
   SAN_SHARED float2 tws[V2_N];
-  load_twiddles(tws, a.twW, V2_N);
   constexpr int W = V2_N;
   const long long nrows = (long long)a.B * a.H;
   const long long row0 = (long long)blockIdx.x * V2_LINES;
   const long long HW = (long long)a.H * W;
-  __syncthreads();
   {
     const int r = threadIdx.x / V2_N2, l = threadIdx.x - r * V2_N2;
     const long long row = row0 + r;
+    float2 v[V2_N1];
+    // the line's elements are requested FIRST, the twiddle table is copied while they are in flight: with the copy (a
+    // dependent global -> shared round trip) and its barrier in front, every CTA paid two memory latencies in series
     if (row < nrows) {
       const long long rowoff = row * W;
       const long long b = row / a.H;
       const long long g = (LOAD == LD_PLANAR_S) ? b / a.C : b;
       const long long hw0 = rowoff - b * HW;
-      float2 v[V2_N1];
+      float2 sv[LOAD == LD_PLANAR_S ? V2_N1 : 1];
 #pragma unroll
       for (int j = 0; j < V2_N1; ++j) {
         const int w = V2_N2 * j + l;
         if (LOAD == LD_C64) {
-          v[j] = a.in_c[rowoff + w];
+          v[j] = SAN_LDG(a.in_c + rowoff + w);
         } else if (LOAD == LD_C64_COLMASK) {
-          v[j] = a.in_c[rowoff + w];
-          const float m = a.colmask[w];
+          v[j] = SAN_LDG(a.in_c + rowoff + w);
+          const float m = SAN_LDG(a.colmask + w);
           v[j].x *= m; v[j].y *= m;
         } else {
-          v[j].x = a.in_p[(g * 2) * HW + hw0 + w];
-          v[j].y = a.in_p[(g * 2 + 1) * HW + hw0 + w];
-          if (LOAD == LD_PLANAR_S) v[j] = cmul2(v[j], a.sens[rowoff + w]);
+          v[j].x = SAN_LDG(a.in_p + (g * 2) * HW + hw0 + w);
+          v[j].y = SAN_LDG(a.in_p + (g * 2 + 1) * HW + hw0 + w);
+          if (LOAD == LD_PLANAR_S) sv[j] = SAN_LDG(a.sens + rowoff + w);
         }
       }
+      if (LOAD == LD_PLANAR_S) {
+#pragma unroll
+        for (int j = 0; j < V2_N1; ++j) v[j] = cmul2(v[j], sv[LOAD == LD_PLANAR_S ? j : 0]);
+      }
+    }
+    load_twiddles(tws, a.twW, V2_N);
+    __syncthreads();
+    if (row < nrows) {
       fft_small::phase1<INV, V2_N1, V2_N2>(v, l, tws);
 #pragma unroll
       for (int k1 = 0; k1 < V2_N1; ++k1) z[r * V2Ex::SIZE + V2Ex::at(k1, l)] = v[k1];
@@ -144,7 +153,6 @@ template <bool INV, int STORE, bool MULTI, int LINES>
 SAN_GLOBAL void SAN_LAUNCH_BOUNDS(LINES * V2_N2) fft_cols_v2_kernel(const FftArgs a) {
   SAN_SHARED float2 z[LINES * V2Ex::SIZE];
   SAN_SHARED float2 tws[V2_N];
-  load_twiddles(tws, a.twH, V2_N);
   constexpr int H = V2_N;
   const int W = a.W;
   const int w0 = blockIdx.x * LINES;
@@ -159,13 +167,18 @@ SAN_GLOBAL void SAN_LAUNCH_BOUNDS(LINES * V2_N2) fft_cols_v2_kernel(const FftArg
   for (int c = 0; c < ncoil; ++c) {
     const long long b = (reducing && MULTI) ? g * a.C + c : g;
     const float2* src = a.tmp + b * HW;
-    __syncthreads();                                 // twiddles visible / previous coil's phase 2 done with z
     {
       const int l = threadIdx.x / LINES, col = threadIdx.x - l * LINES;
+      float2 v[V2_N1];
+      // column elements requested before the twiddle copy / the barrier (see the row pass); plain loads: `tmp` may alias
+      // the output buffer (adjoint use), the row pass has written it in this stream
       if (col < ncol) {
-        float2 v[V2_N1];
 #pragma unroll
         for (int j = 0; j < V2_N1; ++j) v[j] = src[(long long)(V2_N2 * j + l) * W + w0 + col];
+      }
+      if (c == 0) load_twiddles(tws, a.twH, V2_N);
+      __syncthreads();                               // twiddles visible / previous coil's phase 2 done with z
+      if (col < ncol) {
         fft_small::phase1<INV, V2_N1, V2_N2>(v, l, tws);
 #pragma unroll
         for (int k1 = 0; k1 < V2_N1; ++k1) z[col * V2Ex::SIZE + V2Ex::at(k1, l)] = v[k1];
@@ -180,49 +193,72 @@ SAN_GLOBAL void SAN_LAUNCH_BOUNDS(LINES * V2_N2) fft_cols_v2_kernel(const FftArg
         for (int l = 0; l < V2_N2; ++l) v[l] = z[col * V2Ex::SIZE + V2Ex::at(k1, l)];
         fft_small::phase2<INV, V2_N1, V2_N2>(v);
         const int w = w0 + col;
+        // The operands the epilogue reads next to the transform (k, k0, sens) are fetched in BATCHES of V2_EPB through the
+        // read-only path BEFORE the batch's stores: written as load-use-store per element, the (non-restrict) stores kept
+        // every later load behind them - 20 to 40 dependent HBM round trips per thread, which made the soft-DC column pass
+        // 3.4x slower than the plain one (71 vs 21 us, profiles/r2a_fft_v2_ab.txt).
+        constexpr int V2_EPB = 10;
+        const long long col_off = b * HW + w;            // + h * W per element
+        const bool dc_on = (STORE == ST_DC) ? (a.dcmask[w] != 0) : false;
+        const float wgt = (STORE == ST_DC) ? SAN_LDG(a.dcw) : 0.f;
+        const float cm = (STORE == ST_C64_COLMASK) ? a.colmask[w] : 1.f;
 #pragma unroll
-        for (int k2 = 0; k2 < V2_N2; ++k2) {
-          const int h = k1 + V2_N1 * k2;
-          const long long hw = (long long)h * W + w;
-          const long long off = b * HW + hw;
-          float2 o = make_float2(v[k2].x * a.scale, v[k2].y * a.scale);
-          if (STORE == ST_C64) {
-            a.out_c[off] = o;
-          } else if (STORE == ST_C64_COLMASK) {
-            const float m = a.colmask[w];
-            a.out_c[off] = make_float2(o.x * m, o.y * m);
-          } else if (STORE == ST_PLANAR) {
-            a.out_p[(b * 2) * HW + hw] = o.x;
-            a.out_p[(b * 2 + 1) * HW + hw] = o.y;
-          } else if (STORE == ST_DC) {
-            const float2 kk = a.k[off];
-            float2 d = kk;
-            if (a.dcmask[w]) {
-              const float2 k0 = a.k0[off];
-              const float wgt = SAN_LDG(a.dcw);
-              d.x = kk.x - (kk.x - k0.x) * wgt;
-              d.y = kk.y - (kk.y - k0.y) * wgt;
+        for (int kb = 0; kb < V2_N2; kb += V2_EPB) {
+          float2 e0[V2_EPB], e1[V2_EPB];
+          if (STORE == ST_DC) {
+#pragma unroll
+            for (int i = 0; i < V2_EPB; ++i) e0[i] = SAN_LDG(a.k + col_off + (long long)(k1 + V2_N1 * (kb + i)) * W);
+            if (dc_on) {
+#pragma unroll
+              for (int i = 0; i < V2_EPB; ++i) e1[i] = SAN_LDG(a.k0 + col_off + (long long)(k1 + V2_N1 * (kb + i)) * W);
             }
-            a.out_c[off] = make_float2(d.x - o.x, d.y - o.y);
           } else if (STORE == ST_REDUCE) {
-            if (a.out_u) a.out_u[off] = o;
-            float2 t = cmulc2(o, a.sens[off]);
-            if (MULTI) {
-              t.x += acc[MULTI ? k2 : 0].x; t.y += acc[MULTI ? k2 : 0].y;
-              acc[MULTI ? k2 : 0] = t;
+#pragma unroll
+            for (int i = 0; i < V2_EPB; ++i) e0[i] = SAN_LDG(a.sens + col_off + (long long)(k1 + V2_N1 * (kb + i)) * W);
+          }
+#pragma unroll
+          for (int i = 0; i < V2_EPB; ++i) {
+            const int k2 = kb + i;
+            const int h = k1 + V2_N1 * k2;
+            const long long hw = (long long)h * W + w;
+            const long long off = b * HW + hw;
+            float2 o = make_float2(v[k2].x * a.scale, v[k2].y * a.scale);
+            if (STORE == ST_C64) {
+              a.out_c[off] = o;
+            } else if (STORE == ST_C64_COLMASK) {
+              a.out_c[off] = make_float2(o.x * cm, o.y * cm);
+            } else if (STORE == ST_PLANAR) {
+              a.out_p[(b * 2) * HW + hw] = o.x;
+              a.out_p[(b * 2 + 1) * HW + hw] = o.y;
+            } else if (STORE == ST_DC) {
+              const float2 kk = e0[i];
+              float2 d = kk;
+              if (dc_on) {
+                const float2 k0 = e1[i];
+                d.x = kk.x - (kk.x - k0.x) * wgt;
+                d.y = kk.y - (kk.y - k0.y) * wgt;
+              }
+              a.out_c[off] = make_float2(d.x - o.x, d.y - o.y);
+            } else if (STORE == ST_REDUCE) {
+              if (a.out_u) a.out_u[off] = o;
+              float2 t = cmulc2(o, e0[i]);
+              if (MULTI) {
+                t.x += acc[MULTI ? k2 : 0].x; t.y += acc[MULTI ? k2 : 0].y;
+                acc[MULTI ? k2 : 0] = t;
+              }
+              if (c + 1 == ncoil) {
+                a.out_p[(g * 2) * HW + hw] = t.x;
+                a.out_p[(g * 2 + 1) * HW + hw] = t.y;
+              }
+            } else if (STORE == ST_RSS) {
+              if (a.out_u) a.out_u[off] = o;
+              float t = o.x * o.x + o.y * o.y;
+              if (MULTI) {
+                t += acc[MULTI ? k2 : 0].x;
+                acc[MULTI ? k2 : 0].x = t;
+              }
+              if (c + 1 == ncoil) a.out_p[g * HW + hw] = sqrtf(t);
             }
-            if (c + 1 == ncoil) {
-              a.out_p[(g * 2) * HW + hw] = t.x;
-              a.out_p[(g * 2 + 1) * HW + hw] = t.y;
-            }
-          } else if (STORE == ST_RSS) {
-            if (a.out_u) a.out_u[off] = o;
-            float t = o.x * o.x + o.y * o.y;
-            if (MULTI) {
-              t += acc[MULTI ? k2 : 0].x;
-              acc[MULTI ? k2 : 0].x = t;
-            }
-            if (c + 1 == ncoil) a.out_p[g * HW + hw] = sqrtf(t);
           }
         }
       }

@@ -72,6 +72,28 @@ __global__ void in_finalize_fwd_kernel(const float* __restrict__ mean, const flo
   b[i] = 0.f;  // out = rstd * (y - mean)
 }
 
+// InstanceNorm statistics from the per-(n, c) sums the conv epilogue accumulated (san_tc_conv_stats): sums[plane*group + k][2]
+// = (sum, sum of squares) of sub-plane k of a plane (group = 4 for the pixel-shuffled transposed conv, whose four
+// sub-planes normalise together; 1 otherwise), P elements per sub-plane.  Same outputs as plane_stats_kernel + finalise.
+__global__ void in_stats_from_sums_kernel(const double* __restrict__ sums, float* __restrict__ mean, float* __restrict__ m2,
+                                          float* __restrict__ a, float* __restrict__ b, int planes, int group, int P, float eps) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= planes) return;
+  double s1 = 0.0, s2 = 0.0;
+  for (int k = 0; k < group; ++k) {
+    s1 += sums[2 * ((long long)i * group + k)];
+    s2 += sums[2 * ((long long)i * group + k) + 1];
+  }
+  const double cnt = (double)group * P;
+  const double mu = s1 / cnt;
+  double M2 = s2 - s1 * mu;
+  if (M2 < 0.0) M2 = 0.0;
+  mean[i] = (float)mu;
+  m2[i] = (float)M2;
+  a[i] = (float)(1.0 / sqrt(M2 / cnt + (double)eps));
+  b[i] = 0.f;
+}
+
 // one thread per channel
 __global__ void bn_finalize_fwd_kernel(const float* __restrict__ mean, const float* __restrict__ m2,
                                        const float* __restrict__ gamma, const float* __restrict__ beta,
@@ -688,6 +710,14 @@ int san_plane_stats_in(const float* x, float* mean, float* m2, float* a, float* 
                        void* stream) {
   SAN_CHECK_ARG(x && mean && m2 && a && b && planes > 0 && P > 0, "san_plane_stats_in: bad args");
   plane_stats_kernel<<<planes, 256, 0, (cudaStream_t)stream>>>(x, mean, m2, P, a, b, eps);
+  SAN_LAUNCH_CHECK();
+  return SAN_OK;
+}
+
+int san_in_stats_from_sums(const double* sums, float* mean, float* m2, float* a, float* b, int planes, int group, int P,
+                           float eps, void* stream) {
+  SAN_CHECK_ARG(sums && mean && m2 && a && b && planes > 0 && group > 0 && P > 0, "san_in_stats_from_sums: bad args");
+  in_stats_from_sums_kernel<<<san_cdiv(planes, 256), 256, 0, (cudaStream_t)stream>>>(sums, mean, m2, a, b, planes, group, P, eps);
   SAN_LAUNCH_CHECK();
   return SAN_OK;
 }

@@ -94,7 +94,8 @@ bool wg_geometry(int H, int W, int Cin, int Cout, int K, WgGeom* g) {
   const int mg = (2 * kga <= 8) ? 8 : 16;
   const int reach_groups = (stacked ? 0 : kga) + mg;  // groups spanned from the A start of a stage
   int best = 0, best_slack = 0;
-  for (int kc = WG_KC_MAX; kc >= 32; kc -= 16) {
+  static const int kc_max = wg_env_int("SAN_WG_KC_MAX", WG_KC_MAX);   // tuning runs
+  for (int kc = kc_max; kc >= 32; kc -= 16) {
     const int a = kga * 2 * kc * 16, b = g->ncp * g->KGn * 2 * (kc + 16) * 16;
     int slack = reach_groups * kc * 16 - (a + b);
     if (slack < 0) slack = 0;

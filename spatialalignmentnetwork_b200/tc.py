@@ -44,6 +44,9 @@ _IN_BWD_FUSED = os.environ.get("SAN_IN_BWD_FUSED", "1") != "0"
 # gradient of the layer and the join BEFORE its backward returns (autograd accumulates dW on the main stream, and the
 # next tcgen05 launch is the producing layer's data gradient).  SAN_WG_OVERLAP=0: everything on one stream.
 _WG_OVERLAP = os.environ.get("SAN_WG_OVERLAP", "1") != "0"
+# InstanceNorm statistics of a conv output from the conv's own epilogue (san_tc_conv_stats); SAN_EPI_STATS=0: the separate
+# san_plane_stats_in pass over the tensor
+_EPI_STATS = os.environ.get("SAN_EPI_STATS", "1") != "0"
 _side = {}
 
 
@@ -126,7 +129,13 @@ class Raw:
             yd = self.y.detach()
             if self.norm == "in":
                 st = torch.empty(4, planes, dtype=torch.float32, device=yd.device)
-                call("plane_stats_in", yd, st[0], st[1], st[2], st[3], planes, P, _IN_EPS)
+                sums = getattr(self.y, "_san_sums", None)
+                if sums is not None:
+                    # the producing conv's epilogue already accumulated the per-plane sums (san_tc_conv_stats)
+                    group = 4 if self.d2s else 1
+                    call("in_stats_from_sums", sums, st[0], st[1], st[2], st[3], planes, group, P // group, _IN_EPS)
+                else:
+                    call("plane_stats_in", yd, st[0], st[1], st[2], st[3], planes, P, _IN_EPS)
             else:
                 bn = self.bn
                 N, C = yd.shape[0], yd.shape[1]
@@ -239,7 +248,8 @@ class _FusedConv(Function):
 
     @staticmethod
     def forward(ctx, w, bias, spec, *tensors):
-        K, metas = spec        # metas[i] = (norm, slope, d2s, mode, accumulate, coef, bn_training)
+        K, metas, stats = spec  # metas[i] = (norm, slope, d2s, mode, accumulate, coef, bn_training, producer info);
+                                # stats: None | [] = holder that receives the epilogue's per-plane sums of the output
         w = w.contiguous()
         Cout, Cin, Kw, _ = w.shape
         assert Kw == K
@@ -267,7 +277,12 @@ class _FusedConv(Function):
         _stage(xs, N, H, W, _pad8(Cin), terms, _FMT_FWD)
         ws = _stage_weights(w, False, H, W, _FMT_FWD)
         out = torch.empty(N, Cout, H, W, dtype=torch.float32, device=w.device)
-        call("tc_conv", xs, ws, bias, out, N, H, W, Cin, Cout, K, 0, 3 * _FMT_FWD, None)
+        if stats is not None and _EPI_STATS and lib().san_tc_conv_stats_supported(H, W, Cin, Cout, K):
+            sums = torch.empty(2 * N * Cout, dtype=torch.float64, device=w.device)
+            call("tc_conv_stats", xs, ws, bias, out, N, H, W, Cin, Cout, K, 0, 3 * _FMT_FWD, None, sums)
+            stats.append(sums)
+        else:
+            call("tc_conv", xs, ws, bias, out, N, H, W, Cin, Cout, K, 0, 3 * _FMT_FWD, None)
         # The staged operand is kept for the backward only while HBM is plentiful (_keep_staged); otherwise
         # the weight gradient re-stages it from the raw tensors, which autograd holds anyway for the
         # normalisation backward.
@@ -282,7 +297,7 @@ class _FusedConv(Function):
     @staticmethod
     @once_differentiable
     def backward(ctx, gy):
-        K, metas, (N, H, W), has_bias, ntens, kept = ctx.meta
+        K, metas, (N, H, W), has_bias, ntens, kept = ctx.meta    # (the forward's `stats` holder is not needed here)
         saved = ctx.saved_tensors
         w = saved[0]
         tensors = saved[1:1 + ntens]
@@ -439,10 +454,12 @@ class _FusedConv(Function):
         return (dw, db, None, *grads)
 
 
-def fused_conv(sources, weight, bias=None, modes=None):
+def fused_conv(sources, weight, bias=None, modes=None, stats=False):
     """sources: list whose items are a ``Raw`` or a list of ``Raw`` (their SUM); the items are
     concatenated along channels.  modes: per-source resampling mode (default: direct; pixel shuffle for a
-    ``d2s`` term; nearest x2 for an ``up`` term).  Returns the raw fp32 conv output tensor."""
+    ``d2s`` term; nearest x2 for an ``up`` term).  stats: the output will be InstanceNorm-normalised by its consumers:
+    the conv epilogue accumulates its per-plane sums, so that no statistics pass re-reads the tensor (``Raw.coef``).
+    Returns the raw fp32 conv output tensor."""
     metas, tensors = [], []
     for i, src in enumerate(sources):
         group = src if isinstance(src, (list, tuple)) else [src]
@@ -462,6 +479,9 @@ def fused_conv(sources, weight, bias=None, modes=None):
             if r.norm == "bn":
                 tensors += [r.bn.weight, r.bn.bias]
     K = weight.shape[-1]
-    out = _FusedConv.apply(weight, bias, (K, metas), *tensors)
+    holder = [] if stats else None
+    out = _FusedConv.apply(weight, bias, (K, metas, holder), *tensors)
     out._san_conv_out = True
+    if holder:
+        out._san_sums = holder[0]
     return out

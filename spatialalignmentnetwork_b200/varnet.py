@@ -117,21 +117,21 @@ class Unet(nn.Module):
         srcs, modes = [R(im) for im in images], None
         stack = []
         for layer in self.down_sample_layers:
-            y1 = tc.fused_conv(srcs, layer.layers[0].weight, modes=modes)
-            y2 = R(tc.fused_conv([R(y1, "in", 0.2)], layer.layers[3].weight), "in", 0.2)
+            y1 = tc.fused_conv(srcs, layer.layers[0].weight, modes=modes, stats=True)
+            y2 = R(tc.fused_conv([R(y1, "in", 0.2)], layer.layers[3].weight, stats=True), "in", 0.2)
             stack.append(y2)
             srcs, modes = [y2], [tc.MODE_POOL]
-        y1 = tc.fused_conv(srcs, self.conv.layers[0].weight, modes=modes)
-        cur = R(tc.fused_conv([R(y1, "in", 0.2)], self.conv.layers[3].weight), "in", 0.2)
+        y1 = tc.fused_conv(srcs, self.conv.layers[0].weight, modes=modes, stats=True)
+        cur = R(tc.fused_conv([R(y1, "in", 0.2)], self.conv.layers[3].weight, stats=True), "in", 0.2)
         out = None
         for transpose_conv, conv in zip(self.up_transpose_conv, self.up_conv):
             skip = stack.pop()
             wt = transpose_conv.layers[0].weight                       # [Cin, Cout, 2, 2]
             w1 = wt.permute(1, 2, 3, 0).reshape(wt.shape[1] * 4, wt.shape[0], 1, 1)
-            y4 = R(tc.fused_conv([cur], w1), "in", 0.2, d2s=True)      # 1x1 conv to 4*Cout; shuffle on read
+            y4 = R(tc.fused_conv([cur], w1, stats=True), "in", 0.2, d2s=True)      # 1x1 conv to 4*Cout; shuffle on read
             block = conv if isinstance(conv, ConvBlock) else conv[0]
-            y1 = tc.fused_conv([y4, skip], block.layers[0].weight)     # cat([up, skip]) (varnet.py:116)
-            cur = R(tc.fused_conv([R(y1, "in", 0.2)], block.layers[3].weight), "in", 0.2)
+            y1 = tc.fused_conv([y4, skip], block.layers[0].weight, stats=True)     # cat([up, skip]) (varnet.py:116)
+            cur = R(tc.fused_conv([R(y1, "in", 0.2)], block.layers[3].weight, stats=True), "in", 0.2)
             if not isinstance(conv, ConvBlock):
                 out = tc.fused_conv([cur], conv[1].weight, conv[1].bias)   # final 1x1 + bias (varnet.py:78)
         return out

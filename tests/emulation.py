@@ -43,7 +43,7 @@ def _term(r, mode):
     return x
 
 
-def fused_conv(sources, weight, bias=None, modes=None):
+def fused_conv(sources, weight, bias=None, modes=None, stats=False):
     cols = []
     for i, src in enumerate(sources):
         group = src if isinstance(src, (list, tuple)) else [src]

@@ -125,6 +125,47 @@ def test_dc_block_backward():
         assert rel_l2(x.grad, y.grad) < 1e-5, name
 
 
+@pytest.mark.parametrize("C", [1, 2])
+def test_dc_block_320(C):
+    """The benchmark size (320 x 320): C = 1 runs the TMA-staged column pass (fft_cols_tma_kernel), C = 2 the register
+    kernels with the coil loop; forward, NaN-in-unsampled-column select, and every gradient vs torch complex128
+    (reference varnet.py:508-512, 525-530)."""
+    ops = _ops()
+    torch.manual_seed(11)
+    N, H, W = 2, 320, 320
+    k, k0, S = crandn(N, C, H, W), crandn(N, C, H, W), crandn(N, C, H, W)
+    xp = torch.randn(N, 2, H, W)
+    m = torch.rand(W) > 0.6
+    m[:8] = False                       # one whole column tile without a sampled column (k0 tile not fetched)
+    w = torch.tensor([0.7])
+    G = crandn(N, C, H, W)
+
+    def ref(k, S, xp, w, k0):
+        x = torch.complex(xp[:, :1], xp[:, 1:])
+        soft = torch.where(m, k - k0, torch.zeros(1, 1, 1, 1, dtype=k.dtype)) * w
+        out = k - soft - torch.fft.fft2(x * S, norm="ortho")
+        red = (torch.fft.ifft2(k, norm="ortho") * S.conj()).sum(1, keepdim=True)
+        return out, red
+
+    a = [t.clone().double().requires_grad_(True) if not t.is_complex() else t.clone().to(torch.complex128).requires_grad_(True)
+         for t in (k, S, xp, w, k0)]
+    out, red = ref(*a)
+    ((out * G.to(torch.complex128).conj()).real.sum() + (red.real * 0.3 + red.imag * 0.7).sum()).backward()
+    b = [t.clone().cuda().requires_grad_(True) for t in (k, S, xp, w, k0)]
+    out_c = ops.FftExpandDC.apply(b[2], b[1], b[0], b[4], m.cuda(), b[3])
+    red_c = ops.FftReduce.apply(b[0], b[1])
+    assert rel_l2(out_c, out) < 3e-6
+    assert rel_l2(torch.complex(red_c[:, :1], red_c[:, 1:]), red) < 3e-6
+    ((out_c * G.cuda().conj()).real.sum() + (red_c[:, 0] * 0.3 + red_c[:, 1] * 0.7).sum()).backward()
+    for name, x, y in zip(("k", "S", "x", "dc_weight", "k0"), b, a):
+        assert rel_l2(x.grad, y.grad) < 1e-5, name
+    k0n = k0.clone()
+    k0n[..., ~m] = complex(float("nan"), float("nan"))
+    with torch.no_grad():
+        out2 = ops.FftExpandDC.apply(b[2], b[1], b[0], k0n.cuda(), m.cuda(), b[3])
+    assert torch.equal(out2, out_c)
+
+
 def test_fft_rss_and_sens_normalize():
     ops = _ops()
     torch.manual_seed(4)

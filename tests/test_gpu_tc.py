@@ -119,6 +119,51 @@ def test_tc_conv_fwd_and_dgrad(case):
     assert rel_l2(dx, xr.grad) < 2e-5
 
 
+STATS_CASES = [
+    # N, Cin, H, W, Cout, K, bias, group   (group 4 = the pixel-shuffled transposed-conv output, four sub-planes per plane)
+    (3, 18, 64, 64, 18, 3, False, 1), (2, 3, 32, 48, 18, 3, False, 1), (2, 36, 40, 24, 36, 3, False, 1),
+    (2, 144, 20, 20, 288, 3, False, 1), (2, 288, 10, 12, 576, 1, False, 4), (5, 72, 20, 20, 144, 3, True, 1),
+    (2, 18, 320, 320, 18, 3, False, 1), (70, 18, 32, 32, 36, 3, False, 1),
+]
+
+
+@pytest.mark.parametrize("case", STATS_CASES)
+def test_tc_conv_statistics_epilogue(case):
+    """san_tc_conv_stats + san_in_stats_from_sums = san_plane_stats_in of the conv output (InstanceNorm2d statistics,
+    reference varnet.py:141,178), and the conv output itself is unchanged by the statistics epilogue."""
+    N, Cin, H, W, Cout, K, has_bias, group = case
+    L = _lib()
+    assert L.lib().san_tc_conv_stats_supported(H, W, Cin, Cout, K)
+    torch.manual_seed(5)
+    x = torch.randn(N, Cin, H, W, device="cuda") + 0.3
+    w = (torch.randn(Cout, Cin, K, K) / math.sqrt(Cin * K * K)).cuda()
+    b = torch.randn(Cout, device="cuda") if has_bias else None
+    xs = stage(x, F16)
+    ws = torch.empty(L.lib().san_tc_staged_weight_elems(H, W, Cout, Cin, K), dtype=torch.bfloat16, device="cuda")
+    L.call("tc_stage_weights", w, ws, H, W, Cout, Cin, K, 0, F16)
+    y0 = torch.empty(N, Cout, H, W, device="cuda")
+    L.call("tc_conv", xs, ws, b, y0, N, H, W, Cin, Cout, K, 0, 3, None)
+    y1 = torch.empty_like(y0)
+    sums = torch.full((2 * N * Cout,), 7.0, device="cuda", dtype=torch.float64)        # the call zeroes it
+    L.call("tc_conv_stats", xs, ws, b, y1, N, H, W, Cin, Cout, K, 0, 3, None, sums)
+    assert torch.equal(y0, y1)
+    planes, P = N * Cout // group, H * W
+    st = torch.empty(4, planes, device="cuda")
+    L.call("in_stats_from_sums", sums, st[0], st[1], st[2], st[3], planes, group, P, 1e-5)
+    ref = torch.empty(4, planes, device="cuda")
+    L.call("plane_stats_in", y1, ref[0], ref[1], ref[2], ref[3], planes, group * P, 1e-5)
+    yd = y1.double().view(planes, -1)
+    mean64, var64 = yd.mean(1), yd.var(1, unbiased=False)
+    rstd64 = 1.0 / torch.sqrt(var64 + 1e-5)
+    # against fp64 and against the separate statistics pass: mean to 1e-6 of the plane's scale, rstd to 2e-6 relative
+    scale = torch.sqrt(var64 + mean64 ** 2)
+    assert ((st[0].double() - mean64).abs() / scale).max() < 2e-6
+    assert ((st[2].double() - rstd64).abs() / rstd64).max() < 4e-6, ((st[2].double() - rstd64).abs() / rstd64).max()
+    assert ((st[2] - ref[2]).abs() / ref[2]).max() < 4e-6
+    assert ((st[1].double() - var64 * group * P).abs() / (var64 * group * P + 1e-30)).max() < 1e-5
+    assert float(st[3].abs().max()) == 0.0
+
+
 def test_tc_stage_roundtrip_and_fused_sources():
     """Staging = concat [InstanceNorm+LReLU(0.2) of a pixel-shuffled source, avg-pooled activated source,
     identity source] with zero border / zero pad channels; un-staging returns hi + lo."""
