@@ -851,7 +851,8 @@ int san_in_bwd_fused_map(const float* g, int Ctot, int c0, int mode, const float
   // threads per plane: a quarter of the float4 groups, 128 .. 1024 (big planes: one 1024-thread CTA per SM keeps the
   // live planes of all SMs near the L2 capacity)
   int nt = ((P / 16) + 31) / 32 * 32;
-  nt = nt < 128 ? 128 : (nt > 1024 ? 1024 : nt);
+  static const int nt_max = [] { const char* e = getenv("SAN_IN_BWD_NT"); const int v = e ? atoi(e) : 1024; return v < 128 ? 128 : (v > 1024 ? 1024 : v / 32 * 32); }();
+  nt = nt < 128 ? 128 : (nt > nt_max ? nt_max : nt);
   switch (mode) {
     case 0: in_bwd_fused_map_kernel<0><<<planes, nt, 0, st>>>(m, y, mu, a, slope, dy, P, am); break;
     case 1: in_bwd_fused_map_kernel<1><<<planes, nt, 0, st>>>(m, y, mu, a, slope, dy, P, am); break;

@@ -56,4 +56,7 @@ class AdamW(torch.optim.Optimizer):
                 call("adamw_step", *[ctypes.addressof(a) for a in ptrs], ctypes.addressof(numel), n,
                      float(group["lr"]), float(group["betas"][0]), float(group["betas"][1]), float(group["eps"]),
                      float(group["weight_decay"]), step, step_dev, sched_dev)
+                # the kernel wrote through raw pointers: tell autograd (and the staged-weight cache of tc.py, which keys on
+                # the version counter) that the parameters changed
+                torch.autograd.graph.increment_version(ps)
         return loss

@@ -153,6 +153,7 @@ def broadcast_state(modules, src=0, group=None):
     for m in modules:
         for t in list(m.parameters()) + list(m.buffers()):
             dist.broadcast(t.data, src=src, group=group)
+            torch.autograd.graph.increment_version(t)     # written through .data: caches keyed on the version must see it
 
 
 def average_buffers(model, group=None):

@@ -44,6 +44,7 @@ _IN_BWD_FUSED = os.environ.get("SAN_IN_BWD_FUSED", "1") != "0"
 # gradient of the layer and the join BEFORE its backward returns (autograd accumulates dW on the main stream, and the
 # next tcgen05 launch is the producing layer's data gradient).  SAN_WG_OVERLAP=0: everything on one stream.
 _WG_OVERLAP = os.environ.get("SAN_WG_OVERLAP", "1") != "0"
+_WG_PRESTAGE = os.environ.get("SAN_WG_PRESTAGE", "1") != "0"      # 0: the producing layer stages its dY itself (A/B runs)
 # InstanceNorm statistics of a conv output from the conv's own epilogue (san_tc_conv_stats); SAN_EPI_STATS=0: the separate
 # san_plane_stats_in pass over the tensor
 _EPI_STATS = os.environ.get("SAN_EPI_STATS", "1") != "0"
@@ -178,13 +179,91 @@ def _stage(xs, N, H, W, Cpad, terms, fmt, absmax=None):
     call("tc_stage_terms", xs, N, H, W, Cpad, ctypes.addressof(arr), len(terms), fmt, absmax)
 
 
-def _stage_weights(w, dgrad, H, W, fmt):
+def _stage_weights_now(w, ws, dgrad, H, W, fmt):
+    Cout, Cin, K, _ = w.shape
+    call("tc_stage_weights", w, ws, H, W, Cout, Cin, K, int(dgrad), fmt)
+
+
+def _alloc_staged_weights(w, dgrad, H, W):
     Cout, Cin, K, _ = w.shape
     n = lib().san_tc_staged_weight_elems(H, W, Cin if dgrad else Cout, Cout if dgrad else Cin, K)
     assert n > 0, f"tcgen05 conv: unsupported shape H={H} W={W} {tuple(w.shape)}"
-    ws = torch.empty(n, dtype=torch.bfloat16, device=w.device)
-    call("tc_stage_weights", w, ws, H, W, Cout, Cin, K, int(dgrad), fmt)
-    return ws
+    return torch.empty(n, dtype=torch.bfloat16, device=w.device)
+
+
+# Staged weights of nn.Parameters are CACHED per (parameter, forward / data-gradient form, image size, pair format) and
+# keyed on the parameter's version counter (bumped by every in-place update: torch's optimisers, load_state_dict, and
+# optim.AdamW / parallel.attach of this package call torch.autograd.graph.increment_version).  A training step changes
+# every weight once, so it re-stages every weight once either way - but not as 650 tiny launches in the dependency chain
+# of the convolutions: the first stale weight a step meets re-stages ALL stale entries on the side stream, in the order
+# the step will use them, while the main stream goes on; a consumer waits on the event of its batch of 24.  Evaluation
+# (weights fixed) stages nothing at all.  Non-parameter weights (the reshaped ConvTranspose2d filter, spectrally
+# normalised GAN weights) and CUDA-graph captures keep the inline launch.  SAN_WS_CACHE=0 disables the cache.
+_WS_CACHE = os.environ.get("SAN_WS_CACHE", "1") != "0"
+_ws_entries = {}
+
+
+class _WsEntry:
+    __slots__ = ("wref", "shape", "dgrad", "H", "W", "fmt", "ws", "version", "event")
+
+
+def invalidate_weight_cache():
+    """Forget every cached staged weight (after mutating parameters behind autograd's back, e.g. through ``.data``)."""
+    _ws_entries.clear()
+
+
+def _restage_stale(device):
+    main, side = torch.cuda.current_stream(), _side_stream(device)
+    side.wait_stream(main)              # after every kernel that still reads the old staged weights / writes the new values
+    dead, batch = [], []
+    with torch.cuda.stream(side):
+        for key, e in _ws_entries.items():
+            w = e.wref()
+            if w is None:
+                dead.append(key)
+                continue
+            if e.version == w._version or w.device != device:
+                continue
+            _stage_weights_now(w, e.ws, e.dgrad, e.H, e.W, e.fmt)
+            e.version = w._version
+            batch.append(e)
+            if len(batch) == 24:
+                ev = torch.cuda.Event()
+                ev.record(side)
+                for b in batch:
+                    b.event = ev
+                batch = []
+        if batch:
+            ev = torch.cuda.Event()
+            ev.record(side)
+            for b in batch:
+                b.event = ev
+    for key in dead:
+        del _ws_entries[key]
+
+
+def _stage_weights(w, dgrad, H, W, fmt):
+    import weakref
+    if not (_WS_CACHE and isinstance(w, torch.nn.Parameter)) or torch.cuda.is_current_stream_capturing():
+        ws = _alloc_staged_weights(w, dgrad, H, W)
+        _stage_weights_now(w, ws, dgrad, H, W, fmt)
+        return ws
+    key = (id(w), bool(dgrad), H, W, fmt)
+    e = _ws_entries.get(key)
+    if e is None or e.wref() is not w or e.shape != tuple(w.shape):
+        e = _WsEntry()
+        e.wref, e.shape, e.dgrad, e.H, e.W, e.fmt = weakref.ref(w), tuple(w.shape), bool(dgrad), H, W, fmt
+        e.ws = _alloc_staged_weights(w, dgrad, H, W)
+        _stage_weights_now(w, e.ws, dgrad, H, W, fmt)
+        e.version, e.event = w._version, None
+        _ws_entries[key] = e
+        return e.ws
+    if e.version != w._version:
+        _restage_stale(w.device)
+    if e.event is not None:
+        torch.cuda.current_stream().wait_event(e.event)
+        e.event = None
+    return e.ws
 
 
 def _pad8(c):
@@ -223,7 +302,7 @@ def _prestage(dy, t):
     """``dy`` = the gradient this layer's backward just wrote for a conv output with a single consumer: it IS the ``gy`` of
     the producing conv's backward, so it is staged here - inside the window in which this layer's weight-gradient GEMM runs
     on the side stream - and rides on the tensor object like the absmax tag."""
-    if not (_WG_OVERLAP and t["prestage"] and _FMT_BWD == FMT_F16):
+    if not (_WG_OVERLAP and _WG_PRESTAGE and t["prestage"] and _FMT_BWD == FMT_F16):
         return
     tag = getattr(dy, "_san_absmax", None)
     if tag is None:
