@@ -52,17 +52,19 @@ _side = {}
 
 
 def _side_stream(device):
+    """The side stream that belongs to the CURRENT stream (one per sub-batch chain of varnet.VarNet._forward_streams)."""
     idx = device.index if device.index is not None else torch.cuda.current_device()
-    if idx not in _side:
-        _side[idx] = torch.cuda.Stream(device=idx)
-    return _side[idx]
+    key = (idx, torch.cuda.current_stream(idx).cuda_stream)
+    if key not in _side:
+        _side[key] = torch.cuda.Stream(device=idx)
+    return _side[key]
 
 
 # Staged operands are as large as the activations they come from.  They are re-created in the backward
 # pass (for the weight gradient) unless HBM is plentiful: while live tensors take less than
 # this fraction of the device memory, the forward keeps them (a B200 has 180 GB; the benchmark step
 # needs 65 GB without them).
-KEEP_STAGED_BELOW = 0.55
+KEEP_STAGED_BELOW = float(os.environ.get("SAN_KEEP_STAGED_BELOW", "0.55"))
 _total_mem = {}
 
 
@@ -255,14 +257,15 @@ def _stage_weights(w, dgrad, H, W, fmt):
         e.wref, e.shape, e.dgrad, e.H, e.W, e.fmt = weakref.ref(w), tuple(w.shape), bool(dgrad), H, W, fmt
         e.ws = _alloc_staged_weights(w, dgrad, H, W)
         _stage_weights_now(w, e.ws, dgrad, H, W, fmt)
-        e.version, e.event = w._version, None
+        e.version = w._version
+        e.event = torch.cuda.Event()        # other streams (sub-batch chains) wait for this first staging too
+        e.event.record()
         _ws_entries[key] = e
         return e.ws
     if e.version != w._version:
         _restage_stale(w.device)
-    if e.event is not None:
+    if e.event is not None:             # (kept: every stream that uses the entry waits for the sweep that staged it)
         torch.cuda.current_stream().wait_event(e.event)
-        e.event = None
     return e.ws
 
 

@@ -340,6 +340,35 @@ class VarNet(nn.Module):
         self.checkpoint_cascades = False  # recompute each cascade in backward (memory knob, not in the reference)
 
     def forward(self, masked_kspace, mask, ref, num_low_frequencies):
+        ns = N_STREAMS
+        if ns > 1 and masked_kspace.is_cuda and masked_kspace.shape[0] >= MIN_SLICES_PER_STREAM * ns:
+            return self._forward_streams(masked_kspace, mask, ref, num_low_frequencies, ns)
+        return self._forward_one(masked_kspace, mask, ref, num_low_frequencies)
+
+    def _forward_streams(self, masked_kspace, mask, ref, num_low_frequencies, ns):
+        """The batch as ``ns`` independent sub-batches, each on its own CUDA stream (every operation of the network is
+        per-sample - InstanceNorm, the NormUnet normalisation, the FFTs -, so the result is the un-split one; the weight
+        gradients of the sub-batches are summed by autograd).  Why: a step is a strict chain of kernels that alternate
+        between tensor / shared-memory-bound convolutions (HBM 30-40 % busy) and HBM-bound element-wise passes (staging,
+        statistics, normalisation backward).  Two chains give the GPU a convolution of one sub-batch to run next to the
+        element-wise kernels of the other (two tcgen05 kernels never co-reside: the hardware serialises those).  The backward
+        follows by itself: autograd runs every backward node on the stream of its forward node."""
+        main = torch.cuda.current_stream()
+        streams = _sub_streams(masked_kspace.device, ns)
+        ks = masked_kspace.chunk(ns)
+        rs = ref.chunk(ns) if ref is not None else [None] * len(ks)
+        outs = []
+        for st, k, r in zip(streams, ks, rs):
+            st.wait_stream(main)
+            mask.record_stream(st)          # a temporary of the caller, read on st until the backward has run
+            with torch.cuda.stream(st):
+                outs.append(self._forward_one(k, mask, r, num_low_frequencies))
+        for st, o in zip(streams, outs):
+            main.wait_stream(st)
+            o.record_stream(main)           # allocated on st, read by the concatenation on main
+        return torch.cat(outs, 0)
+
+    def _forward_one(self, masked_kspace, mask, ref, num_low_frequencies):
         sens_maps = self.sens_net(masked_kspace, num_low_frequencies)
         kspace_pred = masked_kspace
         ref_normed = None
@@ -354,3 +383,21 @@ class VarNet(nn.Module):
             else:
                 kspace_pred = cascade(kspace_pred, masked_kspace, mask, sens_maps, ref, ref_normed)
         return ops.FftRss.apply(kspace_pred)
+
+
+# Sub-batch streams of VarNet.forward (SAN_VARNET_STREAMS; default 1 = one chain on the current stream).  Measured on the
+# B200 at bs 64 (profiles/r2t_*, r2u_*): 2 chains 390.9 ms/step against 369.1 eagerly (two chains double the launches and
+# the host, at ~30 us per launch, no longer runs ahead of the GPU) and 386.3 against 371.3 even as ONE CUDA graph, 4 chains
+# 420.3: the persistent conv CTAs (576 threads, 50 K registers per SM) leave the element-wise kernels of the other chain
+# too little of each SM for the overlap to pay for the halved kernels.  Kept as an opt-in.
+N_STREAMS = int(os.environ.get("SAN_VARNET_STREAMS", "1"))
+MIN_SLICES_PER_STREAM = 4
+_streams = {}
+
+
+def _sub_streams(device, ns):
+    idx = device.index if device.index is not None else torch.cuda.current_device()
+    have = _streams.setdefault(idx, [])
+    while len(have) < ns:
+        have.append(torch.cuda.Stream(device=idx))
+    return have[:ns]
