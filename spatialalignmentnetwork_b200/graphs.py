@@ -40,6 +40,8 @@ class GraphedUpdate:
             self.loss_sim = getattr(net, "loss_sim", None)     # static tensors: hold the replay's values
             self.loss_smooth = getattr(net, "loss_smooth", None)
         self.launches_per_step = _lib.launch_count() - n0     # kernels of this library inside one replay
+        self._params = [p for n in ("net_T", "net_R", "net_G", "net_D", "net_mask") if getattr(net, n, None) is not None
+                        for p in getattr(net, n).parameters()]
 
     def _step(self):
         self.net.set_input(self.img_full, self.img_aux)
@@ -49,5 +51,12 @@ class GraphedUpdate:
         """One training step on a new batch (same shapes): copy into the static buffers, replay."""
         self.img_full.copy_(img_full, non_blocking=True)
         self.img_aux.copy_(img_aux, non_blocking=True)
-        self.graph.replay()
+        self.replay()
         return self.loss_sim
+
+    def replay(self):
+        """One step on whatever the static input buffers hold.  The replayed optimiser kernels change the parameters
+        without autograd noticing: bump their version counters, so that eager code running afterwards (validation, the
+        staged-weight cache of tc.py) does not mistake them for unchanged."""
+        self.graph.replay()
+        torch.autograd.graph.increment_version(self._params)

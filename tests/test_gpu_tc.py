@@ -164,6 +164,49 @@ def test_tc_conv_statistics_epilogue(case):
     assert float(st[3].abs().max()) == 0.0
 
 
+def test_staged_weight_cache_follows_updates():
+    """tc._stage_weights caches the staged form of an nn.Parameter on its version counter: in-place torch updates, the
+    library's AdamW (raw-pointer kernel + increment_version) and ``.data`` writes followed by invalidate_weight_cache()
+    must all be seen; unchanged weights are not staged again."""
+    tc = tc_mod()
+    from spatialalignmentnetwork_b200 import optim
+    L = _lib()
+    torch.manual_seed(9)
+    w = torch.nn.Parameter((torch.randn(18, 18, 3, 3) / math.sqrt(162)).cuda())
+    x = torch.randn(2, 18, 32, 32, device="cuda")
+
+    def check():
+        y = tc.fused_conv([tc.Raw(x)], w)
+        assert rel_l2(y, F.conv2d(x.double(), w.detach().double(), padding=1)) < 5e-6
+        return y
+
+    check()
+    n0 = L.launch_count()
+    with torch.no_grad():
+        tc.fused_conv([tc.Raw(x)], w)
+    n_cached = L.launch_count() - n0
+    with torch.no_grad():
+        w.mul_(0.5)                      # in-place torch op: version bump
+    n0 = L.launch_count()
+    with torch.no_grad():
+        tc.fused_conv([tc.Raw(x)], w)
+    assert L.launch_count() - n0 == n_cached + 1      # exactly one more launch: the re-staging of the changed weight
+    check()
+    opt = optim.AdamW([w], lr=0.05, weight_decay=0.0)
+    for _ in range(2):                   # backward uses the cached data-gradient form as well (x needs no gradient here)
+        opt.zero_grad()
+        xr = x.clone().requires_grad_(True)
+        y = tc.fused_conv([tc.Raw(xr)], w)
+        (y * y).sum().backward()
+        g_ref = torch.autograd.grad((F.conv2d(xr.double(), w.detach().double(), padding=1) ** 2).sum(), xr)[0]
+        assert rel_l2(xr.grad, g_ref) < 1e-5
+        opt.step()
+        check()
+    w.data.mul_(2.0)                     # behind autograd's back
+    tc.invalidate_weight_cache()
+    check()
+
+
 def test_tc_stage_roundtrip_and_fused_sources():
     """Staging = concat [InstanceNorm+LReLU(0.2) of a pixel-shuffled source, avg-pooled activated source,
     identity source] with zero border / zero pad channels; un-staging returns hi + lo."""

@@ -42,6 +42,10 @@ def main():
                             None, None, None, None, 1.0, 0, 0, None, None, None, None, 1.0, 0, 0, 1)
         L.call("tc_stage_weights", w, ws, HW, HW, Cout, Cin, K, 0, 1)
         cv = lambda: L.call("tc_conv", xs, ws, None, y, N, HW, HW, Cin, Cout, K, 0, 3, None)  # fp16 pairs, as the forward runs
+        t_cs = float("nan")
+        if L.lib().san_tc_conv_stats_supported(HW, HW, Cin, Cout, K):      # the same conv with the statistics epilogue
+            sums = torch.empty(2 * N * Cout, dtype=torch.float64, device="cuda")
+            t_cs = timeit(lambda: L.call("tc_conv_stats", xs, ws, None, y, N, HW, HW, Cin, Cout, K, 0, 3, None, sums))
         wp = ops._pack(w, False)
         y2 = torch.empty_like(y)
         fp = lambda: L.call("conv2d_fwd", x, wp, None, y2, N, Cin, HW, HW, Cout, K, 0, 0)
@@ -56,7 +60,7 @@ def main():
         fl = 2.0 * N * Cout * HW * HW * Cin * K * K
         err = ((y - y2).norm() / y2.norm()).item()
         print(f"{Cin:4d} {Cout:4d} {HW:4d} {K} | {t_st:7.3f} | {t_cv:7.3f} ({fl / t_cv / 1e9:6.1f}) | {t_fp:7.3f} ({fl / t_fp / 1e9:6.1f}) | "
-              f"{t_fp / t_cv:5.2f}x  err {err:.1e} | wgrad {t_wg:7.3f} ms ({fl / t_wg / 1e9:6.1f} TF/s)")
+              f"{t_fp / t_cv:5.2f}x  err {err:.1e} | wgrad {t_wg:7.3f} ms ({fl / t_wg / 1e9:6.1f} TF/s) | conv+stats {t_cs:7.3f} ms")
         del x, xs, y, y2, gy, gys
 
 
