@@ -10,6 +10,8 @@
 // large mean/std ratio costs no precision, like PyTorch's (x - mean) * rstd) with the
 // coefficients produced by tiny finalize kernels from two-pass plane statistics, so a
 // conv output is read twice (stats; L2-resident second pass) and written once.
+#include <cooperative_groups.h>
+
 #include "san_common.cuh"
 #include "../../include/san_b200.h"
 
@@ -473,22 +475,31 @@ __device__ __forceinline__ void fused_load4(const GMap& m, const float* __restri
   }
 }
 
-template <int MODE>
-__global__ void __launch_bounds__(1024) in_bwd_fused_map_kernel(const GMap m, const float* __restrict__ y,
-                                                                const float* __restrict__ mu, const float* __restrict__ a,
-                                                                float slope, float* __restrict__ dy, int P,
-                                                                unsigned int* __restrict__ absmax) {
+// CLUSTER: the plane is split over the two CTAs of a thread-block cluster, which exchange their partial sums through
+// distributed shared memory.  At 320 x 320 a plane with its gradient is 820 KB: one 1024-thread CTA per SM keeps 148 planes
+// = 121 MB live, right at the L2 capacity, and half of the second pass came from HBM again (ncu: 1.47 GB read for 0.94 GB
+// algorithmic); two CTAs per plane halve the live set (74 planes = 61 MB).
+template <int MODE, bool CLUSTER>
+__device__ __forceinline__ void in_bwd_fused_map_body(const GMap& m, const float* __restrict__ y, const float* __restrict__ mu,
+                                                      const float* __restrict__ a, float slope, float* __restrict__ dy, int P,
+                                                      unsigned int* __restrict__ absmax) {
   __shared__ double red[32];
+  __shared__ double part[2];
   __shared__ float coef[3];
-  const long long base = (long long)blockIdx.x * P;
-  const float* gp = gmap_plane<MODE>(m, blockIdx.x);
+  const int plane = CLUSTER ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+  const int rank = CLUSTER ? (int)(blockIdx.x & 1) : 0;
+  const long long base = (long long)plane * P;
+  const float* gp = gmap_plane<MODE>(m, plane);
   const float* yb = y + base;
-  const float cm = mu[blockIdx.x], ca = a[blockIdx.x];
+  const float cm = mu[plane], ca = a[plane];
   const bool vec = (P & 3) == 0 && (m.Wy & 3) == 0;
   const int n4 = P >> 2;
+  // this CTA's share of the plane: float4 groups [q0, q1) (vector path) or elements [e0, e1)
+  const int q0 = CLUSTER ? (int)((long long)n4 * rank / 2) : 0, q1 = CLUSTER ? (int)((long long)n4 * (rank + 1) / 2) : n4;
+  const int e0 = CLUSTER ? (int)((long long)P * rank / 2) : 0, e1 = CLUSTER ? (int)((long long)P * (rank + 1) / 2) : P;
   float t1 = 0.f, t2 = 0.f;
   if (vec) {
-    for (int i = threadIdx.x; i < n4; i += blockDim.x) {
+    for (int i = q0 + threadIdx.x; i < q1; i += blockDim.x) {
       float yv[4], gv[4];
       fused_load4<MODE>(m, yb, gp, i, yv, gv);
 #pragma unroll
@@ -501,7 +512,7 @@ __global__ void __launch_bounds__(1024) in_bwd_fused_map_kernel(const GMap m, co
       }
     }
   } else {
-    for (int i = threadIdx.x; i < P; i += blockDim.x) {
+    for (int i = e0 + threadIdx.x; i < e1; i += blockDim.x) {
       const float yc = __ldg(yb + i) - cm;
       float gg = gmap_load<MODE>(gp, i, m.Hy, m.Wy);
       if (ca * yc <= 0.f) gg *= slope;
@@ -509,8 +520,22 @@ __global__ void __launch_bounds__(1024) in_bwd_fused_map_kernel(const GMap m, co
       t2 += gg * (ca * yc);
     }
   }
-  const double r1 = block_sum_d((double)t1, red);
-  const double r2 = block_sum_d((double)t2, red);
+  double r1 = block_sum_d((double)t1, red);
+  double r2 = block_sum_d((double)t2, red);
+  if (CLUSTER) {
+    namespace cg = cooperative_groups;
+    cg::cluster_group cluster = cg::this_cluster();
+    if (threadIdx.x == 0) { part[0] = r1; part[1] = r2; }
+    cluster.sync();
+    if (threadIdx.x == 0) {
+      const double* peer = cluster.map_shared_rank(part, rank ^ 1);
+      const double p1 = peer[0], p2 = peer[1];
+      // rank 0's partial first in both CTAs: the two halves form bit-identical coefficients
+      r1 = rank == 0 ? r1 + p1 : p1 + r1;
+      r2 = rank == 0 ? r2 + p2 : p2 + r2;
+    }
+    cluster.sync();                 // the peer has read `part` before this CTA may exit
+  }
   if (threadIdx.x == 0) {           // in_finalize_bwd: dy = p g' + q (y - mu) + r
     const double A = ca, M = P;
     coef[0] = (float)A;
@@ -522,8 +547,8 @@ __global__ void __launch_bounds__(1024) in_bwd_fused_map_kernel(const GMap m, co
   float am = 0.f;
   if (vec) {
     float4* d4 = (float4*)(dy + base);
-    for (int k0 = threadIdx.x; k0 < n4; k0 += blockDim.x) {
-      const int i = n4 - 1 - k0;      // reverse: what the first pass read last is still in L2
+    for (int k0 = threadIdx.x; k0 < q1 - q0; k0 += blockDim.x) {
+      const int i = q1 - 1 - k0;      // reverse: what the first pass read last is still in L2
       float yv[4], gv[4];
       fused_load4<MODE>(m, yb, gp, i, yv, gv);
 #pragma unroll
@@ -537,8 +562,8 @@ __global__ void __launch_bounds__(1024) in_bwd_fused_map_kernel(const GMap m, co
       d4[i] = make_float4(yv[0], yv[1], yv[2], yv[3]);
     }
   } else {
-    for (int k0 = threadIdx.x; k0 < P; k0 += blockDim.x) {
-      const int i = P - 1 - k0;
+    for (int k0 = threadIdx.x; k0 < e1 - e0; k0 += blockDim.x) {
+      const int i = e1 - 1 - k0;
       const float yc = __ldg(yb + i) - cm;
       float gg = gmap_load<MODE>(gp, i, m.Hy, m.Wy);
       if (ca * yc <= 0.f) gg *= slope;
@@ -552,6 +577,21 @@ __global__ void __launch_bounds__(1024) in_bwd_fused_map_kernel(const GMap m, co
     for (int o = 16; o > 0; o >>= 1) am = fmaxf(am, __shfl_xor_sync(0xffffffffu, am, o));
     if ((threadIdx.x & 31) == 0 && am < 3.0e38f) atomicMax(absmax, __float_as_uint(am));
   }
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(1024) in_bwd_fused_map_kernel(const GMap m, const float* __restrict__ y,
+                                                                const float* __restrict__ mu, const float* __restrict__ a,
+                                                                float slope, float* __restrict__ dy, int P,
+                                                                unsigned int* __restrict__ absmax) {
+  in_bwd_fused_map_body<MODE, false>(m, y, mu, a, slope, dy, P, absmax);
+}
+template <int MODE>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(1024)
+in_bwd_fused_map_cl2_kernel(const GMap m, const float* __restrict__ y, const float* __restrict__ mu,
+                            const float* __restrict__ a, float slope, float* __restrict__ dy, int P,
+                            unsigned int* __restrict__ absmax) {
+  in_bwd_fused_map_body<MODE, true>(m, y, mu, a, slope, dy, P, absmax);
 }
 
 // dx = rstd * (g' - mean(g') - xhat * mean(g' xhat)), xhat = rstd*(y - mu)  ->  dy = p g' + q (y - mu) + r
@@ -853,6 +893,18 @@ int san_in_bwd_fused_map(const float* g, int Ctot, int c0, int mode, const float
   int nt = ((P / 16) + 31) / 32 * 32;
   static const int nt_max = [] { const char* e = getenv("SAN_IN_BWD_NT"); const int v = e ? atoi(e) : 1024; return v < 128 ? 128 : (v > 1024 ? 1024 : v / 32 * 32); }();
   nt = nt < 128 ? 128 : (nt > nt_max ? nt_max : nt);
+  // planes too large for 148 of them (+ their gradients) to stay in L2: two CTAs of a cluster per plane (SAN_IN_BWD_CL2=0: off)
+  static const int cl2_env = [] { const char* e = getenv("SAN_IN_BWD_CL2"); return e ? atoi(e) : 1; }();
+  if (cl2_env && (long long)P * 8 * san_num_sms() > 100ll * 1024 * 1024) {
+    switch (mode) {
+      case 0: in_bwd_fused_map_cl2_kernel<0><<<2 * planes, nt, 0, st>>>(m, y, mu, a, slope, dy, P, am); break;
+      case 1: in_bwd_fused_map_cl2_kernel<1><<<2 * planes, nt, 0, st>>>(m, y, mu, a, slope, dy, P, am); break;
+      case 2: in_bwd_fused_map_cl2_kernel<2><<<2 * planes, nt, 0, st>>>(m, y, mu, a, slope, dy, P, am); break;
+      default: in_bwd_fused_map_cl2_kernel<3><<<2 * planes, nt, 0, st>>>(m, y, mu, a, slope, dy, P, am); break;
+    }
+    SAN_LAUNCH_CHECK();
+    return SAN_OK;
+  }
   switch (mode) {
     case 0: in_bwd_fused_map_kernel<0><<<planes, nt, 0, st>>>(m, y, mu, a, slope, dy, P, am); break;
     case 1: in_bwd_fused_map_kernel<1><<<planes, nt, 0, st>>>(m, y, mu, a, slope, dy, P, am); break;

@@ -302,6 +302,18 @@ def test_optional_registration_terms():
     assert {"loss_lncc", "loss_mi"} <= set(net.get_vis("scalars")["scalars"])
 
 
+def test_host_prefetcher_order_and_overlap_stream():
+    """prefetch.HostPrefetcher hands out the batches in order, as device tensors usable on the current stream, and stops
+    with the iterable (the input pipeline of bench.py's end-to-end leg; reference train.py:150-165, 207)."""
+    from spatialalignmentnetwork_b200.prefetch import HostPrefetcher
+    batches = [(torch.full((4, 8), float(i)).pin_memory(), torch.full((2,), float(-i)).pin_memory()) for i in range(5)]
+    got = []
+    for a, b in HostPrefetcher(batches, "cuda", depth=2):
+        assert a.is_cuda and b.is_cuda
+        got.append((a.sum().item() / 32, b.sum().item() / 2))
+    assert got == [(float(i), float(-i)) for i in range(5)]
+
+
 def test_graphed_update_matches_eager():
     """graphs.GraphedUpdate: set_input + update() captured into one CUDA graph; two replays on two batches leave the
     same weights and the same loss as two eager steps from the same initial state (AdamW step counter on the device)."""
