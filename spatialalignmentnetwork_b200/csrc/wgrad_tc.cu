@@ -303,13 +303,23 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_tc_kernel(const WgParams 
   }
 }
 
-// dbias[c] = sum over n, pixels of dy[n][c][:]   (grid: (C, N))
+// dbias[c] = sum over n, pixels of dy[n][c][:]   (grid: (C, N, chunks); float4 loads, 4 independent partial sums per thread)
 __global__ void __launch_bounds__(256) bias_grad_kernel(const float* __restrict__ dy, float* __restrict__ db, int C, int P) {
   __shared__ float red[32];
   const float* src = dy + ((long long)blockIdx.y * C + blockIdx.x) * P;
-  float s = 0.f;
-  for (int i = threadIdx.x; i < P; i += blockDim.x) s += src[i];
-  s = block_sum(s, red);
+  const int per = (P + gridDim.z - 1) / gridDim.z;
+  const int i0 = blockIdx.z * per, i1 = min(P, i0 + per);
+  float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+  if ((P & 3) == 0 && (per & 3) == 0) {
+    const float4* s4 = (const float4*)src;
+    for (int i = (i0 >> 2) + threadIdx.x; i < (i1 >> 2); i += blockDim.x) {
+      const float4 v = __ldg(s4 + i);
+      s0 += v.x; s1 += v.y; s2 += v.z; s3 += v.w;
+    }
+  } else {
+    for (int i = i0 + threadIdx.x; i < i1; i += blockDim.x) s0 += __ldg(src + i);
+  }
+  const float s = block_sum((s0 + s1) + (s2 + s3), red);
   if (threadIdx.x == 0) atomicAdd(db + blockIdx.x, s);
 }
 
@@ -372,7 +382,12 @@ int san_tc_wgrad(const void* dys, const void* xs, float* dw, float* dbias, const
   if (dbias) {
     SAN_CHECK_ARG(dy, "san_tc_wgrad: dbias needs the fp32 dy");
     SAN_CUDA(cudaMemsetAsync(dbias, 0, sizeof(float) * (size_t)Cout, st));
-    bias_grad_kernel<<<dim3(Cout, N), 256, 0, st>>>(dy, dbias, Cout, H * W);
+    {
+      const int P = H * W;
+      int chunks = P / 8192;            // ~8 K elements (32 per thread) per block
+      chunks = chunks < 1 ? 1 : (chunks > 16 ? 16 : chunks);
+      bias_grad_kernel<<<dim3(Cout, N, chunks), 256, 0, st>>>(dy, dbias, Cout, P);
+    }
     SAN_LAUNCH_CHECK();
   }
   return SAN_OK;

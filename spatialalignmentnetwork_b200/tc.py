@@ -44,6 +44,7 @@ _IN_BWD_FUSED = os.environ.get("SAN_IN_BWD_FUSED", "1") != "0"
 # gradient of the layer and the join BEFORE its backward returns (autograd accumulates dW on the main stream, and the
 # next tcgen05 launch is the producing layer's data gradient).  SAN_WG_OVERLAP=0: everything on one stream.
 _WG_OVERLAP = os.environ.get("SAN_WG_OVERLAP", "1") != "0"
+_WG_OVERLAP_MIN_ELEMS = 1 << 23
 _WG_PRESTAGE = os.environ.get("SAN_WG_PRESTAGE", "1") != "0"      # 0: the producing layer stages its dY itself (A/B runs)
 # InstanceNorm statistics of a conv output from the conv's own epilogue (san_tc_conv_stats); SAN_EPI_STATS=0: the separate
 # san_plane_stats_in pass over the tensor
@@ -419,7 +420,8 @@ class _FusedConv(Function):
             _stage(gys, N, H, W, _pad8(Cout), [(gy, None, None, None, 1.0, Cout, MODE_DIRECT, False)], _FMT_BWD, amax)
         need_dgrad = any(ctx.needs_input_grad[3 + t["ti"]] for t in terms)
         need_wgrad = ctx.needs_input_grad[0] or (has_bias and ctx.needs_input_grad[1])
-        overlap = _WG_OVERLAP and need_dgrad and need_wgrad
+        # (small problems - the reference's batch of 4, the deepest layers - gain nothing from the fork and pay its host cost)
+        overlap = _WG_OVERLAP and need_dgrad and need_wgrad and N * H * W * max(Cin, Cout) >= _WG_OVERLAP_MIN_ELEMS
 
         # ---- weight gradient: tcgen05 GEMM over the pixel dimension on the staged dY and the (kept or re-staged) input
         dw = db = None
