@@ -164,6 +164,20 @@ int san_tc_conv_stats(const void* xs, const void* ws, const float* bias, float* 
                       int K, long long y_bs, int fmt, const float* a_absmax, double* sums, void* stream);
 int san_in_stats_from_sums(const double* sums, float* mean, float* m2, float* a, float* b, int planes, int group, int P,
                            float eps, void* stream);
+/* Row-ring form of the 3x3 conv for the narrow full-resolution layers (<= 24 input, <= 32 output channels): the kernel reads
+ * the RAW fp32 input x[N,Cin,H,W] and applies the producing layer's per-plane normalisation + LeakyReLU
+ * (act(a*(x-mu)+b), a null = identity: network inputs, gradients) and the fp16-pair split ITSELF - what
+ * san_tc_stage_terms + san_tc_conv do in two passes over HBM (reference varnet.py:141-145 followed by :140,143).  absmax: the
+ * dynamic scale of a gradient operand (identity only).  xs_out (may be null): the staged form of the operand
+ * (san_tc_staged_act_elems), written row by row with TMA bulk stores for the weight-gradient GEMM.  sums (may be null): the
+ * statistics epilogue of san_tc_conv_stats.  Weights: san_tc_stage_weights_rows (fp16 pairs, fmt = 1) into
+ * san_tc_rows_weight_elems elements; Cout / Cin of the _elems / _supported / conv calls are those of the LAUNCH. */
+int san_tc_conv_rows_supported(int H, int W, int Cin, int Cout, int K);
+long long san_tc_rows_weight_elems(int H, int W, int Cout, int Cin);
+int san_tc_stage_weights_rows(const float* w, void* ws, int H, int W, int Cout, int Cin, int dgrad, int fmt, void* stream);
+int san_tc_conv_rows(const float* x, const float* mu, const float* a, const float* b, float slope, const float* absmax,
+                     void* xs_out, const void* ws, const float* bias, float* y, double* sums, int N, int H, int W, int Cin,
+                     int Cout, void* stream);
 
 /* dW[Cout,Cin,K,K] (and dbias[Cout] from the fp32 dy, both optional-bias) from the staged dY and the staged
  * input of the forward conv: tcgen05 GEMM over the pixel dimension, MN-major operands, BF16x3 */

@@ -623,6 +623,413 @@ __device__ __forceinline__ float act1(float v, float mu, float a, float b, float
   return z > 0.f ? z : z * slope;
 }
 
+// ================================================================================== fused-staging conv ("row ring")
+// The narrow full-resolution 3x3 layers (<= 24 input, <= 32 output channels) WITHOUT a staged operand in HBM on the way in:
+// the CTA converts raw fp32 rows itself.  A CTA walks a contiguous range of output rows of one image after the other; the
+// padded input rows it needs live in a RING of shared-memory row slots, each holding the row as the canonical K-major
+// operand planes [hl][kg][slot][8 x 16 bit] - with one-row units every filter-tap window of a 128-pixel tile lies inside ONE
+// padded row, so the three rows of a unit need not be contiguous and every row is converted ONCE per CTA (a strip-wise
+// kernel would convert each row three times).  Converter warps read the raw rows (coalesced per channel plane), apply the
+// producing layer's normalisation + LeakyReLU (or nothing: gradients), split into the fp16 pair and write the planes; one
+// thread optionally copies each finished row to the staged tensor in HBM with TMA bulk stores (the weight-gradient GEMM
+// still reads that form); the MMA warp addresses taps as shifted descriptors into the ring; all K groups and the whole
+// weight block stay resident, so there is no per-unit operand reload at all.  Form: HLS ([W_hi | W_lo] along N), taps of the
+// half-empty last K-step paired INSIDE a filter row (a pair across rows would need the ring distance as a descriptor offset).
+//   warp 0       weight load (once), TMA row stores          warp 1        TMEM + MMA issue
+//   warps 2..17  epilogue (+ statistics) as in conv_tc_kernel   warps 18..25  converters
+constexpr int RR_EPI_WARPS = 12;      // three per TMEM lane quarter: one per 128-pixel tile of a 320-wide row
+constexpr int RR_CONV_WARPS = 16;
+constexpr int RR_THREADS = 64 + 32 * RR_EPI_WARPS + 32 * RR_CONV_WARPS;      // 960
+constexpr int RR_NR_MAX = 8;      // ring slots: 3 rows in use + the rows being converted ahead (as many as shared memory allows)
+constexpr int RR_CMAX = 24;       // input channels (3 groups of 8)
+constexpr int RR_GROUPS = 2;      // converter groups: group g converts rows k = g (mod 2), so two rows' loads are in flight
+constexpr int RR_GT = RR_CONV_WARPS * 32 / RR_GROUPS;      // threads per converter group
+constexpr int RR_MI = 4;          // (pixel slot, channel group) items per converter thread and row
+
+struct RrGeom {
+  int KG, KS, Npad, Ncol, Wp, Hp, PS, T, RS, pair;
+  int plane_bytes, row_bytes, wblk_bytes, w_bytes, NR;
+  int w_off, ring_off, coef_off, stat_off, smem_bytes;
+};
+
+bool rr_geometry(int H, int W, int Cin, int Cout, int K, bool stats, RrGeom* g) {
+  if (K != 3 || Cin > RR_CMAX || pad16(Cout) > 32 || W < 30 || H < 2) return false;
+  g->KG = (Cin + 7) / 8; g->KS = (g->KG + 1) / 2; g->pair = (g->KG & 1) ? 2 : 0;
+  g->Npad = pad16(Cout); g->Ncol = 2 * g->Npad;
+  g->Wp = W + 2; g->Hp = H + 2; g->PS = g->Hp * g->Wp;
+  g->T = (g->Wp + 127) / 128;
+  if (2 * g->T * g->Ncol > 512 || g->Wp * g->KG > RR_MI * RR_GT) return false;
+  g->RS = 128 * g->T + 8;
+  g->plane_bytes = g->RS * 16;
+  g->row_bytes = 2 * g->KG * g->plane_bytes;
+  g->wblk_bytes = 4 * g->Npad * 16;
+  g->w_bytes = g->KS * 9 * g->wblk_bytes;
+  g->w_off = TC_SMEM_HEADER;
+  g->ring_off = g->w_off + g->w_bytes;
+  // The row -> MMA -> "slot free" -> next row chain is a latency loop: with NR slots NR - 2 rows are in flight around it
+  const int fixed = g->ring_off + RR_GROUPS * RR_CMAX * 16 + (stats ? RR_EPI_WARPS * 2 * g->Npad * (int)sizeof(float) : 0);
+  g->NR = (TC_SMEM_MAX - fixed) / g->row_bytes;
+  if (g->NR > RR_NR_MAX) g->NR = RR_NR_MAX;
+  if (g->NR < 4) return false;
+  g->coef_off = g->ring_off + g->NR * g->row_bytes;
+  g->stat_off = g->coef_off + RR_GROUPS * RR_CMAX * 16;
+  g->smem_bytes = g->stat_off + (stats ? RR_EPI_WARPS * 2 * g->Npad * (int)sizeof(float) : 0);
+  if (g->smem_bytes > TC_SMEM_MAX) return false;
+  if (g->smem_bytes < 120 * 1024) g->smem_bytes = 120 * 1024;      // one CTA per SM (all 512 TMEM columns)
+  return true;
+}
+
+struct RrParams {
+  const float* x;            // raw fp32 input [N][Cin][H][W]
+  const float* mu;           // per-plane centre / scale / shift of the producing layer's normalisation (a null: identity)
+  const float* a;
+  const float* b;
+  float slope;
+  const float* absmax;       // null: static activation scale; else device scalar max|x| -> dynamic scale (gradient operand)
+  __nv_bfloat16* xs_out;     // null, or the staged tensor (past the lead-in) that receives every converted row
+  const __nv_bfloat16* ws;   // staged weights, HLS layout, pair = 2 in the last K-step when KG is odd
+  const float* bias;
+  float* y;
+  double* sums;
+  int N, H, W, Cin, Cout, nunits;
+  float out_scale;
+  RrGeom g;
+};
+
+__device__ __forceinline__ void rr_range(const RrParams& p, int& u0, int& u1) {
+  u0 = (int)((long long)blockIdx.x * p.nunits / gridDim.x);
+  u1 = (int)((long long)(blockIdx.x + 1) * p.nunits / gridDim.x);
+}
+__device__ __forceinline__ void bulk_s2g(void* dst, uint32_t src, uint32_t bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(src), "r"(bytes) : "memory");
+}
+
+__global__ void __launch_bounds__(RR_THREADS, 1) conv_rows_kernel(const RrParams p) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  const RrGeom& g = p.g;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t hdr = smem_u32(smem);
+  const uint32_t bar_rfull = hdr, bar_rempty = hdr + 64, bar_accf = hdr + 128, bar_acce = hdr + 144, bar_w = hdr + 160;
+  volatile uint32_t* tmem_slot = (volatile uint32_t*)(smem + 168);
+  const uint32_t w0 = hdr + g.w_off, ring0 = hdr + g.ring_off;
+  const int NRr = g.NR;                                                  // ring slots (<= RR_NR_MAX)
+
+  if (warp == 0 && lane == 0) {
+    for (int i = 0; i < g.NR; ++i) { mbar_init(bar_rfull + 8 * i, RR_CONV_WARPS / RR_GROUPS); mbar_init(bar_rempty + 8 * i, p.xs_out ? 2 : 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(bar_accf + 8 * i, 1); mbar_init(bar_acce + 8 * i, RR_EPI_WARPS); }
+    mbar_init(bar_w, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32((void*)tmem_slot)),
+                 "r"(512)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  {   // the slots past a row's Wp pixels are read by the last tile's windows (results dropped): finite values once
+    uint4* z = (uint4*)(smem + g.ring_off);
+    const int n16 = g.NR * g.row_bytes / 16;
+    for (int i = threadIdx.x; i < n16; i += blockDim.x) z[i] = make_uint4(0, 0, 0, 0);
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
+  int u0, u1;
+  rr_range(p, u0, u1);
+
+  if (warp == 0) {
+    // ============================ weights (once) + TMA stores of the converted rows ============================
+    if (lane == 0) {
+      mbar_expect_tx(bar_w, (uint32_t)g.w_bytes);
+      bulk_g2s(w0, p.ws, (uint32_t)g.w_bytes, bar_w);
+      if (p.xs_out) {
+        const uint32_t bytes = (uint32_t)g.Wp * 16;
+        int k = 0;
+        for (int u = u0; u < u1; ++u) {
+          const int n = u / p.H, yy = u - n * p.H;
+          const bool fresh = (u == u0) || (yy == 0);
+          for (int r = fresh ? 0 : 2; r < 3; ++r, ++k) {
+            const int pr = yy + r, s = k % NRr;
+            mbar_wait_sleep(bar_rfull + 8 * s, (uint32_t)(k / NRr) & 1u);
+            const uint32_t src0 = ring0 + (uint32_t)s * g.row_bytes;
+            for (int hl = 0; hl < 2; ++hl)
+              for (int kg = 0; kg < g.KG; ++kg) {
+                __nv_bfloat16* dst = p.xs_out + (((long long)(n * 2 + hl) * g.KG + kg) * g.PS + (long long)pr * g.Wp) * 8;
+                bulk_s2g(dst, src0 + (uint32_t)(hl * g.KG + kg) * g.plane_bytes, bytes);
+              }
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            if (k > 0) {      // the previous row's stores have read their shared-memory source: its slot may be refilled
+              asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+              mbar_arrive(bar_rempty + 8 * ((k - 1) % NRr));
+            }
+          }
+        }
+        asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+        if (k > 0) mbar_arrive(bar_rempty + 8 * ((k - 1) % NRr));
+        asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+      }
+    }
+  } else if (warp == 1) {
+    // ========================================= MMA issue =========================================
+    const uint32_t idesc = umma_idesc_16(128, g.Npad, 3), idesc2 = umma_idesc_16(128, 2 * g.Npad, 3);
+    const uint32_t hiw = (uint32_t)(umma_desc(0, 0, 128) >> 32);        // SBO 128 B, version bit
+    const uint32_t PPu = (uint32_t)g.RS;                                 // plane pitch in 16 B units
+    const uint32_t a_lbo_pp = PPu << 16;                                 // K group 1 = the next channel-group plane
+    const uint32_t b_lbo = (uint32_t)(2 * g.Npad) << 16;                 // K group 1 of B = the next kk plane of the block
+    const uint32_t wblk16 = (uint32_t)g.wblk_bytes >> 4;
+    mbar_wait_warp(bar_w, 0, lane);
+    int k_next = 0, as = 0;
+    uint32_t aph = 0;
+    for (int u = u0; u < u1; ++u) {
+      const int yy = u % p.H;
+      const bool fresh = (u == u0) || (yy == 0);
+      const int nnew = fresh ? 3 : 1;
+      const int base = fresh ? k_next : k_next - 2;
+      for (int c = k_next; c < k_next + nnew; ++c) mbar_wait_warp(bar_rfull + 8 * (c % NRr), (uint32_t)(c / NRr) & 1u, lane);
+      k_next += nnew;
+      mbar_wait_warp(bar_acce + 8 * as, aph ^ 1, lane);
+      tc_fence_after();
+      const bool next_fresh = (u + 1 == u1) || ((u + 1) % p.H == 0);
+      if (elect_one_sync()) {
+        uint32_t row16[3];
+#pragma unroll
+        for (int dy = 0; dy < 3; ++dy) row16[dy] = (ring0 + (uint32_t)((base + dy) % NRr) * g.row_bytes) >> 4;
+        const uint32_t losplit = (uint32_t)g.KG * PPu;                   // hi -> lo planes of a row slot
+        const uint32_t acc0 = tmem_base + (uint32_t)(as * g.T * g.Ncol);
+        for (int t = 0; t < g.T; ++t) {
+          const uint32_t d = acc0 + (uint32_t)(t * g.Ncol);
+          uint32_t started = 0;
+          for (int ks = 0; ks < g.KS; ++ks) {
+            const uint32_t bks = (w0 >> 4) + (uint32_t)ks * 9u * wblk16;
+            if (g.pair && ks == g.KS - 1) {
+              const uint32_t goff = (uint32_t)(g.KG - 1) * PPu + (uint32_t)t * 128u;
+#pragma unroll
+              for (int blk = 0; blk < 6; ++blk) {
+                const int dy = blk >> 1;
+                const uint32_t al = row16[dy] + goff + ((blk & 1) ? 2u : 0u) + ((blk & 1) ? 0u : (1u << 16));   // pair: LBO = 1 slot
+                const uint32_t bl = bks + (uint32_t)blk * wblk16 + b_lbo;
+                const uint64_t A_hi = ((uint64_t)hiw << 32) | al, A_lo = ((uint64_t)hiw << 32) | (al + losplit);
+                const uint64_t B_all = ((uint64_t)hiw << 32) | bl;
+                tc_mma_bf16(d, A_hi, B_all, idesc2, started);
+                tc_mma_bf16(d, A_lo, B_all, idesc, 1u);
+                started = 1;
+              }
+            } else {
+              const uint32_t goff = (uint32_t)(2 * ks) * PPu + (uint32_t)t * 128u + a_lbo_pp;
+#pragma unroll
+              for (int tap = 0; tap < 9; ++tap) {
+                const uint32_t al = row16[tap / 3] + goff + (uint32_t)(tap % 3);
+                const uint32_t bl = bks + (uint32_t)tap * wblk16 + b_lbo;
+                const uint64_t A_hi = ((uint64_t)hiw << 32) | al, A_lo = ((uint64_t)hiw << 32) | (al + losplit);
+                const uint64_t B_all = ((uint64_t)hiw << 32) | bl;
+                tc_mma_bf16(d, A_hi, B_all, idesc2, started);
+                tc_mma_bf16(d, A_lo, B_all, idesc, 1u);
+                started = 1;
+              }
+            }
+          }
+        }
+        tc_commit(bar_accf + 8 * as);
+        // rows no later unit reads: the oldest one, or all three at the end of an image / of the range
+        tc_commit(bar_rempty + 8 * (base % NRr));
+        if (next_fresh) { tc_commit(bar_rempty + 8 * ((base + 1) % NRr)); tc_commit(bar_rempty + 8 * ((base + 2) % NRr)); }
+      }
+      __syncwarp();
+      if (++as == 2) { as = 0; aph ^= 1; }
+    }
+  } else if (warp < 2 + RR_EPI_WARPS) {
+    // ========================================= epilogue =========================================
+    const int wq = warp & 3, egrp = (warp - 2) >> 2;
+    constexpr int EG = RR_EPI_WARPS / 4;
+    const float oscale = p.absmax ? p.out_scale / tc_dyn_scale(__ldg(p.absmax)) : p.out_scale;
+    const long long HW = (long long)p.H * p.W;
+    float* sacc = (float*)(smem + g.stat_off) + (size_t)(warp - 2) * (2 * g.Npad);
+    int seg = -1;
+    if (p.sums)
+      for (int i = lane; i < 2 * g.Npad; i += 32) sacc[i] = 0.f;
+    int as = 0;
+    uint32_t aph = 0;
+    for (int u = u0; u < u1; ++u) {
+      const int n = u / p.H, yy = u - n * p.H;
+      if (p.sums && seg != n) {
+        if (seg >= 0) {
+          __syncwarp();
+          for (int i = lane; i < 2 * p.Cout; i += 32) {
+            const float v = sacc[i];
+            if (v != 0.f) atomicAdd(p.sums + (long long)seg * p.Cout * 2 + i, (double)v);
+            sacc[i] = 0.f;
+          }
+          __syncwarp();
+        }
+        seg = n;
+      }
+      mbar_wait_warp(bar_accf + 8 * as, aph, lane);
+      tc_fence_after();
+      float* yn = p.y + (long long)n * p.Cout * HW + (long long)yy * p.W;
+      for (int t = egrp; t < g.T; t += EG) {
+        const int x = t * 128 + wq * 32 + lane;
+        const bool valid = x < p.W;
+        float* dst = yn + x;
+        const uint32_t trow = tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)(as * g.T * g.Ncol + t * g.Ncol);
+        for (int c0 = 0; c0 < p.Cout; c0 += 8) {
+          float v[8], v2[8];
+          tc_ld8x2(trow + c0, trow + g.Npad + c0, v, v2);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const int c = c0 + j;
+            const float bv = (p.bias && c < p.Cout) ? __ldg(p.bias + c) : 0.f;
+            v[j] = fmaf(v[j] + v2[j], oscale, bv);
+            if (valid && c < p.Cout) dst[(long long)c * HW] = v[j];
+          }
+          if (p.sums) {
+            float w16[16];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const float xv = valid ? v[j] : 0.f;
+              w16[j] = xv; w16[8 + j] = xv * xv;
+            }
+            const float tot = warp_sum16(w16, lane);
+            const int vi = (lane >> 1) & 15, c = c0 + (vi & 7);
+            if (!(lane & 1) && c < p.Cout) sacc[2 * c + (vi >> 3)] += tot;
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_acce + 8 * as);
+      if (++as == 2) { as = 0; aph ^= 1; }
+    }
+    if (p.sums && seg >= 0) {
+      __syncwarp();
+      for (int i = lane; i < 2 * p.Cout; i += 32) {
+        const float v = sacc[i];
+        if (v != 0.f) atomicAdd(p.sums + (long long)seg * p.Cout * 2 + i, (double)v);
+      }
+    }
+  } else {
+    // ========================================= converters =========================================
+    // A thread owns up to RR_MI (pixel slot, channel group) items of every row - the same ones for every row - and keeps the
+    // raw values of the NEXT row in registers: the global loads are issued right after a row is handed over and complete
+    // while the thread waits for the ring slot, so only arithmetic + shared-memory stores sit between "slot free" and "row
+    // full" (with the loads after the wait every row cost a full memory latency: 4 us per row, measured).
+    const int cw = warp - 2 - RR_EPI_WARPS;
+    const int grp = cw / (RR_CONV_WARPS / RR_GROUPS);                  // this warp's group converts rows k = grp (mod RR_GROUPS)
+    const int ct = (cw % (RR_CONV_WARPS / RR_GROUPS)) * 32 + lane;     // 0 .. RR_GT - 1
+    float4* coef = (float4*)(smem + g.coef_off) + grp * RR_CMAX;       // per channel of the group's current image: mu, a, b, -
+    const float scale = p.absmax ? tc_dyn_scale(__ldg(p.absmax)) : TC_SX;
+    const long long HW = (long long)p.H * p.W;
+    const int items = g.Wp * g.KG;                                     // <= RR_MI * 512 (rr_geometry)
+    // per item (fixed for the whole kernel): channel group, pixel slot, element offset of its first channel at column x - 1
+    // inside an image, and how many of its 8 channels exist (the loads of the missing ones repeat the last real channel and
+    // are zeroed afterwards: unconditional loads, no per-load predicates / descriptor moves - the first version spent 700
+    // warp instructions per row and warp, the kernel was issue-bound)
+    int it_kg[RR_MI], it_x[RR_MI], it_off[RR_MI], it_nreal[RR_MI];
+    bool it_in[RR_MI];
+#pragma unroll
+    for (int m = 0; m < RR_MI; ++m) {
+      const int i = ct + m * RR_GT;
+      it_kg[m] = i < items ? i / g.Wp : -1;
+      it_x[m] = i < items ? i - it_kg[m] * g.Wp : 0;
+      it_in[m] = it_kg[m] >= 0 && it_x[m] >= 1 && it_x[m] <= p.W;
+      const int kg = it_kg[m] < 0 ? 0 : it_kg[m];
+      it_nreal[m] = min(8, p.Cin - kg * 8);
+      it_off[m] = kg * 8 * (int)HW + (it_in[m] ? it_x[m] - 1 : 0);
+    }
+    const int HWi = (int)HW;
+    float va[RR_MI][8];
+    auto load_row = [&](int u, int r, float (&v)[RR_MI][8]) {
+      const int n = u / p.H, pr = (u - n * p.H) + r;                   // padded row pr = image row pr - 1
+      const int yrow = min(max(pr - 1, 0), p.H - 1);                   // (border rows load row 0 / H - 1 and are zeroed)
+      const float* xrow = p.x + (long long)n * p.Cin * HW + (long long)yrow * p.W;
+#pragma unroll
+      for (int m = 0; m < RR_MI; ++m) {
+        if (it_kg[m] >= 0) {
+          const float* src = xrow + it_off[m];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) v[m][j] = __ldg(src + min(j, it_nreal[m] - 1) * HWi);
+        }
+      }
+    };
+    int n_cur = -1;
+    auto convert_row = [&](int u, int r, int k, float (&v)[RR_MI][8]) {
+      const int n = u / p.H, pr = (u - n * p.H) + r, s = k % NRr;
+      if (n != n_cur) {
+        asm volatile("bar.sync %0, %1;" ::"r"(2 + grp), "n"(RR_GT) : "memory");      // the group is done with its old table
+        if (ct < RR_CMAX) {
+          float4 cf = make_float4(0.f, 1.f, 0.f, 0.f);
+          if (p.a && ct < p.Cin) {
+            const long long pl = (long long)n * p.Cin + ct;
+            cf = make_float4(p.mu ? __ldg(p.mu + pl) : 0.f, __ldg(p.a + pl), p.b ? __ldg(p.b + pl) : 0.f, 0.f);
+          }
+          coef[ct] = cf;
+        }
+        asm volatile("bar.sync %0, %1;" ::"r"(2 + grp), "n"(RR_GT) : "memory");
+        n_cur = n;
+      }
+      mbar_wait_warp(bar_rempty + 8 * s, ((uint32_t)(k / NRr) & 1u) ^ 1u, lane);
+      uint8_t* rowp = smem + g.ring_off + (size_t)s * g.row_bytes;
+      const bool inb_row = pr >= 1 && pr <= p.H;
+#pragma unroll
+      for (int m = 0; m < RR_MI; ++m) {
+        if (it_kg[m] >= 0) {
+          const bool inb = inb_row && it_in[m];
+          uint32_t hw[4], lw[4];
+          if (p.a) {
+            const float4* cf8 = coef + it_kg[m] * 8;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const float4 cf = cf8[j];
+              const float z = act1(v[m][j], cf.x, cf.y, cf.z, p.slope);
+              v[m][j] = (inb && j < it_nreal[m]) ? z : 0.f;
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) v[m][j] = (inb && j < it_nreal[m]) ? v[m][j] : 0.f;
+          }
+#pragma unroll
+          for (int j = 0; j < 4; ++j) split16x2(v[m][2 * j], v[m][2 * j + 1], true, scale, hw[j], lw[j]);
+          uint4* dst = (uint4*)(rowp + (size_t)(it_kg[m] * g.RS + it_x[m]) * 16);
+          dst[0] = make_uint4(hw[0], hw[1], hw[2], hw[3]);
+          dst[(size_t)g.KG * g.RS] = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+        }
+      }
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // generic-proxy stores before UMMA / TMA reads
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_rfull + 8 * s);
+    };
+    // row sequence: (u, r) -> next; the first unit of an image / of the range brings three new rows, every other unit one
+    auto advance = [&](int& u, int& r) {
+      if (r < 2) {
+        ++r;
+      } else {
+        ++u;
+        r = ((u % p.H) == 0) ? 0 : 2;
+      }
+    };
+    // one register set per thread; the two groups alternate rows, so while one group waits for its loads the other converts
+    int u = u0, r = 0, k = 0;
+    auto skip_to_mine = [&]() {
+      while (u < u1 && (k % RR_GROUPS) != grp) { advance(u, r); ++k; }
+    };
+    skip_to_mine();
+    if (u < u1) load_row(u, r, va);
+    while (u < u1) {
+      convert_row(u, r, k, va);
+      advance(u, r); ++k;
+      skip_to_mine();
+      if (u < u1) load_row(u, r, va);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
+  }
+}
+
 // Per-block work list: for each of the 8 channels of the block's channel group, the (at most
 // STAGE_MAX_SUM) terms that contribute to it, with everything that does not depend on the pixel slot
 // resolved once (plane base pointer, coefficients).  Missing entries are neutral dummies (a = 0, a
@@ -895,7 +1302,12 @@ __global__ void stage_weights_kernel(const float* __restrict__ w, __nv_bfloat16*
     const int co = ns * Npad + nn;
     int ci = ks * 16 + kk * 8 + j;
     bool live = true;
-    if (pair && ks == KS - 1) {       // block i < 5 holds taps 2i (K group 0) and 2i+1 (K group 1) of the ONE real channel group
+    if (pair == 2 && ks == KS - 1) {  // row-ring kernel: taps paired inside a filter row: block 2*dy = (dx 0, dx 1), block 2*dy+1 = (dx 2, -)
+      ci = ks * 16 + j;
+      const int dy = tap >> 1, odd = tap & 1;
+      live = tap < 6 && !(odd && kk);
+      tap = dy * 3 + (odd ? 2 : kk);
+    } else if (pair && ks == KS - 1) {       // block i < 5 holds taps 2i (K group 0) and 2i+1 (K group 1) of the ONE real channel group
       ci = ks * 16 + j;
       live = tap < 5 && 2 * tap + kk < KK;
       tap = 2 * tap + kk;
@@ -1104,6 +1516,61 @@ int san_tc_conv_stats(const void* xs, const void* ws, const float* bias, float* 
 int san_tc_conv(const void* xs, const void* ws, const float* bias, float* y, int N, int H, int W, int Cin, int Cout,
                 int K, long long y_bs, int fmt, const float* a_absmax, void* stream) {
   return san_tc_conv_stats(xs, ws, bias, y, N, H, W, Cin, Cout, K, y_bs, fmt, a_absmax, nullptr, stream);
+}
+
+// ---- row-ring conv (conv_rows_kernel): the conv reads RAW fp32 rows and stages them itself -------------------------------
+int san_tc_conv_rows_supported(int H, int W, int Cin, int Cout, int K) {
+  RrGeom g;
+  return rr_geometry(H, W, Cin, Cout, K, true, &g) ? 1 : 0;
+}
+
+long long san_tc_rows_weight_elems(int H, int W, int Cout, int Cin) {
+  RrGeom g;
+  if (!rr_geometry(H, W, Cin, Cout, 3, false, &g)) return -1;
+  return (long long)g.w_bytes / 2;
+}
+
+int san_tc_stage_weights_rows(const float* w, void* ws, int H, int W, int Cout, int Cin, int dgrad, int fmt, void* stream) {
+  SAN_CHECK_ARG(w && ws && Cout > 0 && Cin > 0 && fmt == 1, "san_tc_stage_weights_rows: bad args (fp16 pairs only)");
+  RrGeom g;
+  const int Co_k = dgrad ? Cin : Cout, Ci_k = dgrad ? Cout : Cin;
+  SAN_CHECK_ARG(rr_geometry(H, W, Ci_k, Co_k, 3, false, &g), "san_tc_stage_weights_rows: unsupported shape");
+  const long long total = (long long)g.KS * 9 * 4 * g.Npad * 8;
+  stage_weights_kernel<<<ew_blocks(total), 256, 0, (cudaStream_t)stream>>>(w, (__nv_bfloat16*)ws, Cout, Cin, 9, dgrad, 1, g.KS,
+                                                                           g.Npad, fmt, 0, 1, g.pair);
+  SAN_LAUNCH_CHECK();
+  return SAN_OK;
+}
+
+int san_tc_conv_rows(const float* x, const float* mu, const float* a, const float* b, float slope, const float* absmax,
+                     void* xs_out, const void* ws, const float* bias, float* y, double* sums, int N, int H, int W, int Cin,
+                     int Cout, void* stream) {
+  SAN_CHECK_ARG(x && ws && y && N > 0 && H > 0 && W > 0 && Cin > 0 && Cout > 0, "san_tc_conv_rows: bad args");
+  SAN_CHECK_ARG(!(absmax && a), "san_tc_conv_rows: the dynamic scale is for un-normalised (gradient) operands");
+  RrParams p{};
+  SAN_CHECK_ARG(rr_geometry(H, W, Cin, Cout, 3, sums != nullptr, &p.g), "san_tc_conv_rows: unsupported shape H=%d W=%d Cin=%d Cout=%d",
+                H, W, Cin, Cout);
+  cudaStream_t st = (cudaStream_t)stream;
+  p.x = x; p.mu = mu; p.a = a; p.b = b; p.slope = slope; p.absmax = absmax;
+  p.xs_out = xs_out ? (__nv_bfloat16*)xs_out + TC_LEAD : nullptr;
+  p.ws = (const __nv_bfloat16*)ws; p.bias = bias; p.y = y; p.sums = sums;
+  p.N = N; p.H = H; p.W = W; p.Cin = Cin; p.Cout = Cout; p.nunits = N * H;
+  p.out_scale = (absmax ? 1.f : 1.f / TC_SX) / TC_SW;
+  if (sums) SAN_CUDA(cudaMemsetAsync(sums, 0, sizeof(double) * 2 * (size_t)N * Cout, st));
+  if (xs_out) {     // lead-in / trailing slack of the staged buffer (TC_LEAD / TC_TRAIL): zero, like the staging kernels leave them
+    SAN_CUDA(cudaMemsetAsync(xs_out, 0, TC_LEAD * sizeof(__nv_bfloat16), st));
+    SAN_CUDA(cudaMemsetAsync((__nv_bfloat16*)xs_out + TC_LEAD + (long long)N * 2 * p.g.KG * p.g.PS * 8, 0,
+                             TC_TRAIL * sizeof(__nv_bfloat16), st));
+  }
+  static bool attr_set = false;
+  if (!attr_set) {
+    SAN_CUDA(cudaFuncSetAttribute(conv_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_MAX));
+    attr_set = true;
+  }
+  const int grid = p.nunits < san_num_sms() ? p.nunits : san_num_sms();
+  conv_rows_kernel<<<grid, RR_THREADS, p.g.smem_bytes, st>>>(p);
+  SAN_LAUNCH_CHECK();
+  return SAN_OK;
 }
 
 }  // extern "C"

@@ -33,6 +33,30 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
       "r"(parity)
       : "memory");
 }
+// Polling wait that yields the issue slots between polls (roles that idle next to warps doing real work: the converter
+// warps of conv_rows_kernel share their schedulers with 18 waiting warps)
+__device__ __forceinline__ void mbar_wait_sleep(uint32_t bar, uint32_t parity) {
+  uint32_t done = 0;
+  while (true) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred P1;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, P1;\n\t"
+        "}"
+        : "=r"(done)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    if (done) break;
+    __nanosleep(100);
+  }
+}
+// One lane polls (yielding between polls), the warp re-converges behind it: 32 lanes spinning on try_wait cost issue slots
+// that the converter / MMA-issuing warps of conv_rows_kernel need (ncu: 508 M warp instructions, two thirds of them polls)
+__device__ __forceinline__ void mbar_wait_warp(uint32_t bar, uint32_t parity, int lane) {
+  if (lane == 0) mbar_wait(bar, parity);      // (no back-off: these waits sit on the row -> MMA -> row latency chain)
+  __syncwarp();
+}
 __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
                "l"(src), "r"(bytes), "r"(bar)

@@ -208,7 +208,7 @@ _ws_entries = {}
 
 
 class _WsEntry:
-    __slots__ = ("wref", "shape", "dgrad", "H", "W", "fmt", "ws", "version", "event")
+    __slots__ = ("wref", "shape", "ptr", "dgrad", "H", "W", "fmt", "ws", "version", "event")
 
 
 def invalidate_weight_cache():
@@ -226,7 +226,7 @@ def _restage_stale(device):
             if w is None:
                 dead.append(key)
                 continue
-            if e.version == w._version or w.device != device:
+            if e.version == w._version or w.device != device or e.ptr != w.data_ptr():
                 continue
             _stage_weights_now(w, e.ws, e.dgrad, e.H, e.W, e.fmt)
             e.version = w._version
@@ -254,9 +254,10 @@ def _stage_weights(w, dgrad, H, W, fmt):
         return ws
     key = (id(w), bool(dgrad), H, W, fmt)
     e = _ws_entries.get(key)
-    if e is None or e.wref() is not w or e.shape != tuple(w.shape):
+    if e is None or e.wref() is not w or e.shape != tuple(w.shape) or e.ptr != w.data_ptr():
+        # (a different storage behind the same Parameter object - module.to(), p.data = ... - is a new entry)
         e = _WsEntry()
-        e.wref, e.shape, e.dgrad, e.H, e.W, e.fmt = weakref.ref(w), tuple(w.shape), bool(dgrad), H, W, fmt
+        e.wref, e.shape, e.ptr, e.dgrad, e.H, e.W, e.fmt = weakref.ref(w), tuple(w.shape), w.data_ptr(), bool(dgrad), H, W, fmt
         e.ws = _alloc_staged_weights(w, dgrad, H, W)
         _stage_weights_now(w, e.ws, dgrad, H, W, fmt)
         e.version = w._version

@@ -164,6 +164,64 @@ def test_tc_conv_statistics_epilogue(case):
     assert float(st[3].abs().max()) == 0.0
 
 
+ROWS_CASES = [
+    # N, Cin, H, W, Cout, normalised input, dynamic scale
+    (3, 18, 64, 64, 18, True, False), (2, 3, 40, 48, 18, False, False), (2, 16, 32, 64, 8, True, False),
+    (2, 18, 33, 47, 3, False, True), (70, 8, 32, 32, 8, True, False), (5, 24, 20, 36, 32, True, False),
+    (2, 18, 320, 320, 18, True, False), (2, 18, 320, 320, 18, False, True),
+]
+
+
+@pytest.mark.parametrize("case", ROWS_CASES)
+def test_tc_conv_rows_fused_staging(case):
+    """san_tc_conv_rows (the conv stages its raw fp32 input itself: row ring in shared memory) against the two-pass path
+    san_tc_stage_terms + san_tc_conv_stats on the same input: the TMA-stored staged operand is BIT-identical to the staging
+    kernel's, the output agrees to accumulation order, the statistics agree; and against torch fp64
+    (reference varnet.py:139-146: InstanceNorm + LeakyReLU of the producer, then the 3x3 conv)."""
+    N, Cin, H, W, Cout, normed, dyn = case
+    L, tc = _lib(), tc_mod()
+    assert L.lib().san_tc_conv_rows_supported(H, W, Cin, Cout, 3)
+    torch.manual_seed(31)
+    x = torch.randn(N, Cin, H, W, device="cuda") * (1e-7 if dyn else 1.5) + (0.0 if dyn else 0.4)
+    w = (torch.randn(Cout, Cin, 3, 3) / math.sqrt(Cin * 9)).cuda()
+    mu = a = b = None
+    slope = 1.0
+    if normed:
+        mu = torch.randn(N * Cin, device="cuda") * 0.3
+        a = torch.rand(N * Cin, device="cuda") + 0.5
+        b = torch.randn(N * Cin, device="cuda") * 0.1
+        slope = 0.2
+    am = absmax(x) if dyn else None
+    # reference path: staging pass + conv with the statistics epilogue
+    xs_ref = torch.empty(L.lib().san_tc_staged_act_elems(N, H, W, Cin), dtype=torch.bfloat16, device="cuda")
+    tc._stage(xs_ref, N, H, W, (Cin + 7) // 8 * 8, [(x, mu, a, b, slope, Cin, 0, False)], F16, am)
+    ws_ref = torch.empty(L.lib().san_tc_staged_weight_elems(H, W, Cout, Cin, 3), dtype=torch.bfloat16, device="cuda")
+    L.call("tc_stage_weights", w, ws_ref, H, W, Cout, Cin, 3, 0, F16)
+    y_ref = torch.empty(N, Cout, H, W, device="cuda")
+    sums_ref = torch.empty(2 * N * Cout, dtype=torch.float64, device="cuda")
+    L.call("tc_conv_stats", xs_ref, ws_ref, None, y_ref, N, H, W, Cin, Cout, 3, 0, 3, am, sums_ref)
+    # row-ring kernel
+    ws = torch.empty(L.lib().san_tc_rows_weight_elems(H, W, Cout, Cin), dtype=torch.bfloat16, device="cuda")
+    L.call("tc_stage_weights_rows", w, ws, H, W, Cout, Cin, 0, F16)
+    xs = torch.full_like(xs_ref, 3.0)
+    y = torch.full_like(y_ref, 7.0)
+    sums = torch.full_like(sums_ref, 5.0)
+    L.call("tc_conv_rows", x, mu, a, b, slope, am, xs, ws, None, y, sums, N, H, W, Cin, Cout)
+    torch.cuda.synchronize()
+    assert torch.equal(xs.view(torch.int16), xs_ref.view(torch.int16))
+    assert rel_l2(y, y_ref) < 2e-6
+    assert ((sums - sums_ref).abs() / (sums_ref.abs() + 1e-30 + 1e-6 * sums_ref.abs().max())).max() < 1e-4
+    z = x.double()
+    if normed:
+        z = a.double().view(N, Cin, 1, 1) * (z - mu.double().view(N, Cin, 1, 1)) + b.double().view(N, Cin, 1, 1)
+        z = F.leaky_relu(z, slope)
+    assert rel_l2(y, F.conv2d(z, w.double(), padding=1)) < 5e-6
+    # without the staged copy and without statistics: same output
+    y2 = torch.empty_like(y)
+    L.call("tc_conv_rows", x, mu, a, b, slope, am, None, ws, None, y2, None, N, H, W, Cin, Cout)
+    assert torch.equal(y2, y)
+
+
 def test_staged_weight_cache_follows_updates():
     """tc._stage_weights caches the staged form of an nn.Parameter on its version counter: in-place torch updates, the
     library's AdamW (raw-pointer kernel + increment_version) and ``.data`` writes followed by invalidate_weight_cache()

@@ -46,6 +46,15 @@ def main():
         if L.lib().san_tc_conv_stats_supported(HW, HW, Cin, Cout, K):      # the same conv with the statistics epilogue
             sums = torch.empty(2 * N * Cout, dtype=torch.float64, device="cuda")
             t_cs = timeit(lambda: L.call("tc_conv_stats", xs, ws, None, y, N, HW, HW, Cin, Cout, K, 0, 3, None, sums))
+        t_rr = t_rr0 = float("nan")
+        if K == 3 and L.lib().san_tc_conv_rows_supported(HW, HW, Cin, Cout, 3):     # row-ring conv: stages its raw input itself
+            wsr = torch.empty(L.lib().san_tc_rows_weight_elems(HW, HW, Cout, Cin), dtype=torch.bfloat16, device="cuda")
+            L.call("tc_stage_weights_rows", w, wsr, HW, HW, Cout, Cin, 0, 1)
+            mu_ = torch.zeros(N * Cin, device="cuda"); a_ = torch.ones(N * Cin, device="cuda")
+            sums2 = torch.empty(2 * N * Cout, dtype=torch.float64, device="cuda")
+            xs2 = torch.empty_like(xs)
+            t_rr = timeit(lambda: L.call("tc_conv_rows", x, mu_, a_, None, 0.2, None, xs2, wsr, None, y, sums2, N, HW, HW, Cin, Cout))
+            t_rr0 = timeit(lambda: L.call("tc_conv_rows", x, mu_, a_, None, 0.2, None, None, wsr, None, y, None, N, HW, HW, Cin, Cout))
         wp = ops._pack(w, False)
         y2 = torch.empty_like(y)
         fp = lambda: L.call("conv2d_fwd", x, wp, None, y2, N, Cin, HW, HW, Cout, K, 0, 0)
@@ -60,7 +69,7 @@ def main():
         fl = 2.0 * N * Cout * HW * HW * Cin * K * K
         err = ((y - y2).norm() / y2.norm()).item()
         print(f"{Cin:4d} {Cout:4d} {HW:4d} {K} | {t_st:7.3f} | {t_cv:7.3f} ({fl / t_cv / 1e9:6.1f}) | {t_fp:7.3f} ({fl / t_fp / 1e9:6.1f}) | "
-              f"{t_fp / t_cv:5.2f}x  err {err:.1e} | wgrad {t_wg:7.3f} ms ({fl / t_wg / 1e9:6.1f} TF/s) | conv+stats {t_cs:7.3f} ms")
+              f"{t_fp / t_cv:5.2f}x  err {err:.1e} | wgrad {t_wg:7.3f} ms ({fl / t_wg / 1e9:6.1f} TF/s) | conv+stats {t_cs:7.3f} ms | rows(stage+conv+stats+store) {t_rr:7.3f} ms, no store/stats {t_rr0:7.3f} ms")
         del x, xs, y, y2, gy, gys
 
 
