@@ -351,7 +351,13 @@ def test_graphed_update_matches_eager():
     # the capture itself does not execute: steps 2 and 3 are the replays
     l2 = gs(*batches[1]).item()
     l3 = gs(*batches[2]).item()
-    assert abs(l2 - losses[1]) < 1e-4 * abs(losses[1]) and abs(l3 - losses[2]) < 1e-4 * abs(losses[2]), (l2, l3, losses)
+    # step 2 sees the weights after ONE update from identical states: tight.  Step 3 sees them after a second Adam update: Adam's
+    # first steps are sign-like (every weight moves by ~lr whatever the size of its gradient), so a parameter whose gradient is at
+    # the noise level of the atomic summation order (weight-gradient / bias-gradient atomicAdd) may step the other way - two
+    # EAGER runs from the same state already differ by ~1e-4 relative in the step-3 loss (measured 6e-5 .. 5e-4 over this
+    # round's GPU calls).  The bound on the weights themselves follows below.
+    assert abs(l2 - losses[1]) < 1e-5 * abs(losses[1]), (l2, losses)
+    assert abs(l3 - losses[2]) < 1e-3 * abs(losses[2]), (l3, losses)
     got = dict(list(net2.net_T.state_dict().items()) + list(net2.net_R.state_dict().items()))
     # Adam's first steps move every weight by ~lr * sign(g): a parameter whose gradient is at noise level (atomic
     # summation order) may step the other way, so single tensors (zero-initialised biases) can differ by 2 * lr per
