@@ -173,6 +173,10 @@ int san_in_stats_from_sums(const double* sums, float* mean, float* m2, float* a,
  * statistics epilogue of san_tc_conv_stats.  Weights: san_tc_stage_weights_rows (fp16 pairs, fmt = 1) into
  * san_tc_rows_weight_elems elements; Cout / Cin of the _elems / _supported / conv calls are those of the LAUNCH. */
 int san_tc_conv_rows_supported(int H, int W, int Cin, int Cout, int K);
+/* host-only: geometry of the row-ring kernel; out[12] = KG, KS, Npad, Ncol (TMEM columns per tile), Wp, T (128-pixel tiles
+ * per row), RS (slots per row plane), pair (2: taps of the last K-step paired inside a filter row), NR (ring slots),
+ * row_bytes, w_bytes, smem_bytes */
+int san_tc_conv_rows_describe(int H, int W, int Cin, int Cout, int stats, int* out);
 long long san_tc_rows_weight_elems(int H, int W, int Cout, int Cin);
 int san_tc_stage_weights_rows(const float* w, void* ws, int H, int W, int Cout, int Cin, int dgrad, int fmt, void* stream);
 int san_tc_conv_rows(const float* x, const float* mu, const float* a, const float* b, float slope, const float* absmax,

@@ -1524,6 +1524,15 @@ int san_tc_conv_rows_supported(int H, int W, int Cin, int Cout, int K) {
   return rr_geometry(H, W, Cin, Cout, K, true, &g) ? 1 : 0;
 }
 
+// Host-only: the row-ring geometry.  out[0..11] = KG, KS, Npad, Ncol, Wp, T, RS, pair, NR, row_bytes, w_bytes, smem_bytes.
+int san_tc_conv_rows_describe(int H, int W, int Cin, int Cout, int stats, int* out) {
+  RrGeom g;
+  if (!out || !rr_geometry(H, W, Cin, Cout, 3, stats != 0, &g)) return SAN_ERR_UNSUPPORTED;
+  const int v[12] = {g.KG, g.KS, g.Npad, g.Ncol, g.Wp, g.T, g.RS, g.pair, g.NR, g.row_bytes, g.w_bytes, g.smem_bytes};
+  for (int i = 0; i < 12; ++i) out[i] = v[i];
+  return SAN_OK;
+}
+
 long long san_tc_rows_weight_elems(int H, int W, int Cout, int Cin) {
   RrGeom g;
   if (!rr_geometry(H, W, Cin, Cout, 3, false, &g)) return -1;

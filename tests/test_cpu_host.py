@@ -351,6 +351,121 @@ def test_tc_flattened_pixel_formulation_on_cpu(built, shape):
     assert rel_l2(out, ref) < 2e-5
 
 
+@pytest.mark.parametrize("shape", [(3, 18, 7, 36, 18), (2, 3, 5, 40, 18), (2, 16, 6, 33, 8), (1, 24, 4, 130, 32), (2, 18, 5, 320, 18)])
+@pytest.mark.parametrize("nctas", [1, 3])
+def test_tc_row_ring_formulation_on_cpu(built, shape, nctas):
+    """CPU model of conv_rows_kernel (csrc/conv_tc.cu: the conv that stages its own input) driven by the library's geometry
+    (san_tc_conv_rows_describe): contiguous unit ranges per CTA, the converted padded rows in a ring of NR shared-memory row
+    slots [hl][kg][RS][8], one-row units whose tap windows lie inside single ring rows, HLS accumulators, taps of the
+    half-empty last K-step paired INSIDE a filter row (pair = 2 weight layout) -- reproduces conv2d; the ring protocol
+    (a slot is refilled only after the unit that last read it, every row is freed exactly once, no unit waits for a row
+    whose slot depends on itself) and the resource bounds are checked on the way.  No GPU."""
+    import ctypes
+    import torch.nn.functional as F
+    from spatialalignmentnetwork_b200 import _lib
+    L = _lib.lib()
+    N, Cin, H, W, Cout = shape
+    out_g = (ctypes.c_int * 12)()
+    assert L.san_tc_conv_rows_describe(H, W, Cin, Cout, 1, ctypes.addressof(out_g)) == 0
+    KG, KS, Npad, Ncol, Wp, T, RS, pair, NR, row_bytes, w_bytes, smem = list(out_g)
+    assert KG == -(-Cin // 8) <= 3 and KS == (KG + 1) // 2 and pair == (2 if KG % 2 else 0)
+    assert Npad % 16 == 0 and Cout <= Npad <= 32 and Ncol == 2 * Npad and 2 * T * Ncol <= 512      # TMEM, double-buffered
+    assert Wp == W + 2 and 128 * T >= Wp and RS >= 128 * (T - 1) + 2 + 1 + 128                      # every window inside the plane
+    assert row_bytes == 2 * KG * RS * 16 and w_bytes == KS * 9 * 4 * Npad * 16
+    assert 4 <= NR <= 8 and smem <= 225 * 1024 and 256 + w_bytes + NR * row_bytes <= smem
+    assert Wp * KG <= 4 * 256                                                                    # converter items per group and row
+    torch.manual_seed(11)
+    x = torch.randn(N, Cin, H, W)
+    w = torch.randn(Cout, Cin, 3, 3) / (Cin * 9) ** 0.5
+    ref = F.conv2d(x.double(), w.double(), padding=1)
+
+    def split(t):
+        hi = t.to(torch.bfloat16).float()
+        return hi, (t - hi).to(torch.bfloat16).float()
+
+    # weight blocks as stage_weights_kernel writes them (hls = 1, pair as described): blocks[ks][blk] = (B_hi, B_lo) [Npad, 16]
+    wp_ = torch.zeros(Npad, 16 * KS, 9)
+    wp_[:Cout, :Cin] = w.reshape(Cout, Cin, 9)
+    whi, wlo = split(wp_)
+    blocks = []
+    for ks in range(KS):
+        row = []
+        if pair and ks == KS - 1:
+            for blk in range(6):
+                dy, odd = blk >> 1, blk & 1
+                t0 = dy * 3 + (2 if odd else 0)
+                z = torch.zeros(Npad, 8)
+                bh = torch.cat([whi[:, ks * 16:ks * 16 + 8, t0], z if odd else whi[:, ks * 16:ks * 16 + 8, dy * 3 + 1]], 1)
+                bl = torch.cat([wlo[:, ks * 16:ks * 16 + 8, t0], z if odd else wlo[:, ks * 16:ks * 16 + 8, dy * 3 + 1]], 1)
+                row.append((bh.double(), bl.double(), dy, 2 if odd else 0, 0 if odd else 1))     # (.., dy, dx of K group 0, LBO in slots)
+            assert float(whi[:, ks * 16 + 8:ks * 16 + 16].abs().max()) == 0                      # the unstaged padding group
+        else:
+            for tap in range(9):
+                row.append((whi[:, ks * 16:ks * 16 + 16, tap].double(), wlo[:, ks * 16:ks * 16 + 16, tap].double(), tap // 3, tap % 3, None))
+        blocks.append(row)
+
+    def convert(n, pr):          # one padded row as the converters write it: [hl][kg][RS][8], zeros outside the image / past Wp
+        rowt = torch.zeros(2, KG, RS, 8)
+        if 1 <= pr <= H:
+            v = torch.zeros(KG * 8, Wp)
+            v[:Cin, 1:W + 1] = x[n, :, pr - 1]
+            hi, lo = split(v)
+            rowt[0, :, :Wp] = hi.reshape(KG, 8, Wp).permute(0, 2, 1)
+            rowt[1, :, :Wp] = lo.reshape(KG, 8, Wp).permute(0, 2, 1)
+        return rowt
+
+    out = torch.zeros(N, Cout, H, W, dtype=torch.float64)
+    nunits = N * H
+    for cta in range(nctas):
+        u0, u1 = cta * nunits // nctas, (cta + 1) * nunits // nctas
+        ring = [None] * NR                  # ring[s] = (row counter, tensor)
+        freed = set()
+        k_next = 0
+        for u in range(u0, u1):
+            n, yy = divmod(u, H)
+            fresh = u == u0 or yy == 0
+            base = k_next if fresh else k_next - 2
+            for r in (range(3) if fresh else range(2, 3)):       # converters: new rows of this unit, in counter order
+                k = k_next
+                s_ = k % NR
+                if ring[s_] is not None:
+                    assert ring[s_][0] == k - NR and ring[s_][0] in freed, "slot refilled before its row was released"
+                ring[s_] = (k, convert(n, yy + r))
+                k_next += 1
+            rows = []
+            for dy in range(3):
+                kk_, t_ = ring[(base + dy) % NR]
+                assert kk_ == base + dy                           # the MMA warp finds the unit's rows where it expects them
+                rows.append(t_)
+            for t in range(T):
+                acc2 = torch.zeros(128, 2 * Npad, dtype=torch.float64)
+                for ks in range(KS):
+                    for (bh, bl, dy, dx, lbo) in blocks[ks]:
+                        s0 = t * 128 + dx
+                        if lbo is None:                           # K group 1 = the next channel-group plane
+                            kg0 = 2 * ks
+                            a = [torch.cat([rows[dy][hl, kg0, s0:s0 + 128], rows[dy][hl, kg0 + 1, s0:s0 + 128]], 1).double()
+                                 for hl in (0, 1)]
+                        else:                                     # K group 1 = the same plane, lbo slots further (0: against zero weights)
+                            assert s0 + lbo + 128 <= RS
+                            a = [torch.cat([rows[dy][hl, KG - 1, s0:s0 + 128], rows[dy][hl, KG - 1, s0 + lbo:s0 + lbo + 128]], 1).double()
+                                 for hl in (0, 1)]
+                        acc2 += a[0] @ torch.cat([bh, bl], 0).T
+                        acc2[:, :Npad] += a[1] @ bh.T
+                acc = acc2[:, :Npad] + acc2[:, Npad:]
+                for lane in range(128):
+                    xx = t * 128 + lane
+                    if xx < W:
+                        out[n, :, yy, xx] = acc[lane, :Cout]
+            # rows no later unit reads
+            next_fresh = u + 1 == u1 or (u + 1) % H == 0
+            for kf in ([base, base + 1, base + 2] if next_fresh else [base]):
+                assert kf not in freed
+                freed.add(kf)
+        assert freed == set(range(k_next))                        # every converted row was released exactly once
+    assert rel_l2(out, ref) < 2e-5
+
+
 @pytest.mark.parametrize("shape", [(2, 3, 12, 20, 5, 3), (1, 18, 16, 24, 18, 3), (1, 20, 9, 33, 40, 1), (1, 7, 10, 18, 170, 3),
                                    (1, 192, 6, 16, 24, 3), (1, 2048, 3, 16, 16, 1)])
 def test_tc_wgrad_formulation_on_cpu(built, shape):
